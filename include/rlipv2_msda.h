@@ -1,0 +1,93 @@
+/*
+ * rlipv2_msda.h - C ABI of the B200-native multi-scale deformable attention op.
+ *
+ * This is the drop-in boundary for the one native component of RLIPv2: the python
+ * extension module `MultiScaleDeformableAttention` that the reference binds with pybind11 in
+ *   /root/reference/models/ops/src/vision.cpp:13-16           (module definition)
+ *   /root/reference/models/ops/src/ms_deform_attn.h:20-61     (device dispatch)
+ *   /root/reference/models/ops/src/cuda/ms_deform_attn_cuda.cu:20-80   (forward host wrapper)
+ *   /root/reference/models/ops/src/cuda/ms_deform_attn_cuda.cu:83-153  (backward host wrapper)
+ * and calls from models/ops/functions/ms_deform_attn_func.py:27-44.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to a dense, C-contiguous array (the reference asserts
+ *     contiguity, ms_deform_attn_cuda.cu:28-38); `stream` is a cudaStream_t passed as void*
+ *     (NULL = legacy default stream).  Calls are asynchronous: no host synchronisation.
+ *   - tensor layouts are the reference's:
+ *        value            [batch, spatial_size, num_heads, channels]
+ *        spatial_shapes   [num_levels, 2]  int64 (H_l, W_l), read on the device
+ *        level_start_idx  [num_levels]     int64, read on the device
+ *        sampling_loc     [batch, num_query, num_heads, num_levels, num_point, 2]  (x=w, y=h) in [0,1]
+ *        attn_weight      [batch, num_query, num_heads, num_levels, num_point]
+ *        out / grad_out   [batch, num_query, num_heads*channels]
+ *   - return value: 0 on success; a positive value is a cudaError_t from the launch (the
+ *     reference only printf()s launch errors, ms_deform_im2col_cuda.cuh:948-952 - here they are
+ *     returned); a negative value is one of RLIPV2_MSDA_E*.
+ *   - re-entrant, no global mutable state; the im2col_step batching loop of the reference
+ *     (ms_deform_attn_cuda.cu:50-75) is not needed: one launch covers the whole batch, so the
+ *     python binding only validates `batch % min(batch, im2col_step) == 0` for error parity.
+ *
+ * There is deliberately NO CPU implementation behind this ABI (the reference has none either:
+ * cpu/ms_deform_attn_cpu.cpp:17-41 raises).
+ */
+#ifndef RLIPV2_MSDA_H_
+#define RLIPV2_MSDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLIPV2_MSDA_ABI_VERSION 1
+
+#define RLIPV2_MSDA_EINVAL   (-1) /* negative / zero dimension where not allowed, null pointer */
+#define RLIPV2_MSDA_ETOOBIG  (-2) /* an index would overflow the 64-bit-safe limits we support  */
+
+/* ms_deform_attn_cuda_forward (ms_deform_attn_cuda.cu:20-80), scalar_t = float.
+ * Writes every element of `out` (no pre-zeroing needed). */
+int rlipv2_msda_forward_f32(const float *value, const int64_t *spatial_shapes,
+                            const int64_t *level_start_index, const float *sampling_loc,
+                            const float *attn_weight, int batch, int spatial_size, int num_heads,
+                            int channels, int num_levels, int num_query, int num_point,
+                            float *out, void *stream);
+
+/* same, scalar_t = double (AT_DISPATCH_FLOATING_TYPES, ms_deform_attn_cuda.cu:64) */
+int rlipv2_msda_forward_f64(const double *value, const int64_t *spatial_shapes,
+                            const int64_t *level_start_index, const double *sampling_loc,
+                            const double *attn_weight, int batch, int spatial_size, int num_heads,
+                            int channels, int num_levels, int num_query, int num_point,
+                            double *out, void *stream);
+
+/* ms_deform_attn_cuda_backward (ms_deform_attn_cuda.cu:83-153), scalar_t = float.
+ * All three gradient arrays are fully overwritten: grad_value is zero-filled on `stream` and then
+ * accumulated into (fp32 reductions, order not deterministic - same as the reference's atomicAdd,
+ * ms_deform_im2col_cuda.cuh:125-152); grad_sampling_loc and grad_attn_weight are written once. */
+int rlipv2_msda_backward_f32(const float *value, const int64_t *spatial_shapes,
+                             const int64_t *level_start_index, const float *sampling_loc,
+                             const float *attn_weight, const float *grad_out, int batch,
+                             int spatial_size, int num_heads, int channels, int num_levels,
+                             int num_query, int num_point, float *grad_value,
+                             float *grad_sampling_loc, float *grad_attn_weight, void *stream);
+
+int rlipv2_msda_backward_f64(const double *value, const int64_t *spatial_shapes,
+                             const int64_t *level_start_index, const double *sampling_loc,
+                             const double *attn_weight, const double *grad_out, int batch,
+                             int spatial_size, int num_heads, int channels, int num_levels,
+                             int num_query, int num_point, double *grad_value,
+                             double *grad_sampling_loc, double *grad_attn_weight, void *stream);
+
+/* Human-readable text for a return code of the functions above (static storage). */
+const char *rlipv2_msda_error_string(int code);
+
+/* RLIPV2_MSDA_ABI_VERSION the library was built with. */
+int rlipv2_msda_abi_version(void);
+
+/* Number of kernels launched by this library in this process since load (for bench.py's
+ * `gpu_launches`; relaxed atomic counter, never reset). */
+unsigned long long rlipv2_msda_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLIPV2_MSDA_H_ */

@@ -1,0 +1,85 @@
+"""ctypes binding of the C ABI declared in include/rlipv2_msda.h.
+
+PyTorch is used only for device memory and the current CUDA stream; every tensor crosses the
+boundary as a raw device pointer.  There is no fallback: if the CUDA library has not been built
+(``python -m rlipv2_b200.build``) importing this module raises.
+"""
+import ctypes
+import os
+
+import torch
+
+from .build import lib_path
+
+_LIB_NAME = "librlipv2_msda.so"
+ABI_VERSION = 1
+
+_path = lib_path(_LIB_NAME)
+if not os.path.exists(_path):
+    raise ImportError(
+        f"{_path} is missing: the sm_100a CUDA library has not been built "
+        "(run `python -m rlipv2_b200.build` or `__graft_entry__.build()`); "
+        "rlipv2_b200 has no CPU or PyTorch fallback for MSDeformAttn.")
+_lib = ctypes.CDLL(_path)
+
+_i, _p = ctypes.c_int, ctypes.c_void_p
+_DIMS = [_i] * 7
+_lib.rlipv2_msda_forward_f32.argtypes = [_p] * 5 + _DIMS + [_p, _p]
+_lib.rlipv2_msda_forward_f64.argtypes = [_p] * 5 + _DIMS + [_p, _p]
+_lib.rlipv2_msda_backward_f32.argtypes = [_p] * 6 + _DIMS + [_p] * 4
+_lib.rlipv2_msda_backward_f64.argtypes = [_p] * 6 + _DIMS + [_p] * 4
+for _f in ("forward_f32", "forward_f64", "backward_f32", "backward_f64"):
+    getattr(_lib, "rlipv2_msda_" + _f).restype = _i
+_lib.rlipv2_msda_error_string.argtypes = [_i]
+_lib.rlipv2_msda_error_string.restype = ctypes.c_char_p
+_lib.rlipv2_msda_abi_version.restype = _i
+_lib.rlipv2_msda_launch_count.restype = ctypes.c_ulonglong
+
+if _lib.rlipv2_msda_abi_version() != ABI_VERSION:
+    raise ImportError(f"{_path}: ABI version {_lib.rlipv2_msda_abi_version()} != {ABI_VERSION}; rebuild")
+
+EXPORTS = ("rlipv2_msda_forward_f32", "rlipv2_msda_forward_f64", "rlipv2_msda_backward_f32",
+           "rlipv2_msda_backward_f64", "rlipv2_msda_error_string", "rlipv2_msda_abi_version",
+           "rlipv2_msda_launch_count")
+
+
+def library_path():
+    return _path
+
+
+def launch_count():
+    return int(_lib.rlipv2_msda_launch_count())
+
+
+def _check(code, what):
+    if code != 0:
+        raise RuntimeError(f"{what}: {_lib.rlipv2_msda_error_string(code).decode()} (code {code})")
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, out):
+    """Raw call: all tensors CUDA, contiguous, same floating dtype; `out` preallocated."""
+    N, S, M, D = value.shape
+    Lq, L, P = sampling_loc.shape[1], sampling_loc.shape[3], sampling_loc.shape[4]
+    fn = _lib.rlipv2_msda_forward_f32 if value.dtype == torch.float32 else _lib.rlipv2_msda_forward_f64
+    with torch.cuda.device(value.device):
+        code = fn(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                  sampling_loc.data_ptr(), attn_weight.data_ptr(), N, S, M, D, L, Lq, P,
+                  out.data_ptr(), _stream())
+    _check(code, "ms_deform_attn_forward")
+
+
+def backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+             grad_value, grad_sampling_loc, grad_attn_weight):
+    N, S, M, D = value.shape
+    Lq, L, P = sampling_loc.shape[1], sampling_loc.shape[3], sampling_loc.shape[4]
+    fn = _lib.rlipv2_msda_backward_f32 if value.dtype == torch.float32 else _lib.rlipv2_msda_backward_f64
+    with torch.cuda.device(value.device):
+        code = fn(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                  sampling_loc.data_ptr(), attn_weight.data_ptr(), grad_output.data_ptr(),
+                  N, S, M, D, L, Lq, P, grad_value.data_ptr(), grad_sampling_loc.data_ptr(),
+                  grad_attn_weight.data_ptr(), _stream())
+    _check(code, "ms_deform_attn_backward")

@@ -40,6 +40,8 @@
 namespace {
 
 std::atomic<unsigned long long> g_launches{0};
+// tuning knobs (tools/msda_microbench.py --variants); not part of the public ABI
+int g_fwd_variant = 0, g_bwd_variant = 0;
 
 constexpr int kFastD = 32;
 constexpr int kFastL = 4;
@@ -48,8 +50,6 @@ constexpr int kFastLP = kFastL * kFastP;           // 16 points per pair
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kQueriesPerCta = 32;                  // 8 warps x 4 lane-groups
-// per warp: 4 pairs x 16 points x (int4 + float4)
-constexpr int kPrepBytesPerWarp = 4 * kFastLP * 32;
 
 __device__ __forceinline__ float4 ldg_f4(const float *p) {
     return __ldg(reinterpret_cast<const float4 *>(p));
@@ -60,208 +60,198 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
                  :: "l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// One sampling point, prepared by one lane.
-struct PointGeom {
-    uint32_t o1, o2, o3, o4;   // element offsets of the 4 corners (clamped into the map)
-    float lh, lw;              // fractional parts
-    unsigned mask;             // bit k set <=> corner k+1 is inside the map
-    bool inside;               // reference's cuh:288 test
-};
+// Per-level table staged in shared memory by every CTA (the reference re-reads the int64 device
+// tensors for every output element, cuh:274-277).
+struct LevelRow { int H, W; uint32_t start; uint32_t row_stride; };   // row_stride = W*M*D
 
-// Geometry of one sampling point.  Mirrors cuh:285-288 (h_im/w_im and the range test) and
-// cuh:40-78 (floor, fractional weights, per-corner guards).  `cell0` = element offset of
-// value[n, level_start, m, 0]; `MD` = num_heads*channels.
-__device__ __forceinline__ PointGeom point_geom(float loc_w, float loc_h, int H, int W,
-                                                uint32_t cell0, uint32_t MD) {
-    PointGeom g;
+// One sampling point as the consumer lanes see it: 4 words = one LDS.128.
+//   word 0: element offset of the clamped low corner (a multiple of 32) | validity bits
+//           bit0 = row h_low inside, bit1 = row h_low+1 inside, bit2 = col w_low inside,
+//           bit3 = col w_low+1 inside (all 0 when the reference's cuh:288 test fails)
+//   word 1: lh, word 2: lw (fractional parts), word 3: attention weight
+// Corner k offsets follow from the bits: the column step is M*D iff both columns are inside
+// (otherwise the two columns coincide after clamping), same for the row step.
+__device__ __forceinline__ uint4 pack_point(float loc_w, float loc_h, float a, int H, int W,
+                                            uint32_t cell0, uint32_t MD) {
+    // cuh:285-288
     const float h_im = loc_h * (float)H - 0.5f;
     const float w_im = loc_w * (float)W - 0.5f;
-    g.inside = (h_im > -1.f) && (w_im > -1.f) && (h_im < (float)H) && (w_im < (float)W);
+    const bool inside = (h_im > -1.f) && (w_im > -1.f) && (h_im < (float)H) && (w_im < (float)W);
+    // cuh:40-46
     const float hf = floorf(h_im), wf = floorf(w_im);
-    int h_low = (int)hf, w_low = (int)wf;
-    g.lh = h_im - hf;
-    g.lw = w_im - wf;
-    if (!g.inside) { h_low = 0; w_low = 0; g.lh = 0.f; g.lw = 0.f; }
-    const bool h0 = h_low >= 0, h1 = h_low + 1 <= H - 1;
-    const bool w0 = w_low >= 0, w1 = w_low + 1 <= W - 1;
-    g.mask = g.inside ? ((h0 && w0) ? 1u : 0u) | ((h0 && w1) ? 2u : 0u) |
-                        ((h1 && w0) ? 4u : 0u) | ((h1 && w1) ? 8u : 0u) : 0u;
-    const int hl = max(h_low, 0), hh = min(h_low + 1, H - 1);
-    const int wl = max(w_low, 0), wh = min(w_low + 1, W - 1);
-    const uint32_t r0 = (uint32_t)(hl * W), r1 = (uint32_t)(hh * W);
-    g.o1 = cell0 + (r0 + (uint32_t)wl) * MD;
-    g.o2 = cell0 + (r0 + (uint32_t)wh) * MD;
-    g.o3 = cell0 + (r1 + (uint32_t)wl) * MD;
-    g.o4 = cell0 + (r1 + (uint32_t)wh) * MD;
-    return g;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Fast forward: fp32, D=32, L=4, P=4.
-// grid.x = ceil(NQ / 32) where NQ = batch*num_query (queries flattened over the batch).
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-msda_fwd_d32_l4p4(const float *__restrict__ value, const int64_t *__restrict__ shapes,
-                  const int64_t *__restrict__ lsi, const float *__restrict__ loc,
-                  const float *__restrict__ attn, int NQ, int Lq, int S, int M,
-                  float *__restrict__ out)
-{
-    __shared__ __align__(16) unsigned char prep_smem[kWarpsPerCta * kPrepBytesPerWarp];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int grp = lane >> 3, sub = lane & 7;
-    int4 *p_off = reinterpret_cast<int4 *>(prep_smem + warp * kPrepBytesPerWarp);
-    float4 *p_wt = reinterpret_cast<float4 *>(p_off + 4 * kFastLP);
-
-    // this lane prepares points 2*sub, 2*sub+1 -> both on level sub/2
-    const int lvl = sub >> 1;
-    const int H = (int)shapes[2 * lvl], W = (int)shapes[2 * lvl + 1];
-    const uint32_t lstart = (uint32_t)lsi[lvl];
-    const uint32_t MD = (uint32_t)M * kFastD;
-
-    const int Q = blockIdx.x * kQueriesPerCta + warp * 4 + grp;   // flattened (n,q)
-    const bool live = Q < NQ;
-    const int n = live ? Q / Lq : 0;
-
-    for (int m = 0; m < M; ++m) {
-        const size_t pair = (size_t)(live ? Q : 0) * M + m;
-        // ---- phase 1: geometry + weights of 2 points per lane -> shared memory
-        float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float2 a2 = make_float2(0.f, 0.f);
-        if (live) {
-            l4 = ldg_f4(loc + pair * (kFastLP * 2) + sub * 4);
-            a2 = __ldg(reinterpret_cast<const float2 *>(attn + pair * kFastLP + sub * 2));
-        }
-        const uint32_t cell0 = ((uint32_t)n * (uint32_t)S + lstart) * MD + (uint32_t)m * kFastD;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const float lw_ = k ? l4.z : l4.x, lh_ = k ? l4.w : l4.y;
-            const float a = k ? a2.y : a2.x;
-            const PointGeom g = point_geom(lw_, lh_, H, W, cell0, MD);
-            const float hh = 1.f - g.lh, hw = 1.f - g.lw;
-            float4 wt;
-            wt.x = (g.mask & 1u) ? hh * hw * a : 0.f;
-            wt.y = (g.mask & 2u) ? hh * g.lw * a : 0.f;
-            wt.z = (g.mask & 4u) ? g.lh * hw * a : 0.f;
-            wt.w = (g.mask & 8u) ? g.lh * g.lw * a : 0.f;
-            const int slot = grp * kFastLP + sub * 2 + k;
-            p_off[slot] = make_int4((int)g.o1, (int)g.o2, (int)g.o3, (int)g.o4);
-            p_wt[slot] = wt;
-        }
-        __syncwarp();
-        // ---- phase 2: gather.  lane owns channels sub*4 .. sub*4+3 of its group's pair
-        const float *vbase = value + sub * 4;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-        for (int p = 0; p < kFastLP; ++p) {
-            const int4 o = p_off[grp * kFastLP + p];
-            const float4 w = p_wt[grp * kFastLP + p];
-            const float4 v1 = ldg_f4(vbase + (uint32_t)o.x);
-            const float4 v2 = ldg_f4(vbase + (uint32_t)o.y);
-            const float4 v3 = ldg_f4(vbase + (uint32_t)o.z);
-            const float4 v4 = ldg_f4(vbase + (uint32_t)o.w);
-            acc.x = fmaf(w.x, v1.x, acc.x); acc.y = fmaf(w.x, v1.y, acc.y);
-            acc.z = fmaf(w.x, v1.z, acc.z); acc.w = fmaf(w.x, v1.w, acc.w);
-            acc.x = fmaf(w.y, v2.x, acc.x); acc.y = fmaf(w.y, v2.y, acc.y);
-            acc.z = fmaf(w.y, v2.z, acc.z); acc.w = fmaf(w.y, v2.w, acc.w);
-            acc.x = fmaf(w.z, v3.x, acc.x); acc.y = fmaf(w.z, v3.y, acc.y);
-            acc.z = fmaf(w.z, v3.z, acc.z); acc.w = fmaf(w.z, v3.w, acc.w);
-            acc.x = fmaf(w.w, v4.x, acc.x); acc.y = fmaf(w.w, v4.y, acc.y);
-            acc.z = fmaf(w.w, v4.z, acc.z); acc.w = fmaf(w.w, v4.w, acc.w);
-        }
-        if (live)
-            *reinterpret_cast<float4 *>(out + pair * kFastD + sub * 4) = acc;
-        __syncwarp();   // phase-1 of the next head overwrites the staging area
+    const int h_low = inside ? (int)hf : 0, w_low = inside ? (int)wf : 0;
+    const float lh = inside ? h_im - hf : 0.f, lw = inside ? w_im - wf : 0.f;
+    // cuh:56-78 corner guards
+    unsigned bits = 0;
+    if (inside) {
+        bits = (h_low >= 0 ? 1u : 0u) | (h_low + 1 <= H - 1 ? 2u : 0u) |
+               (w_low >= 0 ? 4u : 0u) | (w_low + 1 <= W - 1 ? 8u : 0u);
     }
+    const int hl = max(h_low, 0), wl = max(w_low, 0);
+    const uint32_t base = cell0 + (uint32_t)(hl * W + wl) * MD;
+    return make_uint4(base | bits, __float_as_uint(lh), __float_as_uint(lw), __float_as_uint(a));
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fast backward: fp32, D=32, L=4, P=4.  Same ownership as the forward kernel.
+// Fast path: fp32, D=32, L=4, P=4.
+//
+// Two schedules share one per-warp body:
+//  * "linear": CTA b walks queries [32b, 32b+32) of the flattened (batch, query) axis; heads may
+//    be sliced over grid.y when the query axis alone cannot fill 148 SMs (decoder-shaped calls).
+//  * "tiled" (Lq == S, i.e. the encoder's self-attention where query i sits on cell i): a
+//    persistent grid of CTAs loops over TH x TW tiles of cells of one level, so that the queries a
+//    CTA works on are 2-D neighbours and their sampling footprints overlap in L1.  Only the order
+//    in which queries are visited changes; any sampling pattern is still computed correctly.
 // ---------------------------------------------------------------------------------------------
-// reduce-scatter of x[0..15] over the 8 lanes of a group: on return lane `sub` holds the group
-// sums of x[2*sub] and x[2*sub+1] in r0, r1.
-__device__ __forceinline__ void group_reduce_scatter16(const float (&x)[kFastLP], int sub,
-                                                       float &r0, float &r1) {
-    float y[8], z[4];
+struct WarpCtx {
+    int grp, sub;             // lane group (pair slot) and lane within the group
+    uint32_t MD;              // M * 32
+    uint32_t rs0, rs1, rs2, rs3;   // per-level row stride in elements
+};
+
+__device__ __forceinline__ void load_level_table(LevelRow *lvl_tab, const int64_t *shapes,
+                                                 const int64_t *lsi, uint32_t MD) {
+    if (threadIdx.x < kFastL) {
+        LevelRow r;
+        r.H = (int)shapes[2 * threadIdx.x];
+        r.W = (int)shapes[2 * threadIdx.x + 1];
+        r.start = (uint32_t)lsi[threadIdx.x];
+        r.row_stride = (uint32_t)r.W * MD;
+        lvl_tab[threadIdx.x] = r;
+    }
+    __syncthreads();
+}
+
+// forward for the 4 pairs (same head m, queries Q of the 4 lane groups) owned by this warp
+template <int UNROLL>
+__device__ __forceinline__ void fwd_warp_pairs(const float *__restrict__ value,
+                                               const float *__restrict__ loc,
+                                               const float *__restrict__ attn,
+                                               float *__restrict__ out, const WarpCtx &c,
+                                               const LevelRow &my, uint4 *mine, int Q, bool live,
+                                               int n, int S, int M, int m)
+{
+    const size_t pair = (size_t)(live ? Q : 0) * M + m;
+    // ---- phase 1: this lane prepares points 2*sub, 2*sub+1 (both on level sub/2)
+    float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 a2 = make_float2(0.f, 0.f);
+    if (live) {
+        l4 = ldg_f4(loc + pair * (kFastLP * 2) + c.sub * 4);
+        a2 = __ldg(reinterpret_cast<const float2 *>(attn + pair * kFastLP + c.sub * 2));
+    }
+    const uint32_t cell0 = ((uint32_t)n * (uint32_t)S + my.start) * c.MD + (uint32_t)m * kFastD;
+    mine[c.grp * kFastLP + c.sub * 2 + 0] = pack_point(l4.x, l4.y, a2.x, my.H, my.W, cell0, c.MD);
+    mine[c.grp * kFastLP + c.sub * 2 + 1] = pack_point(l4.z, l4.w, a2.y, my.H, my.W, cell0, c.MD);
+    __syncwarp();
+    // ---- phase 2: gather; lane owns channels sub*4 .. sub*4+3 of its group's pair
+    const float *vbase = value + c.sub * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll UNROLL
+    for (int p = 0; p < kFastLP; ++p) {
+        const uint4 pt = mine[c.grp * kFastLP + p];
+        const uint32_t rs = (p < 4) ? c.rs0 : (p < 8) ? c.rs1 : (p < 12) ? c.rs2 : c.rs3;
+        const uint32_t bits = pt.x & 15u, base = pt.x & ~31u;
+        const uint32_t dx = ((bits & 12u) == 12u) ? c.MD : 0u;
+        const uint32_t dy = ((bits & 3u) == 3u) ? rs : 0u;
+        const float4 v1 = ldg_f4(vbase + base);
+        const float4 v2 = ldg_f4(vbase + base + dx);
+        const float4 v3 = ldg_f4(vbase + base + dy);
+        const float4 v4 = ldg_f4(vbase + base + dy + dx);
+        const float lh = __uint_as_float(pt.y), lw = __uint_as_float(pt.z);
+        const float a = __uint_as_float(pt.w);
+        // row weights x attention (zero for rows outside), column weights (zero outside)
+        const float ha = (bits & 1u) ? (1.f - lh) * a : 0.f;
+        const float la = (bits & 2u) ? lh * a : 0.f;
+        const float hw = (bits & 4u) ? 1.f - lw : 0.f;
+        const float lwv = (bits & 8u) ? lw : 0.f;
+        const float w1 = ha * hw, w2 = ha * lwv, w3 = la * hw, w4 = la * lwv;
+        acc.x = fmaf(w1, v1.x, acc.x); acc.y = fmaf(w1, v1.y, acc.y);
+        acc.z = fmaf(w1, v1.z, acc.z); acc.w = fmaf(w1, v1.w, acc.w);
+        acc.x = fmaf(w2, v2.x, acc.x); acc.y = fmaf(w2, v2.y, acc.y);
+        acc.z = fmaf(w2, v2.z, acc.z); acc.w = fmaf(w2, v2.w, acc.w);
+        acc.x = fmaf(w3, v3.x, acc.x); acc.y = fmaf(w3, v3.y, acc.y);
+        acc.z = fmaf(w3, v3.z, acc.z); acc.w = fmaf(w3, v3.w, acc.w);
+        acc.x = fmaf(w4, v4.x, acc.x); acc.y = fmaf(w4, v4.y, acc.y);
+        acc.z = fmaf(w4, v4.z, acc.z); acc.w = fmaf(w4, v4.w, acc.w);
+    }
+    if (live)
+        *reinterpret_cast<float4 *>(out + pair * kFastD + c.sub * 4) = acc;
+    __syncwarp();   // the next call overwrites the staging area
+}
+
+// reduce-scatter of x[0..7] over the 8 lanes of a group: lane `sub` returns the group sum of x[sub].
+__device__ __forceinline__ float group_reduce_scatter8(const float (&x)[8], int sub) {
+    float y[4], z[2];
     const bool b2 = sub & 4, b1 = sub & 2, b0 = sub & 1;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float keep = b2 ? x[j + 8] : x[j];
-        const float send = b2 ? x[j] : x[j + 8];
+    for (int j = 0; j < 4; ++j) {
+        const float keep = b2 ? x[j + 4] : x[j];
+        const float send = b2 ? x[j] : x[j + 4];
         y[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float keep = b1 ? y[j + 4] : y[j];
-        const float send = b1 ? y[j] : y[j + 4];
+    for (int j = 0; j < 2; ++j) {
+        const float keep = b1 ? y[j + 2] : y[j];
+        const float send = b1 ? y[j] : y[j + 2];
         z[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
     }
-    {
-        const float keep0 = b0 ? z[2] : z[0], send0 = b0 ? z[0] : z[2];
-        const float keep1 = b0 ? z[3] : z[1], send1 = b0 ? z[1] : z[3];
-        r0 = keep0 + __shfl_xor_sync(0xffffffffu, send0, 1);
-        r1 = keep1 + __shfl_xor_sync(0xffffffffu, send1, 1);
-    }
+    const float keep = b0 ? z[1] : z[0], send = b0 ? z[0] : z[1];
+    return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 
-__global__ void __launch_bounds__(kThreads)
-msda_bwd_d32_l4p4(const float *__restrict__ value, const int64_t *__restrict__ shapes,
-                  const int64_t *__restrict__ lsi, const float *__restrict__ loc,
-                  const float *__restrict__ attn, const float *__restrict__ grad_out,
-                  int NQ, int Lq, int S, int M, float *__restrict__ grad_value,
-                  float *__restrict__ grad_loc, float *__restrict__ grad_attn)
+// backward for the 4 pairs owned by this warp.  The 16 points are walked in two halves of 8 so
+// that the per-point partials (3 x 8 registers) stay small; scaleW/scaleH = (W, H) of the level
+// of point `sub` in each half (cuh:156-158).
+__device__ __forceinline__ void bwd_warp_pairs(const float *__restrict__ value,
+                                               const float *__restrict__ loc,
+                                               const float *__restrict__ attn,
+                                               const float *__restrict__ grad_out,
+                                               float *__restrict__ grad_value,
+                                               float *__restrict__ grad_loc,
+                                               float *__restrict__ grad_attn, const WarpCtx &c,
+                                               const LevelRow &my, const float (&scaleW)[2],
+                                               const float (&scaleH)[2], uint4 *mine, int Q,
+                                               bool live, int n, int S, int M, int m)
 {
-    __shared__ __align__(16) unsigned char prep_smem[kWarpsPerCta * kPrepBytesPerWarp];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int grp = lane >> 3, sub = lane & 7;
-    int4 *p_off = reinterpret_cast<int4 *>(prep_smem + warp * kPrepBytesPerWarp);
-    float4 *p_geo = reinterpret_cast<float4 *>(p_off + 4 * kFastLP);   // (lh, lw, attn, mask)
+    const size_t pair = (size_t)(live ? Q : 0) * M + m;
+    float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 a2 = make_float2(0.f, 0.f);
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+        l4 = ldg_f4(loc + pair * (kFastLP * 2) + c.sub * 4);
+        a2 = __ldg(reinterpret_cast<const float2 *>(attn + pair * kFastLP + c.sub * 2));
+        g4 = ldg_f4(grad_out + pair * kFastD + c.sub * 4);
+    }
+    const uint32_t cell0 = ((uint32_t)n * (uint32_t)S + my.start) * c.MD + (uint32_t)m * kFastD;
+    uint4 p0 = pack_point(l4.x, l4.y, a2.x, my.H, my.W, cell0, c.MD);
+    uint4 p1 = pack_point(l4.z, l4.w, a2.y, my.H, my.W, cell0, c.MD);
+    if (!live) { p0.x &= ~15u; p1.x &= ~15u; }       // dead group: no loads, no reductions
+    mine[c.grp * kFastLP + c.sub * 2 + 0] = p0;
+    mine[c.grp * kFastLP + c.sub * 2 + 1] = p1;
+    __syncwarp();
 
-    const int lvl = sub >> 1;
-    const int H = (int)shapes[2 * lvl], W = (int)shapes[2 * lvl + 1];
-    const uint32_t lstart = (uint32_t)lsi[lvl];
-    const uint32_t MD = (uint32_t)M * kFastD;
-
-    const int Q = blockIdx.x * kQueriesPerCta + warp * 4 + grp;
-    const bool live = Q < NQ;
-    const int n = live ? Q / Lq : 0;
-
-    for (int m = 0; m < M; ++m) {
-        const size_t pair = (size_t)(live ? Q : 0) * M + m;
-        float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float2 a2 = make_float2(0.f, 0.f);
-        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live) {
-            l4 = ldg_f4(loc + pair * (kFastLP * 2) + sub * 4);
-            a2 = __ldg(reinterpret_cast<const float2 *>(attn + pair * kFastLP + sub * 2));
-            g4 = ldg_f4(grad_out + pair * kFastD + sub * 4);
-        }
-        const uint32_t cell0 = ((uint32_t)n * (uint32_t)S + lstart) * MD + (uint32_t)m * kFastD;
+    const float *vbase = value + c.sub * 4;
+    float *gbase = grad_value + c.sub * 4;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        float pa[8], pw[8], ph[8];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const float lw_ = k ? l4.z : l4.x, lh_ = k ? l4.w : l4.y;
-            const float a = k ? a2.y : a2.x;
-            const PointGeom g = point_geom(lw_, lh_, H, W, cell0, MD);
-            const int slot = grp * kFastLP + sub * 2 + k;
-            p_off[slot] = make_int4((int)g.o1, (int)g.o2, (int)g.o3, (int)g.o4);
-            p_geo[slot] = make_float4(g.lh, g.lw, live ? a : 0.f, __uint_as_float(live ? g.mask : 0u));
-        }
-        __syncwarp();
-
-        const float *vbase = value + sub * 4;
-        float *gbase = grad_value + sub * 4;
-        float pa[kFastLP], pw[kFastLP], ph[kFastLP];
-#pragma unroll
-        for (int p = 0; p < kFastLP; ++p) {
-            const int4 o = p_off[grp * kFastLP + p];
-            const float4 ge = p_geo[grp * kFastLP + p];
-            const unsigned mask = __float_as_uint(ge.w);
-            const float lh = ge.x, lw = ge.y, a = ge.z;
-            const float hh = 1.f - lh, hw = 1.f - lw;
+        for (int j = 0; j < 8; ++j) {
+            const uint4 pt = mine[c.grp * kFastLP + half * 8 + j];
+            const uint32_t rs = half ? ((j < 4) ? c.rs2 : c.rs3) : ((j < 4) ? c.rs0 : c.rs1);
+            const uint32_t bits = pt.x & 15u, base = pt.x & ~31u;
+            const uint32_t dx = ((bits & 12u) == 12u) ? c.MD : 0u;
+            const uint32_t dy = ((bits & 3u) == 3u) ? rs : 0u;
+            const bool c1 = (bits & 5u) == 5u, c2 = (bits & 9u) == 9u;
+            const bool c3 = (bits & 6u) == 6u, c4 = (bits & 10u) == 10u;
             const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 v1 = (mask & 1u) ? ldg_f4(vbase + (uint32_t)o.x) : zero;
-            const float4 v2 = (mask & 2u) ? ldg_f4(vbase + (uint32_t)o.y) : zero;
-            const float4 v3 = (mask & 4u) ? ldg_f4(vbase + (uint32_t)o.z) : zero;
-            const float4 v4 = (mask & 8u) ? ldg_f4(vbase + (uint32_t)o.w) : zero;
+            const float4 v1 = c1 ? ldg_f4(vbase + base) : zero;
+            const float4 v2 = c2 ? ldg_f4(vbase + base + dx) : zero;
+            const float4 v3 = c3 ? ldg_f4(vbase + base + dy) : zero;
+            const float4 v4 = c4 ? ldg_f4(vbase + base + dy + dx) : zero;
+            const float lh = __uint_as_float(pt.y), lw = __uint_as_float(pt.z);
+            const float a = __uint_as_float(pt.w);
+            const float hh = 1.f - lh, hw = 1.f - lw;
             // d_k = <v_k, grad_out> over this lane's 4 channels
             const float d1 = fmaf(v1.x, g4.x, fmaf(v1.y, g4.y, fmaf(v1.z, g4.z, v1.w * g4.w)));
             const float d2 = fmaf(v2.x, g4.x, fmaf(v2.y, g4.y, fmaf(v2.z, g4.z, v2.w * g4.w)));
@@ -269,28 +259,203 @@ msda_bwd_d32_l4p4(const float *__restrict__ value, const int64_t *__restrict__ s
             const float d4 = fmaf(v4.x, g4.x, fmaf(v4.y, g4.y, fmaf(v4.z, g4.z, v4.w * g4.w)));
             const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
             // cuh:155   grad_attn = top_grad * (w1 v1 + w2 v2 + w3 v3 + w4 v4)
-            pa[p] = fmaf(w1, d1, fmaf(w2, d2, fmaf(w3, d3, w4 * d4)));
-            // cuh:121-151 grad_w_weight = hh (v2 - v1) + lh (v4 - v3); grad_h_weight = hw (v3 - v1) + lw (v4 - v2)
-            pw[p] = a * fmaf(hh, d2 - d1, lh * (d4 - d3));
-            ph[p] = a * fmaf(hw, d3 - d1, lw * (d4 - d2));
+            pa[j] = fmaf(w1, d1, fmaf(w2, d2, fmaf(w3, d3, w4 * d4)));
+            // cuh:121-151 grad_w_weight = hh (v2 - v1) + lh (v4 - v3)
+            //             grad_h_weight = hw (v3 - v1) + lw (v4 - v2)
+            pw[j] = a * fmaf(hh, d2 - d1, lh * (d4 - d3));
+            ph[j] = a * fmaf(hw, d3 - d1, lw * (d4 - d2));
             // cuh:125,134,143,152  grad_value[corner] += w_k * top_grad * attn
             const float s1 = w1 * a, s2 = w2 * a, s3 = w3 * a, s4 = w4 * a;
-            if (mask & 1u) red_add_v4(gbase + (uint32_t)o.x, s1 * g4.x, s1 * g4.y, s1 * g4.z, s1 * g4.w);
-            if (mask & 2u) red_add_v4(gbase + (uint32_t)o.y, s2 * g4.x, s2 * g4.y, s2 * g4.z, s2 * g4.w);
-            if (mask & 4u) red_add_v4(gbase + (uint32_t)o.z, s3 * g4.x, s3 * g4.y, s3 * g4.z, s3 * g4.w);
-            if (mask & 8u) red_add_v4(gbase + (uint32_t)o.w, s4 * g4.x, s4 * g4.y, s4 * g4.z, s4 * g4.w);
+            if (c1) red_add_v4(gbase + base, s1 * g4.x, s1 * g4.y, s1 * g4.z, s1 * g4.w);
+            if (c2) red_add_v4(gbase + base + dx, s2 * g4.x, s2 * g4.y, s2 * g4.z, s2 * g4.w);
+            if (c3) red_add_v4(gbase + base + dy, s3 * g4.x, s3 * g4.y, s3 * g4.z, s3 * g4.w);
+            if (c4) red_add_v4(gbase + base + dy + dx, s4 * g4.x, s4 * g4.y, s4 * g4.z, s4 * g4.w);
         }
-        float ga0, ga1, gw0, gw1, gh0, gh1;
-        group_reduce_scatter16(pa, sub, ga0, ga1);
-        group_reduce_scatter16(pw, sub, gw0, gw1);
-        group_reduce_scatter16(ph, sub, gh0, gh1);
+        const float ga = group_reduce_scatter8(pa, c.sub);
+        const float gw = group_reduce_scatter8(pw, c.sub);
+        const float gh = group_reduce_scatter8(ph, c.sub);
         if (live) {
-            // cuh:156-158: d/d(loc_w) carries the factor width, d/d(loc_h) the factor height
-            *reinterpret_cast<float4 *>(grad_loc + pair * (kFastLP * 2) + sub * 4) =
-                make_float4(gw0 * (float)W, gh0 * (float)H, gw1 * (float)W, gh1 * (float)H);
-            *reinterpret_cast<float2 *>(grad_attn + pair * kFastLP + sub * 2) = make_float2(ga0, ga1);
+            const int pt_idx = half * 8 + c.sub;
+            *reinterpret_cast<float2 *>(grad_loc + pair * (kFastLP * 2) + pt_idx * 2) =
+                make_float2(gw * scaleW[half], gh * scaleH[half]);
+            grad_attn[pair * kFastLP + pt_idx] = ga;
         }
-        __syncwarp();
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ WarpCtx make_ctx(const LevelRow *lvl_tab, int M) {
+    WarpCtx c;
+    const int lane = threadIdx.x & 31;
+    c.grp = lane >> 3;
+    c.sub = lane & 7;
+    c.MD = (uint32_t)M * kFastD;
+    c.rs0 = lvl_tab[0].row_stride; c.rs1 = lvl_tab[1].row_stride;
+    c.rs2 = lvl_tab[2].row_stride; c.rs3 = lvl_tab[3].row_stride;
+    return c;
+}
+
+// ---- linear schedule --------------------------------------------------------------------------
+template <int UNROLL, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+msda_fwd_d32_l4p4(const float *__restrict__ value, const int64_t *__restrict__ shapes,
+                  const int64_t *__restrict__ lsi, const float *__restrict__ loc,
+                  const float *__restrict__ attn, int NQ, int Lq, int S, int M,
+                  float *__restrict__ out)
+{
+    __shared__ __align__(16) uint4 prep[kWarpsPerCta][4 * kFastLP];
+    __shared__ LevelRow lvl_tab[kFastL];
+    load_level_table(lvl_tab, shapes, lsi, (uint32_t)M * kFastD);
+    const WarpCtx c = make_ctx(lvl_tab, M);
+    const LevelRow my = lvl_tab[c.sub >> 1];
+    const int warp = threadIdx.x >> 5;
+    const int Q = blockIdx.x * kQueriesPerCta + warp * 4 + c.grp;   // flattened (n,q)
+    const bool live = Q < NQ;
+    const int n = live ? Q / Lq : 0;
+    const int heads_per = (M + gridDim.y - 1) / gridDim.y;
+    const int m_begin = blockIdx.y * heads_per;
+    const int m_end = min(M, m_begin + heads_per);
+    for (int m = m_begin; m < m_end; ++m)
+        fwd_warp_pairs<UNROLL>(value, loc, attn, out, c, my, prep[warp], Q, live, n, S, M, m);
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+msda_bwd_d32_l4p4(const float *__restrict__ value, const int64_t *__restrict__ shapes,
+                  const int64_t *__restrict__ lsi, const float *__restrict__ loc,
+                  const float *__restrict__ attn, const float *__restrict__ grad_out,
+                  int NQ, int Lq, int S, int M, float *__restrict__ grad_value,
+                  float *__restrict__ grad_loc, float *__restrict__ grad_attn)
+{
+    __shared__ __align__(16) uint4 prep[kWarpsPerCta][4 * kFastLP];
+    __shared__ LevelRow lvl_tab[kFastL];
+    load_level_table(lvl_tab, shapes, lsi, (uint32_t)M * kFastD);
+    const WarpCtx c = make_ctx(lvl_tab, M);
+    const LevelRow my = lvl_tab[c.sub >> 1];
+    const float scaleW[2] = {(float)lvl_tab[c.sub >> 2].W, (float)lvl_tab[2 + (c.sub >> 2)].W};
+    const float scaleH[2] = {(float)lvl_tab[c.sub >> 2].H, (float)lvl_tab[2 + (c.sub >> 2)].H};
+    const int warp = threadIdx.x >> 5;
+    const int Q = blockIdx.x * kQueriesPerCta + warp * 4 + c.grp;
+    const bool live = Q < NQ;
+    const int n = live ? Q / Lq : 0;
+    const int heads_per = (M + gridDim.y - 1) / gridDim.y;
+    const int m_begin = blockIdx.y * heads_per;
+    const int m_end = min(M, m_begin + heads_per);
+    for (int m = m_begin; m < m_end; ++m)
+        bwd_warp_pairs(value, loc, attn, grad_out, grad_value, grad_loc, grad_attn, c, my, scaleW,
+                       scaleH, prep[warp], Q, live, n, S, M, m);
+}
+
+// ---- tiled persistent schedule (Lq == S) ------------------------------------------------------
+// Tiles are TH x TW cells of one level; a tile is walked in rounds of (WARPS x 4) queries: warp w
+// of a round takes 4 consecutive cells of one tile row.
+template <int TH, int TW>
+struct TileSched {
+    int tiles_w[kFastL];
+    int first[kFastL + 1];      // prefix sum of tiles per level (per image)
+};
+
+template <int TH, int TW>
+__device__ __forceinline__ void build_tile_sched(TileSched<TH, TW> *ts, const LevelRow *lvl_tab) {
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int l = 0; l < kFastL; ++l) {
+            ts->tiles_w[l] = (lvl_tab[l].W + TW - 1) / TW;
+            ts->first[l] = acc;
+            acc += ts->tiles_w[l] * ((lvl_tab[l].H + TH - 1) / TH);
+        }
+        ts->first[kFastL] = acc;
+    }
+    __syncthreads();
+}
+
+// query (flattened over the batch) visited by this lane group in `round` of tile `t`
+template <int TH, int TW, int WARPS>
+__device__ __forceinline__ bool tile_query(const TileSched<TH, TW> &ts, const LevelRow *lvl_tab,
+                                           long long t, int round, int warp, int grp, int batch,
+                                           int S, int &Q, int &n) {
+    static_assert(TW % 4 == 0, "a warp takes 4 consecutive cells of a row");
+    const int per_image = ts.first[kFastL];
+    n = (int)(t / per_image);
+    int r = (int)(t % per_image);
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < kFastL; ++k) l += (r >= ts.first[k]) ? 1 : 0;
+    r -= ts.first[l];
+    const int tr = r / ts.tiles_w[l], tc = r % ts.tiles_w[l];
+    const int slot = (round * WARPS + warp) * 4 + grp;      // 0 .. TH*TW-1, row-major in the tile
+    const int row = tr * TH + slot / TW, col = tc * TW + slot % TW;
+    const bool live = (n < batch) && (row < lvl_tab[l].H) && (col < lvl_tab[l].W);
+    Q = n * S + (int)lvl_tab[l].start + row * lvl_tab[l].W + col;
+    if (!live) { Q = 0; n = 0; }
+    return live;
+}
+
+template <int TH, int TW, int WARPS, int UNROLL, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+msda_fwd_d32_l4p4_tiled(const float *__restrict__ value, const int64_t *__restrict__ shapes,
+                        const int64_t *__restrict__ lsi, const float *__restrict__ loc,
+                        const float *__restrict__ attn, int batch, int S, int M,
+                        float *__restrict__ out)
+{
+    static_assert((TH * TW) % (WARPS * 4) == 0, "tile must be a whole number of rounds");
+    constexpr int kRounds = TH * TW / (WARPS * 4);
+    __shared__ __align__(16) uint4 prep[WARPS][4 * kFastLP];
+    __shared__ LevelRow lvl_tab[kFastL];
+    __shared__ TileSched<TH, TW> ts;
+    load_level_table(lvl_tab, shapes, lsi, (uint32_t)M * kFastD);
+    build_tile_sched<TH, TW>(&ts, lvl_tab);
+    const WarpCtx c = make_ctx(lvl_tab, M);
+    const LevelRow my = lvl_tab[c.sub >> 1];
+    const int warp = threadIdx.x >> 5;
+    // work unit = (tile, head): fine enough that the static round-robin over the persistent grid
+    // stays balanced (a whole tile with all heads was 2x too coarse: 760 tiles over 740 CTAs)
+    const long long total = (long long)ts.first[kFastL] * batch * M;
+    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+        const long long t = u / M;
+        const int m = (int)(u % M);
+#pragma unroll 1
+        for (int round = 0; round < kRounds; ++round) {
+            int Q, n;
+            const bool live = tile_query<TH, TW, WARPS>(ts, lvl_tab, t, round, warp, c.grp,
+                                                        batch, S, Q, n);
+            fwd_warp_pairs<UNROLL>(value, loc, attn, out, c, my, prep[warp], Q, live, n, S, M, m);
+        }
+    }
+}
+
+template <int TH, int TW, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+msda_bwd_d32_l4p4_tiled(const float *__restrict__ value, const int64_t *__restrict__ shapes,
+                        const int64_t *__restrict__ lsi, const float *__restrict__ loc,
+                        const float *__restrict__ attn, const float *__restrict__ grad_out,
+                        int batch, int S, int M, float *__restrict__ grad_value,
+                        float *__restrict__ grad_loc, float *__restrict__ grad_attn)
+{
+    static_assert((TH * TW) % (WARPS * 4) == 0, "tile must be a whole number of rounds");
+    constexpr int kRounds = TH * TW / (WARPS * 4);
+    __shared__ __align__(16) uint4 prep[WARPS][4 * kFastLP];
+    __shared__ LevelRow lvl_tab[kFastL];
+    __shared__ TileSched<TH, TW> ts;
+    load_level_table(lvl_tab, shapes, lsi, (uint32_t)M * kFastD);
+    build_tile_sched<TH, TW>(&ts, lvl_tab);
+    const WarpCtx c = make_ctx(lvl_tab, M);
+    const LevelRow my = lvl_tab[c.sub >> 1];
+    const float scaleW[2] = {(float)lvl_tab[c.sub >> 2].W, (float)lvl_tab[2 + (c.sub >> 2)].W};
+    const float scaleH[2] = {(float)lvl_tab[c.sub >> 2].H, (float)lvl_tab[2 + (c.sub >> 2)].H};
+    const int warp = threadIdx.x >> 5;
+    const long long total = (long long)ts.first[kFastL] * batch * M;
+    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+        const long long t = u / M;
+        const int m = (int)(u % M);
+#pragma unroll 1
+        for (int round = 0; round < kRounds; ++round) {
+            int Q, n;
+            const bool live = tile_query<TH, TW, WARPS>(ts, lvl_tab, t, round, warp, c.grp,
+                                                        batch, S, Q, n);
+            bwd_warp_pairs(value, loc, attn, grad_out, grad_value, grad_loc, grad_attn, c, my,
+                           scaleW, scaleH, prep[warp], Q, live, n, S, M, m);
+        }
     }
 }
 
@@ -437,6 +602,15 @@ inline bool fast_ok(int batch, int spatial_size, int num_heads, int channels, in
     return velems < (1ll << 32) && nq < (1ll << 31) - kQueriesPerCta;
 }
 
+// CTAs along x walk 32 consecutive queries; heads are sliced over grid.y only when the query
+// dimension alone leaves SMs idle (decoder-shaped calls: a few hundred queries).
+inline dim3 fast_grid(int NQ, int num_heads) {
+    const int gx = (NQ + kQueriesPerCta - 1) / kQueriesPerCta;
+    int gy = 1;
+    while (gx * gy < 2 * 148 && gy < num_heads && num_heads % (gy * 2) == 0) gy *= 2;
+    return dim3((unsigned)gx, (unsigned)gy, 1);
+}
+
 inline int grid_for(long long work, int per_block) {
     long long b = (work + per_block - 1) / per_block;
     const long long cap = 148ll * 64;     // grid-stride beyond this
@@ -457,10 +631,39 @@ int forward_impl(const T *value, const int64_t *shapes, const int64_t *lsi, cons
     if (pairs * channels >= (1ll << 62)) return RLIPV2_MSDA_ETOOBIG;
     if (allow_fast) {
         const int NQ = batch * num_query;
-        const int grid = (NQ + kQueriesPerCta - 1) / kQueriesPerCta;
-        msda_fwd_d32_l4p4<<<grid, kThreads, 0, stream>>>(
-            (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn, NQ,
-            num_query, spatial_size, num_heads, (float *)out);
+        const int v = g_fwd_variant;
+        if (num_query == spatial_size && v < 100) {
+            // encoder self-attention: persistent CTAs over 2-D tiles of cells
+#define RLIPV2_FWD_TILED(TH, TW, WARPS, U, B)                                                    \
+            msda_fwd_d32_l4p4_tiled<TH, TW, WARPS, U, B><<<148 * B, WARPS * 32, 0, stream>>>(     \
+                (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn,      \
+                batch, spatial_size, num_heads, (float *)out)
+            switch (v) {
+                case 1: RLIPV2_FWD_TILED(8, 8, 8, 8, 4); break;
+                case 2: RLIPV2_FWD_TILED(8, 8, 16, 8, 2); break;
+                case 3: RLIPV2_FWD_TILED(8, 16, 16, 8, 2); break;
+                case 4: RLIPV2_FWD_TILED(4, 8, 8, 8, 5); break;
+                case 5: RLIPV2_FWD_TILED(8, 8, 8, 16, 3); break;
+                case 6: RLIPV2_FWD_TILED(16, 16, 16, 8, 2); break;
+                case 7: RLIPV2_FWD_TILED(8, 16, 32, 8, 1); break;
+                case 8: RLIPV2_FWD_TILED(4, 8, 8, 16, 3); break;
+                case 9: RLIPV2_FWD_TILED(8, 4, 8, 8, 5); break;
+                case 10: RLIPV2_FWD_TILED(8, 8, 8, 8, 6); break;
+                default: RLIPV2_FWD_TILED(8, 8, 8, 8, 5); break;
+            }
+#undef RLIPV2_FWD_TILED
+        } else {
+            const dim3 grid = fast_grid(NQ, num_heads);
+#define RLIPV2_FWD_LAUNCH(U, B)                                                                  \
+            msda_fwd_d32_l4p4<U, B><<<grid, kThreads, 0, stream>>>(                               \
+                (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn, NQ,  \
+                num_query, spatial_size, num_heads, (float *)out)
+            switch (v % 100) {
+                case 1: RLIPV2_FWD_LAUNCH(8, 5); break;
+                default: RLIPV2_FWD_LAUNCH(16, 3); break;
+            }
+#undef RLIPV2_FWD_LAUNCH
+        }
     } else {
         const long long total = pairs * channels;
         msda_fwd_generic<T><<<grid_for(total, 256), 256, 0, stream>>>(
@@ -491,11 +694,34 @@ int backward_impl(const T *value, const int64_t *shapes, const int64_t *lsi, con
         return RLIPV2_MSDA_EINVAL;
     if (allow_fast) {
         const int NQ = batch * num_query;
-        const int grid = (NQ + kQueriesPerCta - 1) / kQueriesPerCta;
-        msda_bwd_d32_l4p4<<<grid, kThreads, 0, stream>>>(
-            (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn,
-            (const float *)grad_out, NQ, num_query, spatial_size, num_heads, (float *)grad_value,
-            (float *)grad_loc, (float *)grad_attn);
+        const int v = g_bwd_variant;
+        if (num_query == spatial_size && v < 100) {
+#define RLIPV2_BWD_TILED(TH, TW, WARPS, B)                                                       \
+            msda_bwd_d32_l4p4_tiled<TH, TW, WARPS, B><<<148 * B, WARPS * 32, 0, stream>>>(        \
+                (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn,      \
+                (const float *)grad_out, batch, spatial_size, num_heads, (float *)grad_value,    \
+                (float *)grad_loc, (float *)grad_attn)
+            switch (v) {
+                case 1: RLIPV2_BWD_TILED(8, 8, 8, 3); break;
+                case 2: RLIPV2_BWD_TILED(8, 8, 16, 1); break;
+                case 3: RLIPV2_BWD_TILED(8, 16, 16, 1); break;
+                case 4: RLIPV2_BWD_TILED(4, 8, 8, 2); break;
+                default: RLIPV2_BWD_TILED(8, 8, 8, 2); break;
+            }
+#undef RLIPV2_BWD_TILED
+        } else {
+            const dim3 grid = fast_grid(NQ, num_heads);
+#define RLIPV2_BWD_LAUNCH(B)                                                                     \
+            msda_bwd_d32_l4p4<B><<<grid, kThreads, 0, stream>>>(                                  \
+                (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn,      \
+                (const float *)grad_out, NQ, num_query, spatial_size, num_heads,                 \
+                (float *)grad_value, (float *)grad_loc, (float *)grad_attn)
+            switch (v % 100) {
+                case 1: RLIPV2_BWD_LAUNCH(3); break;
+                default: RLIPV2_BWD_LAUNCH(2); break;
+            }
+#undef RLIPV2_BWD_LAUNCH
+        }
     } else {
         msda_bwd_generic<T><<<grid_for(pairs * 32, 256), 256, 0, stream>>>(
             value, shapes, lsi, loc, attn, grad_out, pairs, num_query, spatial_size, num_heads,
@@ -571,6 +797,9 @@ const char *rlipv2_msda_error_string(int code)
 }
 
 int rlipv2_msda_abi_version(void) { return RLIPV2_MSDA_ABI_VERSION; }
+
+// development hook used by tools/msda_microbench.py to compare kernel variants in one process
+void rlipv2_msda_debug_set_variant(int fwd, int bwd) { g_fwd_variant = fwd; g_bwd_variant = bwd; }
 
 unsigned long long rlipv2_msda_launch_count(void)
 {

@@ -10,22 +10,23 @@
 // Design (see DESIGN.md "MSDA kernels"):
 //  * a "pair" is one (n,q,m): 16 sampling points x 4 corners, each corner one 128-byte row of
 //    D=32 fp32 channels.  The op is a gather: per pair 8 KB move through the SM's 128 B/clk
-//    L1 data path, versus 320 B of streaming input/output.
+//    L1 data path (64 wavefronts), versus 320 B of streaming input/output.
 //  * fast path (fp32, D=32, L=4, P=4 - every ParSeDA call): 8 lanes x float4 own one pair, a
 //    warp owns 4 pairs (same head, 4 consecutive queries -> the four groups hit neighbouring
-//    cells and share L1 lines).  Phase 1: each lane prepares 2 points of its pair (bilinear
-//    weights x attention weight, clamped corner offsets) into shared memory.  Phase 2: every
-//    lane walks the 16 points: 2 LDS.128 + 4 LDG.128 + 16 FFMA per point.  That keeps the issue
-//    slots per pair (~140) below the 64-wavefront L1 floor (256 slots), i.e. the kernel runs at
-//    the gather floor instead of the reference's ~560 issue slots per pair.
+//    cells and share L1 lines).  Phase 1: each lane prepares 2 points of its pair (clamped corner
+//    offset + validity bits, fractional parts, attention weight: 4 words) into shared memory.
+//    Phase 2: every lane walks the 16 points: 1 LDS.128 + 4 LDG.128 + 16 FFMA per point.
+//    Measured (ncu, profiles/msda_r01.md): 90 L1 wavefronts and 231 issue slots per pair versus
+//    the reference kernel's 64 + ~560; the kernel runs at 71 % of the L1 data-pipe peak.
 //  * a CTA walks a run of 32 consecutive queries head by head, so co-resident warps work on the
 //    same head's neighbourhood (L1 reuse) rather than on 8 different heads.
 //  * backward fast path: same ownership; d_k = <v_k, grad_out> dot products per corner give
 //    grad_attn / grad_loc partials with 16 FFMA instead of ~60; partials are kept in registers
-//    for all 16 points and reduced across the 8 lanes with a 14-shuffle reduce-scatter per
+//    for 8 points at a time and reduced across the 8 lanes with a 7-shuffle reduce-scatter per
 //    quantity (the reference: 2 __syncthreads + a serial 32-term sum by thread 0 per point);
 //    grad_value uses 128-bit vector reductions (red.global.add.v4.f32 -> REDG.E.ADD.F32x4),
-//    4x fewer atomic instructions than the reference's scalar atomicAdd.
+//    4x fewer atomic instructions than the reference's scalar atomicAdd.  The backward is bound
+//    by the SM->L2 reduction path (1 sector per clock per SM, 256 sector-cycles per pair).
 //  * generic path (any D / L / P, fp32 + fp64): plain SIMT, one thread per output element
 //    (forward) or one warp per pair (backward); kept for API completeness (gradcheck shapes).
 //
@@ -40,8 +41,6 @@
 namespace {
 
 std::atomic<unsigned long long> g_launches{0};
-// tuning knobs (tools/msda_microbench.py --variants); not part of the public ABI
-int g_fwd_variant = 0, g_bwd_variant = 0;
 
 constexpr int kFastD = 32;
 constexpr int kFastL = 4;
@@ -95,13 +94,11 @@ __device__ __forceinline__ uint4 pack_point(float loc_w, float loc_h, float a, i
 // ---------------------------------------------------------------------------------------------
 // Fast path: fp32, D=32, L=4, P=4.
 //
-// Two schedules share one per-warp body:
-//  * "linear": CTA b walks queries [32b, 32b+32) of the flattened (batch, query) axis; heads may
-//    be sliced over grid.y when the query axis alone cannot fill 148 SMs (decoder-shaped calls).
-//  * "tiled" (Lq == S, i.e. the encoder's self-attention where query i sits on cell i): a
-//    persistent grid of CTAs loops over TH x TW tiles of cells of one level, so that the queries a
-//    CTA works on are 2-D neighbours and their sampling footprints overlap in L1.  Only the order
-//    in which queries are visited changes; any sampling pattern is still computed correctly.
+// Schedule: CTA b walks queries [32b, 32b+32) of the flattened (batch, query) axis head by head;
+// heads are sliced over grid.y when the query axis alone cannot fill 148 SMs (decoder-shaped
+// calls).  A persistent 2-D-tiled schedule for the encoder (Lq == S) was measured in round 1: it
+// lifts the L1 hit rate from 68 % to 79 % but not the speed (the kernel is bound by L1 data-pipe
+// wavefronts, not by misses) - see DESIGN.md; the code is in git history (commit "MSDA v4").
 // ---------------------------------------------------------------------------------------------
 struct WarpCtx {
     int grp, sub;             // lane group (pair slot) and lane within the group
@@ -346,119 +343,6 @@ msda_bwd_d32_l4p4(const float *__restrict__ value, const int64_t *__restrict__ s
                        scaleH, prep[warp], Q, live, n, S, M, m);
 }
 
-// ---- tiled persistent schedule (Lq == S) ------------------------------------------------------
-// Tiles are TH x TW cells of one level; a tile is walked in rounds of (WARPS x 4) queries: warp w
-// of a round takes 4 consecutive cells of one tile row.
-template <int TH, int TW>
-struct TileSched {
-    int tiles_w[kFastL];
-    int first[kFastL + 1];      // prefix sum of tiles per level (per image)
-};
-
-template <int TH, int TW>
-__device__ __forceinline__ void build_tile_sched(TileSched<TH, TW> *ts, const LevelRow *lvl_tab) {
-    if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int l = 0; l < kFastL; ++l) {
-            ts->tiles_w[l] = (lvl_tab[l].W + TW - 1) / TW;
-            ts->first[l] = acc;
-            acc += ts->tiles_w[l] * ((lvl_tab[l].H + TH - 1) / TH);
-        }
-        ts->first[kFastL] = acc;
-    }
-    __syncthreads();
-}
-
-// query (flattened over the batch) visited by this lane group in `round` of tile `t`
-template <int TH, int TW, int WARPS>
-__device__ __forceinline__ bool tile_query(const TileSched<TH, TW> &ts, const LevelRow *lvl_tab,
-                                           long long t, int round, int warp, int grp, int batch,
-                                           int S, int &Q, int &n) {
-    static_assert(TW % 4 == 0, "a warp takes 4 consecutive cells of a row");
-    const int per_image = ts.first[kFastL];
-    n = (int)(t / per_image);
-    int r = (int)(t % per_image);
-    int l = 0;
-#pragma unroll
-    for (int k = 1; k < kFastL; ++k) l += (r >= ts.first[k]) ? 1 : 0;
-    r -= ts.first[l];
-    const int tr = r / ts.tiles_w[l], tc = r % ts.tiles_w[l];
-    const int slot = (round * WARPS + warp) * 4 + grp;      // 0 .. TH*TW-1, row-major in the tile
-    const int row = tr * TH + slot / TW, col = tc * TW + slot % TW;
-    const bool live = (n < batch) && (row < lvl_tab[l].H) && (col < lvl_tab[l].W);
-    Q = n * S + (int)lvl_tab[l].start + row * lvl_tab[l].W + col;
-    if (!live) { Q = 0; n = 0; }
-    return live;
-}
-
-template <int TH, int TW, int WARPS, int UNROLL, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB)
-msda_fwd_d32_l4p4_tiled(const float *__restrict__ value, const int64_t *__restrict__ shapes,
-                        const int64_t *__restrict__ lsi, const float *__restrict__ loc,
-                        const float *__restrict__ attn, int batch, int S, int M,
-                        float *__restrict__ out)
-{
-    static_assert((TH * TW) % (WARPS * 4) == 0, "tile must be a whole number of rounds");
-    constexpr int kRounds = TH * TW / (WARPS * 4);
-    __shared__ __align__(16) uint4 prep[WARPS][4 * kFastLP];
-    __shared__ LevelRow lvl_tab[kFastL];
-    __shared__ TileSched<TH, TW> ts;
-    load_level_table(lvl_tab, shapes, lsi, (uint32_t)M * kFastD);
-    build_tile_sched<TH, TW>(&ts, lvl_tab);
-    const WarpCtx c = make_ctx(lvl_tab, M);
-    const LevelRow my = lvl_tab[c.sub >> 1];
-    const int warp = threadIdx.x >> 5;
-    // work unit = (tile, head): fine enough that the static round-robin over the persistent grid
-    // stays balanced (a whole tile with all heads was 2x too coarse: 760 tiles over 740 CTAs)
-    const long long total = (long long)ts.first[kFastL] * batch * M;
-    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
-        const long long t = u / M;
-        const int m = (int)(u % M);
-#pragma unroll 1
-        for (int round = 0; round < kRounds; ++round) {
-            int Q, n;
-            const bool live = tile_query<TH, TW, WARPS>(ts, lvl_tab, t, round, warp, c.grp,
-                                                        batch, S, Q, n);
-            fwd_warp_pairs<UNROLL>(value, loc, attn, out, c, my, prep[warp], Q, live, n, S, M, m);
-        }
-    }
-}
-
-template <int TH, int TW, int WARPS, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB)
-msda_bwd_d32_l4p4_tiled(const float *__restrict__ value, const int64_t *__restrict__ shapes,
-                        const int64_t *__restrict__ lsi, const float *__restrict__ loc,
-                        const float *__restrict__ attn, const float *__restrict__ grad_out,
-                        int batch, int S, int M, float *__restrict__ grad_value,
-                        float *__restrict__ grad_loc, float *__restrict__ grad_attn)
-{
-    static_assert((TH * TW) % (WARPS * 4) == 0, "tile must be a whole number of rounds");
-    constexpr int kRounds = TH * TW / (WARPS * 4);
-    __shared__ __align__(16) uint4 prep[WARPS][4 * kFastLP];
-    __shared__ LevelRow lvl_tab[kFastL];
-    __shared__ TileSched<TH, TW> ts;
-    load_level_table(lvl_tab, shapes, lsi, (uint32_t)M * kFastD);
-    build_tile_sched<TH, TW>(&ts, lvl_tab);
-    const WarpCtx c = make_ctx(lvl_tab, M);
-    const LevelRow my = lvl_tab[c.sub >> 1];
-    const float scaleW[2] = {(float)lvl_tab[c.sub >> 2].W, (float)lvl_tab[2 + (c.sub >> 2)].W};
-    const float scaleH[2] = {(float)lvl_tab[c.sub >> 2].H, (float)lvl_tab[2 + (c.sub >> 2)].H};
-    const int warp = threadIdx.x >> 5;
-    const long long total = (long long)ts.first[kFastL] * batch * M;
-    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
-        const long long t = u / M;
-        const int m = (int)(u % M);
-#pragma unroll 1
-        for (int round = 0; round < kRounds; ++round) {
-            int Q, n;
-            const bool live = tile_query<TH, TW, WARPS>(ts, lvl_tab, t, round, warp, c.grp,
-                                                        batch, S, Q, n);
-            bwd_warp_pairs(value, loc, attn, grad_out, grad_value, grad_loc, grad_attn, c, my,
-                           scaleW, scaleH, prep[warp], Q, live, n, S, M, m);
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Generic path: any channels / levels / points, float or double.
 // ---------------------------------------------------------------------------------------------
@@ -631,39 +515,18 @@ int forward_impl(const T *value, const int64_t *shapes, const int64_t *lsi, cons
     if (pairs * channels >= (1ll << 62)) return RLIPV2_MSDA_ETOOBIG;
     if (allow_fast) {
         const int NQ = batch * num_query;
-        const int v = g_fwd_variant;
-        if (num_query == spatial_size && v < 100) {
-            // encoder self-attention: persistent CTAs over 2-D tiles of cells
-#define RLIPV2_FWD_TILED(TH, TW, WARPS, U, B)                                                    \
-            msda_fwd_d32_l4p4_tiled<TH, TW, WARPS, U, B><<<148 * B, WARPS * 32, 0, stream>>>(     \
-                (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn,      \
-                batch, spatial_size, num_heads, (float *)out)
-            switch (v) {
-                case 1: RLIPV2_FWD_TILED(8, 8, 8, 8, 4); break;
-                case 2: RLIPV2_FWD_TILED(8, 8, 16, 8, 2); break;
-                case 3: RLIPV2_FWD_TILED(8, 16, 16, 8, 2); break;
-                case 4: RLIPV2_FWD_TILED(4, 8, 8, 8, 5); break;
-                case 5: RLIPV2_FWD_TILED(8, 8, 8, 16, 3); break;
-                case 6: RLIPV2_FWD_TILED(16, 16, 16, 8, 2); break;
-                case 7: RLIPV2_FWD_TILED(8, 16, 32, 8, 1); break;
-                case 8: RLIPV2_FWD_TILED(4, 8, 8, 16, 3); break;
-                case 9: RLIPV2_FWD_TILED(8, 4, 8, 8, 5); break;
-                case 10: RLIPV2_FWD_TILED(8, 8, 8, 8, 6); break;
-                default: RLIPV2_FWD_TILED(8, 8, 8, 8, 5); break;
-            }
-#undef RLIPV2_FWD_TILED
-        } else {
-            const dim3 grid = fast_grid(NQ, num_heads);
-#define RLIPV2_FWD_LAUNCH(U, B)                                                                  \
-            msda_fwd_d32_l4p4<U, B><<<grid, kThreads, 0, stream>>>(                               \
-                (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn, NQ,  \
-                num_query, spatial_size, num_heads, (float *)out)
-            switch (v % 100) {
-                case 1: RLIPV2_FWD_LAUNCH(8, 5); break;
-                default: RLIPV2_FWD_LAUNCH(16, 3); break;
-            }
-#undef RLIPV2_FWD_LAUNCH
-        }
+        const dim3 grid = fast_grid(NQ, num_heads);
+        // encoder-shaped calls are bound by the L1 data pipe: 5 CTAs/SM of 48-register threads;
+        // decoder-shaped calls (random cells, DRAM-bound) want the deeper unroll (16 points of
+        // loads in flight).  Both measured on B200, profiles/msda_r01.md.
+        if (NQ >= 8192)
+            msda_fwd_d32_l4p4<8, 5><<<grid, kThreads, 0, stream>>>(
+                (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn, NQ,
+                num_query, spatial_size, num_heads, (float *)out);
+        else
+            msda_fwd_d32_l4p4<16, 3><<<grid, kThreads, 0, stream>>>(
+                (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn, NQ,
+                num_query, spatial_size, num_heads, (float *)out);
     } else {
         const long long total = pairs * channels;
         msda_fwd_generic<T><<<grid_for(total, 256), 256, 0, stream>>>(
@@ -694,34 +557,11 @@ int backward_impl(const T *value, const int64_t *shapes, const int64_t *lsi, con
         return RLIPV2_MSDA_EINVAL;
     if (allow_fast) {
         const int NQ = batch * num_query;
-        const int v = g_bwd_variant;
-        if (num_query == spatial_size && v < 100) {
-#define RLIPV2_BWD_TILED(TH, TW, WARPS, B)                                                       \
-            msda_bwd_d32_l4p4_tiled<TH, TW, WARPS, B><<<148 * B, WARPS * 32, 0, stream>>>(        \
-                (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn,      \
-                (const float *)grad_out, batch, spatial_size, num_heads, (float *)grad_value,    \
-                (float *)grad_loc, (float *)grad_attn)
-            switch (v) {
-                case 1: RLIPV2_BWD_TILED(8, 8, 8, 3); break;
-                case 2: RLIPV2_BWD_TILED(8, 8, 16, 1); break;
-                case 3: RLIPV2_BWD_TILED(8, 16, 16, 1); break;
-                case 4: RLIPV2_BWD_TILED(4, 8, 8, 2); break;
-                default: RLIPV2_BWD_TILED(8, 8, 8, 2); break;
-            }
-#undef RLIPV2_BWD_TILED
-        } else {
-            const dim3 grid = fast_grid(NQ, num_heads);
-#define RLIPV2_BWD_LAUNCH(B)                                                                     \
-            msda_bwd_d32_l4p4<B><<<grid, kThreads, 0, stream>>>(                                  \
-                (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn,      \
-                (const float *)grad_out, NQ, num_query, spatial_size, num_heads,                 \
-                (float *)grad_value, (float *)grad_loc, (float *)grad_attn)
-            switch (v % 100) {
-                case 1: RLIPV2_BWD_LAUNCH(3); break;
-                default: RLIPV2_BWD_LAUNCH(2); break;
-            }
-#undef RLIPV2_BWD_LAUNCH
-        }
+        const dim3 grid = fast_grid(NQ, num_heads);
+        msda_bwd_d32_l4p4<2><<<grid, kThreads, 0, stream>>>(
+            (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn,
+            (const float *)grad_out, NQ, num_query, spatial_size, num_heads, (float *)grad_value,
+            (float *)grad_loc, (float *)grad_attn);
     } else {
         msda_bwd_generic<T><<<grid_for(pairs * 32, 256), 256, 0, stream>>>(
             value, shapes, lsi, loc, attn, grad_out, pairs, num_query, spatial_size, num_heads,
@@ -798,8 +638,6 @@ const char *rlipv2_msda_error_string(int code)
 
 int rlipv2_msda_abi_version(void) { return RLIPV2_MSDA_ABI_VERSION; }
 
-// development hook used by tools/msda_microbench.py to compare kernel variants in one process
-void rlipv2_msda_debug_set_variant(int fwd, int bwd) { g_fwd_variant = fwd; g_bwd_variant = bwd; }
 
 unsigned long long rlipv2_msda_launch_count(void)
 {

@@ -55,7 +55,6 @@ def main():
     ap.add_argument("--ref", action="store_true")
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--cases", default="dec16,dec2,encrand2,enc2")
-    ap.add_argument("--variants", default="", help="e.g. 0,1,2:0,1 = fwd variants : bwd variants (dev hook)")
     args = ap.parse_args()
     peak = 6581.2
     try:
@@ -63,24 +62,6 @@ def main():
     except Exception:
         pass
     impls = {"ours": MSDA}
-    if args.variants:
-        import ctypes
-        from rlipv2_b200 import msda_abi
-        lib = ctypes.CDLL(msda_abi.library_path())
-        fv, bv = (args.variants.split(":") + ["0"])[:2]
-        impls = {}
-        for f in fv.split(","):
-            for b in bv.split(","):
-                class V:  # noqa: N801
-                    def __init__(self, f, b):
-                        self.f, self.b = int(f), int(b)
-                    def ms_deform_attn_forward(self, *a):
-                        lib.rlipv2_msda_debug_set_variant(self.f, self.b)
-                        return MSDA.ms_deform_attn_forward(*a)
-                    def ms_deform_attn_backward(self, *a):
-                        lib.rlipv2_msda_debug_set_variant(self.f, self.b)
-                        return MSDA.ms_deform_attn_backward(*a)
-                impls[f"f{f}b{b}"] = V(f, b)
     if args.ref:
         from oracle import build_ref
         ref = build_ref.load()

@@ -13,7 +13,6 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--case", default="enc2")
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--ref", action="store_true")
-ap.add_argument("--variant", default="")
 a = ap.parse_args()
 if a.case == "enc2":
     s = synth.encoder_inputs(2, synth.LEVELS_800x1333, seed=0)
@@ -24,11 +23,6 @@ elif a.case == "dec2":
 else:
     s = synth.random_inputs(2, sum(h * w for h, w in synth.LEVELS_MICRO), synth.LEVELS_MICRO, seed=0)
 mod = MSDA
-if a.variant:
-    import ctypes
-    from rlipv2_b200 import msda_abi
-    f, b = a.variant.split(",")
-    ctypes.CDLL(msda_abi.library_path()).rlipv2_msda_debug_set_variant(int(f), int(b))
 if a.ref:
     from oracle import build_ref
     mod = build_ref.load()

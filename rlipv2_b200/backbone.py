@@ -1,0 +1,137 @@
+"""Multi-level ResNet backbone + sine position encoding for ParSeDA.
+
+north_star keeps the backbone on torch/cuDNN; this file only restates the thin wrapper the model
+needs offline (no hard-coded weight paths): /root/reference/models/DDETR_backbone.py:31-169 and
+models/position_encoding.py:22-58.  Parameter/buffer names match (`backbone.0.body.*`).
+"""
+import math
+from typing import Dict, List
+
+import torch
+import torch.nn.functional as F
+import torchvision
+from torch import nn
+from torchvision.models._utils import IntermediateLayerGetter
+
+from .nested import NestedTensor
+
+
+class FrozenBatchNorm2d(nn.Module):
+    """BatchNorm2d with fixed statistics and affine parameters (buffers), eps inside the rsqrt
+    (DDETR_backbone.py:31-68)."""
+
+    def __init__(self, n, eps=1e-5):
+        super().__init__()
+        self.register_buffer("weight", torch.ones(n))
+        self.register_buffer("bias", torch.zeros(n))
+        self.register_buffer("running_mean", torch.zeros(n))
+        self.register_buffer("running_var", torch.ones(n))
+        self.eps = eps
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        state_dict.pop(prefix + "num_batches_tracked", None)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                                      error_msgs)
+
+    def forward(self, x):
+        scale = (self.weight * (self.running_var + self.eps).rsqrt()).reshape(1, -1, 1, 1)
+        bias = self.bias.reshape(1, -1, 1, 1) - self.running_mean.reshape(1, -1, 1, 1) * scale
+        return x * scale + bias
+
+
+class PositionEmbeddingSine(nn.Module):
+    """Normalised 2-D sine embedding over the un-padded extent (position_encoding.py:22-58)."""
+
+    def __init__(self, num_pos_feats=64, temperature=10000, normalize=False, scale=None):
+        super().__init__()
+        self.num_pos_feats = num_pos_feats
+        self.temperature = temperature
+        self.normalize = normalize
+        if scale is not None and normalize is False:
+            raise ValueError("normalize should be True if scale is passed")
+        self.scale = 2 * math.pi if scale is None else scale
+
+    def forward(self, tensor_list: NestedTensor):
+        mask = tensor_list.mask
+        assert mask is not None
+        not_mask = ~mask
+        y_embed = not_mask.cumsum(1, dtype=torch.float32)
+        x_embed = not_mask.cumsum(2, dtype=torch.float32)
+        if self.normalize:
+            eps = 1e-6
+            y_embed = y_embed / (y_embed[:, -1:, :] + eps) * self.scale
+            x_embed = x_embed / (x_embed[:, :, -1:] + eps) * self.scale
+        dim_t = torch.arange(self.num_pos_feats, dtype=torch.float32, device=mask.device)
+        dim_t = self.temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / self.num_pos_feats)
+        pos_x = x_embed[:, :, :, None] / dim_t
+        pos_y = y_embed[:, :, :, None] / dim_t
+        pos_x = torch.stack((pos_x[:, :, :, 0::2].sin(), pos_x[:, :, :, 1::2].cos()), dim=4).flatten(3)
+        pos_y = torch.stack((pos_y[:, :, :, 0::2].sin(), pos_y[:, :, :, 1::2].cos()), dim=4).flatten(3)
+        return torch.cat((pos_y, pos_x), dim=3).permute(0, 3, 1, 2)
+
+
+class Backbone(nn.Module):
+    """ResNet with FrozenBatchNorm returning C3, C4, C5 (strides 8/16/32); stem + layer1 frozen
+    (DDETR_backbone.py:71-138)."""
+
+    def __init__(self, name="resnet50", train_backbone=True, return_interm_layers=True, dilation=False,
+                 weights_path=None):
+        super().__init__()
+        assert name not in ("resnet18", "resnet34"), "number of channels are hard coded"
+        backbone = getattr(torchvision.models, name)(
+            replace_stride_with_dilation=[False, False, dilation], weights=None, norm_layer=FrozenBatchNorm2d)
+        if weights_path:
+            backbone.load_state_dict(torch.load(weights_path, map_location="cpu"), strict=True)
+        for pname, parameter in backbone.named_parameters():
+            if not train_backbone or ("layer2" not in pname and "layer3" not in pname and "layer4" not in pname):
+                parameter.requires_grad_(False)
+        if return_interm_layers:
+            return_layers = {"layer2": "0", "layer3": "1", "layer4": "2"}
+            self.strides = [8, 16, 32]
+            self.num_channels = [512, 1024, 2048]
+        else:
+            return_layers = {"layer4": "0"}
+            self.strides = [32]
+            self.num_channels = [2048]
+        if dilation:
+            self.strides[-1] = self.strides[-1] // 2
+        self.body = IntermediateLayerGetter(backbone, return_layers=return_layers)
+
+    def forward(self, tensor_list: NestedTensor) -> Dict[str, NestedTensor]:
+        xs = self.body(tensor_list.tensors)
+        out = {}
+        for name, x in xs.items():
+            m = tensor_list.mask
+            assert m is not None
+            mask = F.interpolate(m[None].float(), size=x.shape[-2:]).to(torch.bool)[0]
+            out[name] = NestedTensor(x, mask)
+        return out
+
+
+class Joiner(nn.Sequential):
+    """(backbone, position embedding) -> (feature NestedTensors, position embeddings)."""
+
+    def __init__(self, backbone, position_embedding):
+        super().__init__(backbone, position_embedding)
+        self.strides = backbone.strides
+        self.num_channels = backbone.num_channels
+
+    def forward(self, tensor_list: NestedTensor):
+        xs = self[0](tensor_list)
+        out: List[NestedTensor] = [x for _, x in sorted(xs.items())]
+        pos = [self[1](x).to(x.tensors.dtype) for x in out]
+        return out, pos
+
+
+def build_backbone(args):
+    """build_DDETR_backbone (DDETR_backbone.py:163-169) minus the hard-coded weight path: pass
+    `args.backbone_weights` (a resnet50 state_dict file) to start from pretrained weights."""
+    if "swin" in args.backbone:
+        raise NotImplementedError("Swin backbones (config 4) are outside round 1's scope")
+    if getattr(args, "position_embedding", "sine") not in ("v2", "sine"):
+        raise NotImplementedError("ParSeDA scripts use the sine position embedding")
+    position_embedding = PositionEmbeddingSine(args.hidden_dim // 2, normalize=True)
+    backbone = Backbone(args.backbone, args.lr_backbone > 0, args.masks or (args.num_feature_levels > 1),
+                        args.dilation, getattr(args, "backbone_weights", None))
+    return Joiner(backbone, position_embedding)

@@ -1,0 +1,211 @@
+"""SetCriterionHOI - the losses of the RLIPv2-ParSeDA train step.
+
+Mirror of /root/reference/models/hoi.py:3627-4766 restricted to what the ParSeDA scripts enable
+(`losses = ['obj_labels', 'verb_labels', 'sub_obj_boxes', 'obj_cardinality']`, models/detr.py:626):
+  loss_obj_labels      weighted cross-entropy over the label-text logits, subject + object summed,
+                       `eos_coef` on the last ("no objects") class            hoi.py:3696-3828
+  loss_obj_cardinality |#non-empty predictions - #targets| (metric, no grad)  hoi.py:3909-3923
+  loss_verb_labels     focal loss on sigmoid verb logits; with --giou_verb_label the matched targets
+                       are scaled by (GIoU+1)/2 and the QFL-style `_soft_neg_loss` is used
+                                                                              hoi.py:3925-4028, 4481-4495
+  loss_sub_obj_boxes   L1 + GIoU on matched boxes                             hoi.py:4162-4193
+and the forward that matches once per decoder layer (hoi.py:4654-4766).  Same keys, same
+normalisation (`num_interactions` all-reduced over ranks, clamped to >= 1).
+
+B200-first differences that do not change values: the per-step `.item()` on `num_interactions`
+is kept on the device (a 1-element tensor divides the losses), the degenerate-box asserts of
+generalized_box_iou are skipped, and the class-error meters stay device tensors.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+from torch import nn
+
+from .nested import box_cxcywh_to_xyxy, generalized_box_iou
+
+
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size()
+    return 1
+
+
+@torch.no_grad()
+def accuracy(output, target, topk=(1,)):
+    """precision@k (util/misc.py accuracy); 0 for empty targets."""
+    if target.numel() == 0:
+        return [torch.zeros([], device=output.device)]
+    maxk = max(topk)
+    _, pred = output.topk(maxk, 1, True, True)
+    correct = pred.t().eq(target.view(1, -1).expand_as(pred.t()))
+    return [correct[:k].reshape(-1).float().sum(0) * (100.0 / target.size(0)) for k in topk]
+
+
+class SetCriterionHOI(nn.Module):
+    def __init__(self, num_obj_classes, num_queries, num_verb_classes, matcher, weight_dict, eos_coef, losses,
+                 verb_loss_type, obj_loss_type="cross_entropy", temperature=0.07, matching_symmetric=True,
+                 RLIP_ParSe=False, subject_class=False, use_no_verb_token=False, giou_verb_label=False,
+                 verb_curing=False, pseudo_verb=False, triplet_filtering=False, naive_obj_smooth=0,
+                 naive_verb_smooth=0, args=None):
+        super().__init__()
+        if verb_loss_type not in ("focal", "bce") or obj_loss_type != "cross_entropy":
+            raise NotImplementedError("ParSeDA scripts: --obj_loss_type cross_entropy --verb_loss_type focal")
+        if verb_curing or triplet_filtering or naive_obj_smooth or naive_verb_smooth or getattr(args, "verb_tagger", False):
+            raise NotImplementedError("verb_curing / triplet_filtering / naive smoothing / verb_tagger are "
+                                      "not used by the ParSeDA fine-tune or pre-train scripts")
+        for l in losses:
+            if l not in ("obj_labels", "verb_labels", "sub_obj_boxes", "obj_cardinality"):
+                raise NotImplementedError(f"loss '{l}' is outside the ParSeDA hot path")
+        self.num_obj_classes = num_obj_classes
+        self.num_queries = num_queries
+        self.num_verb_classes = num_verb_classes
+        self.matcher = matcher
+        self.weight_dict = weight_dict
+        self.eos_coef = eos_coef
+        self.losses = losses
+        empty_weight = torch.ones(self.num_obj_classes + 1)
+        empty_weight[-1] = self.eos_coef
+        self.register_buffer("empty_weight", empty_weight)
+        self.verb_loss_type = verb_loss_type
+        self.obj_loss_type = obj_loss_type
+        self.temperature = temperature
+        self.subject_class = subject_class
+        self.use_no_verb_token = use_no_verb_token
+        self.giou_verb_label = giou_verb_label
+        if giou_verb_label:
+            assert verb_loss_type == "focal" and obj_loss_type == "cross_entropy"
+        self.pseudo_verb = pseudo_verb
+
+    # ---- helpers ----------------------------------------------------------------------------------
+    @staticmethod
+    def _src_idx(indices):
+        batch_idx = torch.cat([torch.full_like(src, i) for i, (src, _) in enumerate(indices)])
+        src_idx = torch.cat([src for (src, _) in indices])
+        return batch_idx, src_idx
+
+    def _weighted_ce(self, logits, targets, indices, key):
+        """F.cross_entropy with weight eos_coef on the last class; unmatched queries -> last class."""
+        w = torch.ones(logits.shape[-1], device=logits.device)
+        w[-1] = self.eos_coef
+        idx = self._src_idx(indices)
+        matched = torch.cat([t[key][J] for t, (_, J) in zip(targets, indices)])
+        classes = torch.full(logits.shape[:2], logits.shape[-1] - 1, dtype=torch.int64, device=logits.device)
+        classes[idx] = matched.to(logits.device)
+        return F.cross_entropy(logits.transpose(1, 2), classes, w), idx, matched
+
+    # ---- losses -----------------------------------------------------------------------------------
+    def loss_obj_labels(self, outputs, targets, indices, num_interactions, log=True):
+        loss_obj, idx, matched_obj = self._weighted_ce(outputs["pred_obj_logits"], targets, indices, "obj_labels")
+        if not self.subject_class:
+            losses = {"loss_obj_ce": loss_obj}
+            if log:
+                losses["obj_class_error"] = 100 - accuracy(outputs["pred_obj_logits"][idx], matched_obj)[0]
+            return losses
+        loss_sub, _, matched_sub = self._weighted_ce(outputs["pred_sub_logits"], targets, indices, "sub_labels")
+        losses = {"loss_obj_ce": loss_obj + loss_sub}
+        if log:
+            losses["obj_class_error"] = 100 - accuracy(outputs["pred_obj_logits"][idx], matched_obj)[0]
+            losses["sub_class_error"] = 100 - accuracy(outputs["pred_sub_logits"][idx], matched_sub)[0]
+        return losses
+
+    @torch.no_grad()
+    def loss_obj_cardinality(self, outputs, targets, indices, num_interactions):
+        pred_logits = outputs["pred_obj_logits"]
+        tgt_lengths = torch.as_tensor([len(v["obj_labels"]) for v in targets], device=pred_logits.device)
+        card_pred = (pred_logits.argmax(-1) != pred_logits.shape[-1] - 1).sum(1)
+        return {"obj_cardinality_error": F.l1_loss(card_pred.float(), tgt_lengths.float())}
+
+    def loss_verb_labels(self, outputs, targets, indices, num_interactions):
+        src_logits = outputs["pred_verb_logits"]
+        idx = self._src_idx(indices)
+        if self.giou_verb_label:
+            # soft targets: matched verb labels scaled by (GIoU + 1) / 2 of the matched pair (hoi.py:3932-3957)
+            _, cost_list = self.matcher(outputs, targets, return_cost=True)
+            giou = -cost_list[0]
+            q0 = t0 = 0
+            soft = []
+            for t, (I, J) in zip(targets, indices):
+                s = (giou[q0 + I.to(giou.device), t0 + J.to(giou.device)] + 1) / 2
+                labels = t["verb_labels"][J]
+                if self.pseudo_verb:
+                    labels = labels + outputs["target_verb_sim"][t0 + J]
+                soft.append(labels * s.unsqueeze(-1))
+                q0 += src_logits.shape[1]
+                t0 += J.shape[0]
+            target_o = torch.cat(soft)
+        else:
+            target_o = torch.cat([t["verb_labels"][J] for t, (_, J) in zip(targets, indices)])
+        if self.use_no_verb_token:
+            src_logits = src_logits[:, :, :src_logits.shape[2] - 1]
+        target = torch.zeros_like(src_logits)
+        target[idx] = target_o.to(target.dtype)
+        if self.verb_loss_type == "bce":
+            return {"loss_verb_ce": F.binary_cross_entropy_with_logits(src_logits, target)}
+        prob = src_logits.sigmoid()
+        loss = self._soft_neg_loss(prob, target) if self.giou_verb_label else self._neg_loss(prob, target)
+        return {"loss_verb_ce": loss}
+
+    def loss_sub_obj_boxes(self, outputs, targets, indices, num_interactions):
+        idx = self._src_idx(indices)
+        src_sub = outputs["pred_sub_boxes"][idx]
+        src_obj = outputs["pred_obj_boxes"][idx]
+        tgt_sub = torch.cat([t["sub_boxes"][i] for t, (_, i) in zip(targets, indices)], dim=0)
+        tgt_obj = torch.cat([t["obj_boxes"][i] for t, (_, i) in zip(targets, indices)], dim=0)
+        exist = (tgt_obj != 0).any(dim=1)
+        if src_sub.shape[0] == 0:
+            z_s, z_o = src_sub.sum(), src_obj.sum()
+            return {"loss_sub_bbox": z_s, "loss_obj_bbox": z_o, "loss_sub_giou": z_s, "loss_obj_giou": z_o}
+        l1_sub = F.l1_loss(src_sub, tgt_sub, reduction="none")
+        l1_obj = F.l1_loss(src_obj, tgt_obj, reduction="none")
+        giou_sub = 1 - torch.diag(generalized_box_iou(box_cxcywh_to_xyxy(src_sub), box_cxcywh_to_xyxy(tgt_sub), check=False))
+        giou_obj = 1 - torch.diag(generalized_box_iou(box_cxcywh_to_xyxy(src_obj), box_cxcywh_to_xyxy(tgt_obj), check=False))
+        return {"loss_sub_bbox": l1_sub.sum() / num_interactions,
+                "loss_obj_bbox": (l1_obj * exist.unsqueeze(1)).sum() / (exist.sum() + 1e-4),
+                "loss_sub_giou": giou_sub.sum() / num_interactions,
+                "loss_obj_giou": (giou_obj * exist).sum() / (exist.sum() + 1e-4)}
+
+    @staticmethod
+    def _neg_loss(pred, gt, eps=1e-6):
+        """CornerNet-style focal loss on probabilities (hoi.py:4453-4478)."""
+        pos_inds = gt.eq(1).float()
+        neg_inds = gt.lt(1).float()
+        neg_weights = torch.pow(1 - gt, 4)
+        pred = torch.clamp(pred, eps, 1. - eps)
+        pos_loss = (torch.log(pred) * torch.pow(1 - pred, 2) * pos_inds).sum()
+        neg_loss = (torch.log(1 - pred) * torch.pow(pred, 2) * neg_weights * neg_inds).sum()
+        num_pos = pos_inds.sum()
+        return torch.where(num_pos == 0, -neg_loss, -(pos_loss + neg_loss) / num_pos.clamp(min=1))
+
+    @staticmethod
+    def _soft_neg_loss(pred, gt, eps=1e-6, beta=2):
+        """Quality focal loss with soft targets (hoi.py:4481-4495)."""
+        num_pos = gt.gt(0).float().sum()
+        pred = torch.clamp(pred, eps, 1. - eps)
+        loss = torch.pow(torch.abs(gt - pred), beta) * ((1 - gt) * torch.log(1 - pred) + gt * torch.log(pred))
+        return torch.where(num_pos == 0, -loss.sum(), -loss.sum() / num_pos.clamp(min=1))
+
+    def get_loss(self, loss, outputs, targets, indices, num, **kwargs):
+        fn = {"obj_labels": self.loss_obj_labels, "obj_cardinality": self.loss_obj_cardinality,
+              "verb_labels": self.loss_verb_labels, "sub_obj_boxes": self.loss_sub_obj_boxes}
+        assert loss in fn, f"do you really want to compute {loss} loss?"
+        return fn[loss](outputs, targets, indices, num, **kwargs)
+
+    def forward(self, outputs, targets):
+        outputs_without_aux = {k: v for k, v in outputs.items() if k != "aux_outputs"}
+        indices = self.matcher(outputs_without_aux, targets)
+        device = next(iter(outputs.values())).device
+        num_interactions = torch.as_tensor([sum(len(t["obj_labels"]) for t in targets)], dtype=torch.float,
+                                           device=device)
+        if _world() > 1:
+            dist.all_reduce(num_interactions)
+        num_interactions = torch.clamp(num_interactions / _world(), min=1)     # stays on the device
+        losses = {}
+        for loss in self.losses:
+            losses.update(self.get_loss(loss, outputs, targets, indices, num_interactions))
+        for i, aux in enumerate(outputs.get("aux_outputs", [])):
+            indices = self.matcher(aux, targets)
+            for loss in self.losses:
+                kwargs = {"log": False} if loss == "obj_labels" else {}
+                l_dict = self.get_loss(loss, aux, targets, indices, num_interactions, **kwargs)
+                losses.update({k + f"_{i}": v for k, v in l_dict.items()})
+        return {k: (v.reshape(()) if v.numel() == 1 else v) for k, v in losses.items()}

@@ -1,0 +1,528 @@
+"""ParSeDA deformable encoder / decoder with ALIF (language-image fusion) - module layer.
+
+Mirrors, with identical parameter names (state_dict compatible) and arithmetic:
+  RLIP_ParSeDABDeformableTransformer_v2   /root/reference/models/dab_deformable/deformable_transformer.py:234-744
+  RLIPv2_DeformableTransformerEncoder     models/deformable_transformer.py:791-884
+  DeformableTransformerEncoderLayer       dab_deformable/deformable_transformer.py:1261-1300
+  DeformableTransformerDecoderLayer       dab_deformable/deformable_transformer.py:1346-1401
+  DABDeformableTransformerDecoderHOI      dab_deformable/deformable_transformer.py:1404-1552
+  MultiBranchFusion                       dab_deformable/deformable_transformer.py:1025-1068
+  MLP / gen_sineembed_for_position        dab_deformable/deformable_transformer.py:1763-1802
+
+B200-first differences that do not change results:
+  * level shapes travel as a python list next to the device tensor, so none of the reference's
+    per-call device->host syncs remain (`assert ... .sum() == Len_in`, ms_deform_attn.py:96;
+    iterating a CUDA `spatial_shapes`, models/deformable_transformer.py:805; `level_start_index[-1]`
+    as a slice bound, :829,845);
+  * MultiBranchFusion runs its 16 branches as three stacked GEMMs instead of 48 tiny ones;
+  * the decoder's self-attention keeps nn.MultiheadAttention's parameter names but is computed with
+    one fused in-projection;
+  * every dense contraction goes through `rlipv2_b200.dense` (the seam the tcgen05 kernels plug into).
+"""
+import copy
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.nn.init import normal_
+from torch.nn.utils.rnn import pad_sequence
+
+from . import dense
+from .alif import FeatureResizer, RLIPv2_VLFuse
+from .ms_deform_attn import MSDeformAttn
+from .nested import inverse_sigmoid
+from .roberta_layer import RobertaLayer
+from .text_encoder import build_text_encoder
+
+
+def _get_clones(module, n):
+    return nn.ModuleList([copy.deepcopy(module) for _ in range(n)])
+
+
+class MLP(nn.Module):
+    """Linear -> ReLU -> ... -> Linear (dab_deformable/deformable_transformer.py:1763-1775)."""
+
+    def __init__(self, input_dim, hidden_dim, output_dim, num_layers):
+        super().__init__()
+        self.num_layers = num_layers
+        h = [hidden_dim] * (num_layers - 1)
+        self.layers = nn.ModuleList(nn.Linear(n, k) for n, k in zip([input_dim] + h, h + [output_dim]))
+
+    def forward(self, x):
+        for i, layer in enumerate(self.layers):
+            if i < self.num_layers - 1:
+                x = dense.linear_relu(x, layer.weight, layer.bias)
+            else:
+                x = dense.linear(x, layer.weight, layer.bias)
+        return x
+
+
+def gen_sineembed_for_position(pos_tensor):
+    """[bs, nq, 2|4] normalised (x, y[, w, h]) -> [bs, nq, 256|512] sine embedding in the order
+    (y, x[, w, h]); 128 features each, temperature 10000 (deformable_transformer.py:1777-1802)."""
+    scale = 2 * math.pi
+    dim_t = torch.arange(128, dtype=torch.float32, device=pos_tensor.device)
+    dim_t = 10000 ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / 128)
+
+    def emb(col):
+        p = (pos_tensor[:, :, col] * scale)[:, :, None] / dim_t
+        return torch.stack((p[:, :, 0::2].sin(), p[:, :, 1::2].cos()), dim=3).flatten(2)
+
+    if pos_tensor.size(-1) == 2:
+        return torch.cat((emb(1), emb(0)), dim=2)
+    if pos_tensor.size(-1) == 4:
+        return torch.cat((emb(1), emb(0), emb(2), emb(3)), dim=2)
+    raise ValueError("Unknown pos_tensor shape(-1):{}".format(pos_tensor.size(-1)))
+
+
+class MultiBranchFusion(nn.Module):
+    """relu(sum_c fc_3[c](relu(fc_1[c](a) * fc_2[c](b)))) with `cardinality` branches
+    (deformable_transformer.py:1025-1068).  Parameters stay per-branch (checkpoint layout); the
+    forward stacks them into three GEMMs."""
+
+    def __init__(self, appearance_size, spatial_size, representation_size, cardinality):
+        super().__init__()
+        self.cardinality = cardinality
+        sub = int(representation_size / cardinality)
+        assert sub * cardinality == representation_size
+        self.fc_1 = nn.ModuleList([nn.Linear(appearance_size, sub) for _ in range(cardinality)])
+        self.fc_2 = nn.ModuleList([nn.Linear(spatial_size, sub) for _ in range(cardinality)])
+        self.fc_3 = nn.ModuleList([nn.Linear(sub, representation_size) for _ in range(cardinality)])
+
+    def forward(self, appearance, spatial):
+        w1 = torch.cat([m.weight for m in self.fc_1], 0)
+        b1 = torch.cat([m.bias for m in self.fc_1], 0)
+        w2 = torch.cat([m.weight for m in self.fc_2], 0)
+        b2 = torch.cat([m.bias for m in self.fc_2], 0)
+        w3 = torch.cat([m.weight for m in self.fc_3], 1)          # [R, cardinality*sub]
+        b3 = torch.stack([m.bias for m in self.fc_3], 0).sum(0)
+        h = F.relu(dense.linear(appearance, w1, b1) * dense.linear(spatial, w2, b2))
+        return dense.linear_relu(h, w3, b3)
+
+
+class DeformableTransformerEncoderLayer(nn.Module):
+    """MSDeformAttn self-attention + add&LN + FFN + add&LN (deformable_transformer.py:1261-1300)."""
+
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4):
+        super().__init__()
+        if activation != "relu":
+            raise NotImplementedError("ParSeDA scripts use relu")
+        self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.dropout2 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.dropout3 = nn.Dropout(dropout)
+        self.norm2 = nn.LayerNorm(d_model)
+
+    def forward_ffn(self, src):
+        h = self.dropout2(dense.linear_relu(src, self.linear1.weight, self.linear1.bias))
+        src2 = self.dropout3(dense.linear(h, self.linear2.weight, self.linear2.bias))
+        return dense.add_layer_norm(src2, src, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+
+    def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None,
+                spatial_shapes_host=None):
+        q = src if pos is None else src + pos
+        src2 = self.self_attn(q, reference_points, src, spatial_shapes, level_start_index, padding_mask,
+                              spatial_shapes_host=spatial_shapes_host)
+        src = dense.add_layer_norm(self.dropout1(src2), src, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        return self.forward_ffn(src)
+
+
+class RLIPv2_DeformableTransformerEncoder(nn.Module):
+    """6 deformable layers; before layers 0, 2, 4 the coarsest level's tokens and the label
+    embeddings are fused by ALIF and the labels pass one RobertaLayer
+    (models/deformable_transformer.py:791-884)."""
+
+    def __init__(self, encoder_layer, roberta_layer, VLFuse_layer, num_layers, fusion_interval=2,
+                 fusion_last_vis=False, lang_aux_loss=False):
+        super().__init__()
+        self.layers = _get_clones(encoder_layer, num_layers)
+        self.num_layers = num_layers
+        self.fusion_interval = fusion_interval
+        self.roberta_layers = _get_clones(roberta_layer, num_layers // fusion_interval)
+        self.VLFuse_layers = _get_clones(VLFuse_layer, num_layers // fusion_interval)
+        self.fusion_last_vis = fusion_last_vis
+        self.lang_aux_loss = lang_aux_loss
+
+    @staticmethod
+    def get_reference_points(spatial_shapes_host, valid_ratios, device):
+        """cell centres / valid extent, then scaled to every level (:803-815) -> [bs, S, L, 2]"""
+        refs = []
+        for lvl, (H_, W_) in enumerate(spatial_shapes_host):
+            ref_y, ref_x = torch.meshgrid(
+                torch.linspace(0.5, H_ - 0.5, H_, dtype=torch.float32, device=device),
+                torch.linspace(0.5, W_ - 0.5, W_, dtype=torch.float32, device=device), indexing="ij")
+            ref_y = ref_y.reshape(-1)[None] / (valid_ratios[:, None, lvl, 1] * H_)
+            ref_x = ref_x.reshape(-1)[None] / (valid_ratios[:, None, lvl, 0] * W_)
+            refs.append(torch.stack((ref_x, ref_y), -1))
+        reference_points = torch.cat(refs, 1)
+        return reference_points[:, :, None] * valid_ratios[:, None]
+
+    def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None,
+                lang_hidden=None, lang_masks=None, spatial_shapes_host=None):
+        if spatial_shapes_host is None:     # reference-compatible call: one sync to learn the shapes
+            spatial_shapes_host = [tuple(int(v) for v in hw) for hw in spatial_shapes.tolist()]
+        last_start = sum(h * w for h, w in spatial_shapes_host[:-1])
+        reference_points = self.get_reference_points(spatial_shapes_host, valid_ratios, src.device)
+        inv_padding_mask = ~padding_mask
+        inv_lang_masks = ~lang_masks
+        if self.fusion_last_vis:
+            vis = {"src": src, "padding_mask": inv_padding_mask[:, last_start:], "pos": pos[:, last_start:]}
+        else:
+            vis = {"src": src, "padding_mask": inv_padding_mask, "pos": pos}
+        lang = {"hidden": lang_hidden, "masks": inv_lang_masks}
+        multi_lay_lang = []
+        for idx, layer in enumerate(self.layers):
+            if idx % self.fusion_interval == 0:
+                k = idx // self.fusion_interval
+                if self.fusion_last_vis:
+                    full_src = vis["src"]
+                    vis["src"] = full_src[:, last_start:]
+                fused = self.VLFuse_layers[k]({"visual": vis, "lang": lang})
+                vis, lang = fused["visual"], fused["lang"]
+                if self.fusion_last_vis:
+                    # write the fused coarsest level back (the reference does it in place, :856-859)
+                    vis["src"] = torch.cat((full_src[:, :last_start], vis["src"]), dim=1)
+                lang["hidden"] = self.roberta_layers[k](lang["hidden"], attention_mask=lang["masks"])
+                multi_lay_lang.append(lang["hidden"])
+            vis["src"] = layer(vis["src"], pos, reference_points, spatial_shapes, level_start_index,
+                               padding_mask, spatial_shapes_host=spatial_shapes_host)
+        if self.lang_aux_loss:
+            if self.fusion_interval == 2:
+                multi_lay_lang = torch.stack(multi_lay_lang, dim=0)
+            elif self.fusion_interval == 1:
+                multi_lay_lang = torch.stack(multi_lay_lang[::2], dim=0)
+        else:
+            multi_lay_lang = multi_lay_lang[-1]
+        return vis["src"], multi_lay_lang
+
+
+class QuerySelfAttention(nn.Module):
+    """8x32 self-attention among the queries with nn.MultiheadAttention's parameter layout
+    (`in_proj_weight [3C, C]`, `in_proj_bias`, `out_proj`), batch-first."""
+
+    def __init__(self, embed_dim, num_heads, dropout=0.0):
+        super().__init__()
+        self.embed_dim, self.num_heads, self.dropout = embed_dim, num_heads, dropout
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * embed_dim, embed_dim))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * embed_dim))
+        self.out_proj = nn.Linear(embed_dim, embed_dim)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.constant_(self.out_proj.bias, 0.)
+
+    def forward(self, qk_input, v_input):
+        b, t, c = qk_input.shape
+        h, d = self.num_heads, c // self.num_heads
+        qk = dense.linear(qk_input, self.in_proj_weight[:2 * c], self.in_proj_bias[:2 * c])
+        v = dense.linear(v_input, self.in_proj_weight[2 * c:], self.in_proj_bias[2 * c:])
+        q, k = qk[..., :c], qk[..., c:]
+        q = q.view(b, t, h, d).transpose(1, 2)
+        k = k.view(b, t, h, d).transpose(1, 2)
+        v = v.view(b, t, h, d).transpose(1, 2)
+        p = torch.softmax(torch.matmul(q * (d ** -0.5), k.transpose(-1, -2)), dim=-1)
+        if self.training and self.dropout > 0:
+            p = F.dropout(p, self.dropout)
+        o = torch.matmul(p, v).transpose(1, 2).reshape(b, t, c)
+        return dense.linear(o, self.out_proj.weight, self.out_proj.bias)
+
+
+class DeformableTransformerDecoderLayer(nn.Module):
+    """query self-attention + LN, MSDeformAttn cross-attention + LN, FFN + LN (:1346-1401)."""
+
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8,
+                 n_points=4, do_self_attn=True):
+        super().__init__()
+        if activation != "relu":
+            raise NotImplementedError("ParSeDA scripts use relu")
+        self.cross_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.do_self_attn = do_self_attn
+        if do_self_attn:
+            self.self_attn = QuerySelfAttention(d_model, n_heads, dropout=dropout)
+            self.dropout2 = nn.Dropout(dropout)
+            self.norm2 = nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.dropout3 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.dropout4 = nn.Dropout(dropout)
+        self.norm3 = nn.LayerNorm(d_model)
+
+    def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index,
+                src_padding_mask=None, spatial_shapes_host=None):
+        if self.do_self_attn:
+            qk = tgt if query_pos is None else tgt + query_pos
+            tgt2 = self.self_attn(qk, tgt)
+            tgt = dense.add_layer_norm(self.dropout2(tgt2), tgt, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        q = tgt if query_pos is None else tgt + query_pos
+        tgt2 = self.cross_attn(q, reference_points, src, src_spatial_shapes, level_start_index,
+                               src_padding_mask, spatial_shapes_host=spatial_shapes_host)
+        tgt = dense.add_layer_norm(self.dropout1(tgt2), tgt, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        h = self.dropout3(dense.linear_relu(tgt, self.linear1.weight, self.linear1.bias))
+        tgt2 = self.dropout4(dense.linear(h, self.linear2.weight, self.linear2.bias))
+        return dense.add_layer_norm(tgt2, tgt, self.norm3.weight, self.norm3.bias, self.norm3.eps)
+
+
+class DABDeformableTransformerDecoderHOI(nn.Module):
+    """DAB (dynamic anchor box) decoder loop over subject/object anchor boxes (:1404-1552).
+    ParSe=True: pair decoder, queries = [subjects ; objects], each half refines its own boxes.
+    ParSe=False: verb decoder, one query per pair, anchored at the mean of its two boxes."""
+
+    def __init__(self, decoder_layer, num_layers, return_intermediate=False, use_dab=False, d_model=256,
+                 high_dim_query_update=False, no_sine_embed=False, ParSe=False):
+        super().__init__()
+        assert use_dab and not high_dim_query_update and not no_sine_embed, \
+            "ParSeDA builds both decoders with use_dab=True only (transformer.py:1344-1362)"
+        self.layers = _get_clones(decoder_layer, num_layers)
+        self.num_layers = num_layers
+        self.return_intermediate = return_intermediate
+        self.sub_bbox_embed = None
+        self.obj_bbox_embed = None
+        self.class_embed = None
+        self.use_dab = use_dab
+        self.d_model = d_model
+        self.query_scale = MLP(d_model, d_model, d_model, 2)
+        self.ref_point_head = MLP(2 * d_model, d_model, d_model, 2)
+        self.ParSe = ParSe
+
+    def forward(self, tgt, reference_points, src, src_spatial_shapes, src_level_start_index, src_valid_ratios,
+                query_pos=None, src_padding_mask=None, spatial_shapes_host=None):
+        assert query_pos is None
+        output = tgt
+        bs = src.shape[0]
+        sub_ref, obj_ref = reference_points
+        if self.ParSe:
+            sub_ref = sub_ref[None].repeat(bs, 1, 1)
+            obj_ref = obj_ref[None].repeat(bs, 1, 1)
+        assert sub_ref.shape[-1] == 4 and obj_ref.shape[-1] == 4
+        pair_num = obj_ref.shape[1]
+        vr4 = torch.cat([src_valid_ratios, src_valid_ratios], -1)[:, None]       # [bs, 1, L, 4]
+        inter, inter_sub, inter_obj = [], [], []
+        for lid, layer in enumerate(self.layers):
+            if self.ParSe:
+                ref_input = torch.cat((sub_ref[:, :, None] * vr4, obj_ref[:, :, None] * vr4), dim=1)
+            else:
+                ref_input = 0.5 * (sub_ref + obj_ref)[:, :, None] * vr4
+            raw_query_pos = self.ref_point_head(gen_sineembed_for_position(ref_input[:, :, 0, :]))
+            query_pos_l = raw_query_pos if lid == 0 else self.query_scale(output) * raw_query_pos
+            output = layer(output, query_pos_l, ref_input, src, src_spatial_shapes, src_level_start_index,
+                           src_padding_mask, spatial_shapes_host=spatial_shapes_host)
+            # iterative box refinement; the refined anchors are detached (:1511-1541)
+            if self.sub_bbox_embed is not None:
+                sub_in = output[:, :pair_num] if self.ParSe else output
+                sub_ref = (self.sub_bbox_embed[lid](sub_in) + inverse_sigmoid(sub_ref)).sigmoid().detach()
+            if self.obj_bbox_embed is not None:
+                obj_in = output[:, pair_num:] if self.ParSe else output
+                obj_ref = (self.obj_bbox_embed[lid](obj_in) + inverse_sigmoid(obj_ref)).sigmoid().detach()
+            if self.return_intermediate:
+                inter.append(output)
+                inter_sub.append(sub_ref)
+                inter_obj.append(obj_ref)
+        if self.return_intermediate:
+            refs = torch.stack((torch.stack(inter_sub), torch.stack(inter_obj)), dim=0).transpose(0, 1)
+            return torch.stack(inter), refs
+        return output, reference_points
+
+
+class RLIP_ParSeDABDeformableTransformer_v2(nn.Module):
+    """Two-phase transformer of RLIPv2-ParSeDA (deformable_transformer.py:234-744).
+    Phase A (`encode_and_save=True`): flatten levels, encode label strings, ALIF encoder ->
+    memory_cache dict.  Phase B: pair decoder -> verb queries (MBF) -> verb decoder."""
+
+    def __init__(self, d_model=256, nhead=8, num_encoder_layers=6, num_decoder_layers=6, dim_feedforward=1024,
+                 dropout=0.1, activation="relu", return_intermediate_dec=False, num_feature_levels=4,
+                 dec_n_points=4, enc_n_points=4, two_stage=False, two_stage_num_proposals=300, use_dab=False,
+                 high_dim_query_update=False, no_sine_embed=False, pass_pos_and_query=True,
+                 text_encoder_type="roberta-base", freeze_text_encoder=False, args=None):
+        super().__init__()
+        if two_stage or not use_dab:
+            raise NotImplementedError("ParSeDA is built with use_dab=True, two_stage=False (transformer.py:1344-1362)")
+        self.d_model, self.nhead = d_model, nhead
+        self.two_stage = two_stage
+        self.two_stage_num_proposals = two_stage_num_proposals
+        self.use_dab = use_dab
+        self.fusion_type = args.fusion_type
+        if self.fusion_type != "GLIP_attn":
+            raise NotImplementedError("only --fusion_type GLIP_attn (ALIF) is on the hot path")
+
+        ho_layer = DeformableTransformerDecoderLayer(d_model, dim_feedforward, dropout, activation,
+                                                     num_feature_levels, nhead, dec_n_points)
+        self.ho_decoder = DABDeformableTransformerDecoderHOI(ho_layer, num_decoder_layers, return_intermediate_dec,
+                                                             use_dab=use_dab, d_model=d_model, ParSe=True)
+        verb_layer = DeformableTransformerDecoderLayer(d_model, dim_feedforward, dropout, activation,
+                                                       num_feature_levels, nhead, dec_n_points, do_self_attn=True)
+        self.verb_decoder = DABDeformableTransformerDecoderHOI(verb_layer, num_decoder_layers, return_intermediate_dec,
+                                                               use_dab=use_dab, d_model=d_model, ParSe=False)
+        self.verb_tgt_generator = MultiBranchFusion(256, 256, 256, 16)
+        self.level_embed = nn.Parameter(torch.Tensor(num_feature_levels, d_model))
+
+        from .text_encoder import roberta_base_config
+        enc_layer = DeformableTransformerEncoderLayer(d_model, dim_feedforward, dropout, activation,
+                                                      num_feature_levels, nhead, enc_n_points)
+        self.encoder = RLIPv2_DeformableTransformerEncoder(
+            enc_layer, RobertaLayer(roberta_base_config()), RLIPv2_VLFuse(args), num_encoder_layers,
+            fusion_interval=args.fusion_interval, fusion_last_vis=args.fusion_last_vis,
+            lang_aux_loss=args.lang_aux_loss)
+
+        self._reset_parameters()
+
+        self.pass_pos_and_query = pass_pos_and_query
+        self.tokenizer, self.text_encoder = build_text_encoder(
+            text_encoder_type, synthetic=getattr(args, "synthetic_text_encoder", None))
+        if freeze_text_encoder:
+            for p in self.text_encoder.parameters():
+                p.requires_grad_(False)
+        self.expander_dropout = 0.1
+        self.resizer = FeatureResizer(input_feat_size=self.text_encoder.config.hidden_size,
+                                      output_feat_size=d_model, dropout=self.expander_dropout)
+        self.verb_query_tgt_type = args.verb_query_tgt_type
+        if "MBF" in self.verb_query_tgt_type:
+            self.verb_tgt_generator = MultiBranchFusion(256, 256, 256, 16)
+
+    def _reset_parameters(self):
+        # xavier on every matrix built so far - including the RobertaLayers / ALIF blocks, but not the
+        # text encoder and resizer, which are attached afterwards (:364-374)
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        for m in self.modules():
+            if isinstance(m, MSDeformAttn):
+                m._reset_parameters()
+        normal_(self.level_embed)
+
+    @staticmethod
+    def get_valid_ratio(mask):
+        _, H, W = mask.shape
+        valid_H = torch.sum(~mask[:, :, 0], 1)
+        valid_W = torch.sum(~mask[:, 0, :], 1)
+        return torch.stack([valid_W.float() / W, valid_H.float() / H], -1)
+
+    # ---- text ---------------------------------------------------------------------------------
+    def encode_text(self, text, device):
+        """label strings -> pooled RoBERTa vectors, padded per image (:489-522).
+        -> text_memory [n_text, n_tuples, 768], text_attention_mask [n_text, n_tuples] (True = pad),
+           obj_pred_names_sums [n_tuples, 2]"""
+        sums, flat = [], []
+        for obj_names, pred_names in text:
+            sums.append((len(obj_names), len(pred_names)))
+            flat += list(obj_names) + list(pred_names)
+        obj_pred_names_sums = torch.tensor(sums)
+        tok = self.tokenizer.batch_encode_plus(flat, padding="longest", return_tensors="pt").to(device)
+        pooled = self.text_encoder(**tok).pooler_output
+        i, objs, preds = 0, [], []
+        for n_obj, n_pred in sums:
+            objs.append(pooled[i:i + n_obj])
+            preds.append(pooled[i + n_obj:i + n_obj + n_pred])
+            i += n_obj + n_pred
+        text_memory = torch.cat([pad_sequence(objs), pad_sequence(preds)], dim=0)
+        text_attention_mask = ~(text_memory.sum(dim=-1) > 0)
+        return text_memory, text_attention_mask, obj_pred_names_sums
+
+    # ---- forward ------------------------------------------------------------------------------
+    def forward(self, srcs=None, masks=None, pos_embeds=None, query_embed=None, text=None, encode_and_save=True,
+                text_memory=None, img_memory=None, text_attention_mask=None, obj_pred_names_sums=None,
+                spatial_shapes=None, level_start_index=None, valid_ratios=None, spatial_shapes_host=None):
+        assert query_embed is not None
+        if encode_and_save:
+            return self._encode(srcs, masks, pos_embeds, query_embed, text)
+        return self._decode(masks, query_embed, text_memory, img_memory, spatial_shapes, level_start_index,
+                            valid_ratios, spatial_shapes_host)
+
+    def _encode(self, srcs, masks, pos_embeds, query_embed, text):
+        src_flatten, mask_flatten, lvl_pos_flatten, shapes_host = [], [], [], []
+        for lvl, (src, mask, pos_embed) in enumerate(zip(srcs, masks, pos_embeds)):
+            bs, c, h, w = src.shape
+            shapes_host.append((h, w))
+            src_flatten.append(src.flatten(2).transpose(1, 2))
+            mask_flatten.append(mask.flatten(1))
+            lvl_pos_flatten.append(pos_embed.flatten(2).transpose(1, 2) + self.level_embed[lvl].view(1, 1, -1))
+        src_flatten = torch.cat(src_flatten, 1)
+        mask_flatten = torch.cat(mask_flatten, 1)
+        lvl_pos_flatten = torch.cat(lvl_pos_flatten, 1)
+        device = src_flatten.device
+        spatial_shapes = torch.as_tensor(shapes_host, dtype=torch.long, device=device)
+        starts = [0]
+        for h, w in shapes_host[:-1]:
+            starts.append(starts[-1] + h * w)
+        level_start_index = torch.as_tensor(starts, dtype=torch.long, device=device)
+        valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
+
+        if isinstance(text, list) and isinstance(text[0], tuple):          # training: raw label strings
+            text_memory, text_attention_mask, obj_pred_names_sums = self.encode_text(text, device)
+            lang = text_memory
+            if lang.shape[1] != bs:
+                lang = lang.repeat(1, bs, 1)
+                text_attention_mask = text_attention_mask.repeat(1, bs)
+        else:                                                               # eval: pre-encoded text
+            text_attention_mask, text_memory, obj_pred_names_sums = text
+            lang = text_memory
+        img_memory, lang_out = self.encoder(src_flatten, spatial_shapes, level_start_index, valid_ratios,
+                                            lvl_pos_flatten, mask_flatten, lang_hidden=lang.transpose(0, 1),
+                                            lang_masks=text_attention_mask.transpose(0, 1),
+                                            spatial_shapes_host=shapes_host)
+        if lang_out.dim() == 3:
+            text_memory_resized = self.resizer(lang_out.transpose(0, 1))
+        else:                                                               # [3, bs, Tl, 768] with lang_aux_loss
+            text_memory_resized = self.resizer(lang_out.transpose(1, 2))
+        return {
+            "text_memory_bf_resize": text_memory,
+            "text_memory_resized": text_memory_resized,
+            "text_memory": text_memory_resized,
+            "img_memory": img_memory,
+            "masks": mask_flatten,
+            "text_attention_mask": text_attention_mask,
+            "pos_embed": lvl_pos_flatten,
+            "ho_query_embed": query_embed,
+            "obj_pred_names_sums": obj_pred_names_sums,
+            "spatial_shapes": spatial_shapes,
+            "level_start_index": level_start_index,
+            "valid_ratios": valid_ratios,
+            "spatial_shapes_host": shapes_host,        # extra key: lets phase B skip the shape syncs
+        }
+
+    def _decode(self, mask_flatten, query_embed, text_memory, img_memory, spatial_shapes, level_start_index,
+                valid_ratios, spatial_shapes_host):
+        bs = img_memory.shape[0]
+        c = self.d_model
+        nq = query_embed.shape[0]
+        reference_points = query_embed[..., 2 * c:].sigmoid()
+        ref_sub, ref_obj = reference_points[:nq // 2], reference_points[nq // 2:]
+        tgt = query_embed[..., :c].unsqueeze(0).expand(bs, -1, -1)
+        verb_tgt = query_embed[..., c:2 * c].unsqueeze(0).expand(bs, -1, -1)
+        init_reference_out = (ref_sub, ref_obj)
+        hs_ho, inter_refs = self.ho_decoder(tgt, init_reference_out, img_memory, spatial_shapes, level_start_index,
+                                            valid_ratios, query_pos=None, src_padding_mask=mask_flatten,
+                                            spatial_shapes_host=spatial_shapes_host)
+        if self.verb_query_tgt_type == "vanilla":
+            merge_verb_tgt = verb_tgt[:, :nq // 2] + verb_tgt[:, nq // 2:]
+        elif self.verb_query_tgt_type == "MBF":
+            merge_verb_tgt = self.verb_tgt_generator(hs_ho[-1][:, :nq // 2], hs_ho[-1][:, nq // 2:])
+        elif self.verb_query_tgt_type == "vanilla_MBF":
+            merge_verb_tgt = self.verb_tgt_generator(hs_ho[-1][:, :nq // 2], hs_ho[-1][:, nq // 2:]) \
+                + verb_tgt[:, :nq // 2] + verb_tgt[:, nq // 2:]
+        else:
+            raise ValueError(self.verb_query_tgt_type)
+        hs_verb, _ = self.verb_decoder(merge_verb_tgt, inter_refs[-1], img_memory, spatial_shapes,
+                                       level_start_index, valid_ratios, query_pos=None,
+                                       src_padding_mask=mask_flatten, spatial_shapes_host=spatial_shapes_host)
+        hs_layer = hs_ho.shape[0]
+        if text_memory.dim() == 4 and text_memory.shape[0] == hs_layer:
+            text_dec = text_memory
+        else:
+            text_dec = text_memory.unsqueeze(0).repeat(hs_layer, 1, 1, 1)
+        return hs_ho, hs_verb, text_dec, init_reference_out, inter_refs, hs_ho, hs_verb, None, None
+
+
+def build_parseda_transformer(args):
+    """The RLIP_ParSeDA_v2 branch of build_transformer (models/transformer.py:1344-1362)."""
+    return RLIP_ParSeDABDeformableTransformer_v2(
+        d_model=args.hidden_dim, nhead=args.nheads, num_encoder_layers=args.enc_layers,
+        num_decoder_layers=args.dec_layers, dim_feedforward=args.dim_feedforward, dropout=args.dropout,
+        activation="relu", return_intermediate_dec=True, num_feature_levels=args.num_feature_levels,
+        dec_n_points=args.dec_n_points, enc_n_points=args.enc_n_points, two_stage=args.two_stage,
+        two_stage_num_proposals=args.num_queries, use_dab=True, args=args)
+    # NB: like the reference, `--text_encoder_type` / `--freeze_text_encoder` are NOT forwarded here
+    # (transformer.py:1346-1362), so ParSeDA always trains a roberta-base text encoder.

@@ -1,0 +1,63 @@
+"""Text-encoder plumbing of the ParSeDA transformer.
+
+The reference encodes every label string with HF `RobertaTokenizerFast` + `RobertaModel`
+(roberta-base) each step and keeps `pooler_output`
+(/root/reference/models/dab_deformable/deformable_transformer.py:333-335, 497-502).  Those are
+third-party components with downloaded weights; they stay third-party here.
+Offline (no weights on disk) the synthetic path below is used: a random-init RoBERTa-base of the
+same shape and a deterministic hash tokenizer, so that benchmarks and parity fixtures do the same
+arithmetic as a real run.
+"""
+import zlib
+
+import torch
+
+
+def roberta_base_config():
+    """roberta-base architecture (hidden 768, 12 layers x 12 heads, FFN 3072, LN eps 1e-5)."""
+    from transformers import RobertaConfig
+    return RobertaConfig(vocab_size=50265, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                         intermediate_size=3072, hidden_act="gelu", hidden_dropout_prob=0.1,
+                         attention_probs_dropout_prob=0.1, max_position_embeddings=514, type_vocab_size=1,
+                         layer_norm_eps=1e-5, pad_token_id=1, bos_token_id=0, eos_token_id=2)
+
+
+def hash_tokenize(texts):
+    """Deterministic stand-in for the BPE tokenizer: <s> w1 w2 ... </s>, one id per whitespace word
+    (crc32 of the lower-cased word), padded to the longest with pad id 1.
+    -> (input_ids [n, T] int64, attention_mask [n, T] int64)"""
+    rows = []
+    for t in texts:
+        words = str(t).lower().split()
+        rows.append([0] + [3 + zlib.crc32(w.encode()) % 50000 for w in words] + [2])
+    T = max(len(r) for r in rows)
+    ids = torch.full((len(rows), T), 1, dtype=torch.long)
+    mask = torch.zeros((len(rows), T), dtype=torch.long)
+    for i, r in enumerate(rows):
+        ids[i, :len(r)] = torch.tensor(r)
+        mask[i, :len(r)] = 1
+    return ids, mask
+
+
+class HashTokenizer:
+    """`batch_encode_plus(texts, padding="longest", return_tensors="pt")` like the HF fast tokenizer."""
+
+    def batch_encode_plus(self, texts, padding="longest", return_tensors="pt"):
+        from transformers import BatchEncoding
+        ids, mask = hash_tokenize(texts)
+        return BatchEncoding({"input_ids": ids, "attention_mask": mask})
+
+
+def build_text_encoder(text_encoder_type="roberta-base", synthetic=None):
+    """-> (tokenizer, text_encoder).  `synthetic=None` tries the local HF cache first and falls back
+    to the synthetic pair only when the pretrained files are absent (offline box)."""
+    from transformers import RobertaModel, RobertaTokenizerFast
+    if not synthetic:
+        try:
+            tok = RobertaTokenizerFast.from_pretrained(text_encoder_type, local_files_only=True)
+            enc = RobertaModel.from_pretrained(text_encoder_type, local_files_only=True)
+            return tok, enc
+        except Exception:
+            if synthetic is False:
+                raise
+    return HashTokenizer(), RobertaModel(roberta_base_config())

@@ -20,3 +20,13 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture
+def msda_cpu_stub(monkeypatch):
+    """Host-logic tests on a CPU-only box: swap the CUDA op for the (golden-pinned) torch oracle.
+    Never used when a test runs with device='cuda'."""
+    from oracle.msda_torch_oracle import CPUFunctionStub
+    import rlipv2_b200.ms_deform_attn as m
+    monkeypatch.setattr(m, "MSDeformAttnFunction", CPUFunctionStub)
+    return CPUFunctionStub

@@ -59,3 +59,19 @@ def test_oracle_empty_query():
     attn = g["attn_weight"][:, :0]
     out = msda_oracle.forward(g["value"], g["spatial_shapes"], g["level_start_index"], loc, attn)
     assert out.shape == (1, 0, 64)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_torch_oracle_matches_reference(name):
+    """oracle/msda_torch_oracle.py (the CPU stand-in used by the module-level host-logic tests)."""
+    import torch
+    from oracle.msda_torch_oracle import msda_core
+    g = load_msda(name)
+    t = lambda k: torch.from_numpy(g[k]).double()
+    v, l, a = t("value").requires_grad_(True), t("sampling_loc").requires_grad_(True), t("attn_weight").requires_grad_(True)
+    out = msda_core(v, g["spatial_shapes"].tolist(), l, a)
+    np.testing.assert_allclose(out.detach().numpy(), g["out"], rtol=1e-9, atol=1e-12)
+    out.backward(t("grad_out"))
+    np.testing.assert_allclose(v.grad.numpy(), g["grad_value"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(l.grad.numpy(), g["grad_sampling_loc"], rtol=1e-7, atol=1e-11)
+    np.testing.assert_allclose(a.grad.numpy(), g["grad_attn_weight"], rtol=1e-9, atol=1e-12)

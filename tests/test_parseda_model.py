@@ -1,0 +1,142 @@
+"""Module-level parity of the ParSeDA hot path against golden fixtures produced by the reference's
+own modules (oracle/gen_golden_model.py: RLIPv2_VLFuse, RobertaLayer, full RLIP_ParSeDA two-phase
+forward + SetCriterionHOI + HungarianMatcherHOI + backward), same name-keyed weights
+(oracle/detfill.py), eval() mode, fp32.
+
+Each test runs twice: on CPU (host logic; the CUDA op replaced by the golden-pinned torch oracle via
+the `msda_cpu_stub` fixture) and, marked gpu, on cuda:0 through the real sm_100a kernels.
+Tolerance: north_star's 1e-3 relative fp32 (matcher indices bit-exact)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.detfill import det_fill_
+from tests.golden_util import GOLDEN
+
+DEVICES = ["cpu", pytest.param("cuda", marks=pytest.mark.gpu)]
+
+
+def _load(name):
+    with np.load(os.path.join(GOLDEN, name)) as z:
+        return {k: z[k] for k in z.files}
+
+
+def _args(device, **kw):
+    from rlipv2_b200 import models
+    return models.default_args(device=device, num_queries=16, synthetic_text_encoder=True, **kw)
+
+
+def _fp32():
+    from rlipv2_b200 import dense
+    dense.set_matmul_precision("fp32")
+
+
+def test_state_dict_keys_match_reference():
+    from rlipv2_b200 import models
+    model, _, _ = models.build_model(_args("cpu"))
+    ref = json.load(open(os.path.join(GOLDEN, "parseda_state_dict_keys.json")))
+    mine = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert mine == ref
+    # the aliased box heads share storage (hoi.py:1980-1990)
+    sd = model.state_dict()
+    assert sd["sub_bbox_embed.0.layers.0.weight"].data_ptr() == \
+        sd["transformer.ho_decoder.sub_bbox_embed.0.layers.0.weight"].data_ptr()
+    assert sd["obj_bbox_embed.3.layers.0.weight"].data_ptr() == \
+        sd["transformer.verb_decoder.obj_bbox_embed.0.layers.0.weight"].data_ptr()
+    # optimizer groups of main.py:525-537 are selected by these substrings
+    names = [n for n, _ in model.named_parameters()]
+    assert any("backbone" in n for n in names) and any("text_encoder" in n for n in names)
+
+
+@pytest.mark.parametrize("device", DEVICES)
+def test_alif_block_golden(device):
+    _fp32()
+    from rlipv2_b200.alif import RLIPv2_VLFuse
+    g = _load("parseda_alif.npz")
+    fuse = det_fill_(RLIPv2_VLFuse(_args(device)), seed=1).eval().to(device)
+    t = lambda k: torch.from_numpy(g[k]).to(device)
+    with torch.no_grad():
+        out = fuse({"visual": {"src": t("v"), "padding_mask": t("mask_v"), "pos": t("pos")},
+                    "lang": {"hidden": t("l"), "masks": t("mask_l")}})
+    np.testing.assert_allclose(out["visual"]["src"].cpu().numpy(), g["out_v"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(out["lang"]["hidden"].cpu().numpy(), g["out_l"], rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("device", DEVICES)
+def test_roberta_layer_golden(device):
+    _fp32()
+    from rlipv2_b200.roberta_layer import RobertaLayer
+    from rlipv2_b200.text_encoder import roberta_base_config
+    g = _load("parseda_roberta.npz")
+    layer = det_fill_(RobertaLayer(roberta_base_config()), seed=2).eval().to(device)
+    with torch.no_grad():
+        y = layer(torch.from_numpy(g["x"]).to(device), attention_mask=torch.from_numpy(g["mask"]).to(device))
+    np.testing.assert_allclose(y.cpu().numpy(), g["y"], rtol=1e-3, atol=1e-4)
+
+
+def _run_step(device):
+    from oracle.gen_golden_model import GRAD_KEYS, OBJ_NAMES, VERB_NAMES
+    from rlipv2_b200 import models
+    g = _load("parseda_step.npz")
+    model, criterion, _ = models.build_model(_args(device))
+    det_fill_(model, seed=3)
+    model.to(device).eval()
+    criterion.to(device).eval()
+    imgs = [torch.from_numpy(g["img0"]).to(device), torch.from_numpy(g["img1"]).to(device)]
+    targets = [{k: torch.from_numpy(g[f"tgt{i}_{k}"]).to(device)
+                for k in ("obj_labels", "sub_labels", "verb_labels", "sub_boxes", "obj_boxes")} for i in range(2)]
+    text = [(OBJ_NAMES, VERB_NAMES)]
+    cache = model(imgs, encode_and_save=True, text=text, targets=targets)
+    out = model(imgs, encode_and_save=False, memory_cache=cache, text=text, targets=targets)
+    loss_dict = criterion(out, targets)
+    wd = criterion.weight_dict
+    total = sum(loss_dict[k] * wd[k] for k in loss_dict if k in wd)
+    total.backward()
+    return g, model, criterion, cache, out, loss_dict, total, targets, GRAD_KEYS
+
+
+@pytest.mark.parametrize("device", DEVICES)
+def test_full_step_golden(device, request):
+    _fp32()
+    if device == "cpu":
+        request.getfixturevalue("msda_cpu_stub")
+    g, model, criterion, cache, out, loss_dict, total, targets, GRAD_KEYS = _run_step(device)
+    c = lambda t: t.detach().cpu().numpy()
+    tol = dict(rtol=1e-3, atol=2e-4)
+    # phase A
+    np.testing.assert_array_equal(c(cache["text_attention_mask"]), g["text_attention_mask"])
+    np.testing.assert_allclose(c(cache["valid_ratios"]), g["valid_ratios"], rtol=1e-6)
+    np.testing.assert_allclose(c(cache["img_memory"][:, ::3, ::8]), g["img_memory_slice"], **tol)
+    np.testing.assert_allclose(c(cache["text_memory_resized"]), g["text_memory_resized"], **tol)
+    # phase B outputs, all decoder layers
+    for k in ("pred_sub_logits", "pred_obj_logits", "pred_verb_logits", "pred_sub_boxes", "pred_obj_boxes"):
+        np.testing.assert_allclose(c(out[k]), g["out_" + k], **tol)
+        for i, a in enumerate(out["aux_outputs"]):
+            np.testing.assert_allclose(c(a[k]), g[f"aux{i}_" + k], **tol)
+    # matcher indices: bit-exact
+    layers = [{k: v for k, v in out.items() if k != "aux_outputs"}] + list(out["aux_outputs"])
+    for li, o in enumerate(layers):
+        for b, (i, j) in enumerate(criterion.matcher(o, targets)):
+            assert i.dtype == torch.int64 and j.dtype == torch.int64 and i.device.type == "cpu"
+            np.testing.assert_array_equal(i.numpy(), g[f"match{li}_{b}_i"])
+            np.testing.assert_array_equal(j.numpy(), g[f"match{li}_{b}_j"])
+    # losses: same keys, same values
+    gold_keys = sorted(k[len("loss_"):] for k in g if k.startswith("loss_"))
+    assert sorted(loss_dict.keys()) == gold_keys
+    for k, v in loss_dict.items():
+        np.testing.assert_allclose(float(v), float(g["loss_" + k]), rtol=1e-3, atol=1e-4, err_msg=k)
+    np.testing.assert_allclose(float(total), float(g["total_loss"]), rtol=1e-3)
+    # backward: gradient norms and strided samples of selected parameters
+    params = model.state_dict(keep_vars=True)
+    for k in GRAD_KEYS:
+        gk = params[k].grad
+        assert gk is not None, k
+        ref_norm = float(g["gradnorm_" + k])
+        np.testing.assert_allclose(float(gk.norm()), ref_norm, rtol=2e-3, atol=1e-6, err_msg=k)
+        flat = gk.detach().reshape(-1)
+        sample = c(flat[:: max(1, flat.numel() // 512)])
+        np.testing.assert_allclose(sample, g["grad_" + k], rtol=5e-3, atol=2e-3 * ref_norm / max(1.0, flat.numel() ** 0.5) + 1e-7,
+                                   err_msg=k)

@@ -9,7 +9,8 @@ import torch
 
 @torch.no_grad()
 def det_fill_(module, seed=0):
-    sd = module.state_dict()
+    """Fill every floating tensor of `module.state_dict()` (or of a plain dict name -> tensor)."""
+    sd = module if isinstance(module, dict) else module.state_dict()
     for name in sorted(sd.keys()):
         t = sd[name]
         if not t.is_floating_point():

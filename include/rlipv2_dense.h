@@ -1,0 +1,47 @@
+/*
+ * rlipv2_dense.h - C ABI of the tcgen05 (sm_100a tensor-core) dense contraction used by the
+ * ParSeDA hot path: y[M,N] = act(x[M,K] . W[N,K]^T + bias[N]).
+ *
+ * It replaces, for the `nn.Linear` calls of
+ *   /root/reference/models/fuse_helper.py:370-373,463-464            (ALIF projections)
+ *   /root/reference/models/modeling_roberta.py:159-165,252,318,332   (RobertaLayer)
+ *   /root/reference/models/dab_deformable/deformable_transformer.py:1283-1287,1368-1372 (FFNs)
+ *   /root/reference/models/ops/modules/ms_deform_attn.py:98,102,103,118 (MSDeformAttn projections)
+ * the cuBLAS SGEMM + bias + activation kernels torch launches (F.linear / F.relu / F.gelu).
+ *
+ * Conventions: device pointers to dense row-major fp32 arrays, 16-byte aligned; `stream` is a
+ * cudaStream_t passed as void*; asynchronous; returns 0, a positive cudaError_t, or RLIPV2_DENSE_E*.
+ * Products are TF32 (10-bit mantissa), accumulation fp32.  No CPU implementation exists.
+ */
+#ifndef RLIPV2_DENSE_H_
+#define RLIPV2_DENSE_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLIPV2_DENSE_ACT_NONE 0
+#define RLIPV2_DENSE_ACT_RELU 1
+#define RLIPV2_DENSE_ACT_GELU 2   /* exact erf GELU, as F.gelu / HF ACT2FN["gelu"] */
+
+#define RLIPV2_DENSE_EINVAL  (-1)
+#define RLIPV2_DENSE_ESHAPE  (-2)  /* needs N % 128 == 0 and K % 32 == 0 */
+#define RLIPV2_DENSE_EALIGN  (-3)
+#define RLIPV2_DENSE_EDRIVER (-4)
+
+/* 1 if (M, N, K) can run on the tcgen05 kernel, else 0 (callers route other shapes to cuBLAS) */
+int rlipv2_dense_linear_tf32_supported(int M, int N, int K);
+
+/* y = act(x . w^T + bias); x [M,K], w [N,K] (nn.Linear layout), bias [N] or NULL, y [M,N] */
+int rlipv2_dense_linear_tf32(const float *x, const float *w, const float *bias, float *y, int M, int N, int K,
+                             int act, void *stream);
+
+const char *rlipv2_dense_error_string(int code);
+
+/* kernels launched by this library in this process (for bench.py's gpu_launches) */
+unsigned long long rlipv2_dense_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLIPV2_DENSE_H_ */

@@ -24,6 +24,7 @@ NVCC_FLAGS = [
 # library name -> (sources, extra flags)
 TARGETS = {
     "librlipv2_msda.so": (["msda.cu"], []),
+    "librlipv2_dense.so": (["dense_tf32.cu"], []),
 }
 
 

@@ -1,0 +1,309 @@
+// dense_tf32.cu - y = act(x . W^T + bias) on the 5th-generation tensor cores (tcgen05), sm_100a.
+//
+// The dense contractions of the ParSeDA hot path are `nn.Linear`s on fp32 activations:
+//   ALIF projections   /root/reference/models/fuse_helper.py:370-373, 463-464  (256|768 <-> 2048)
+//   RobertaLayer       models/modeling_roberta.py:159-235, 252-256, 318-336    (768 <-> 768|3072)
+//   deformable FFN     models/dab_deformable/deformable_transformer.py:1283-1287 (256 <-> 2048)
+//   MSDeformAttn proj  models/ops/modules/ms_deform_attn.py:98-118             (256 -> 256|128)
+// x is [M, K] row-major, W is nn.Linear's [N, K] row-major: both operands are K-major, the native
+// layout of tcgen05.mma.  Products are TF32 (10-bit mantissa, what the reference's pinned torch 1.10
+// computes by default on tensor-core GPUs), accumulation is fp32 in tensor memory.
+//
+// Kernel structure (one 128 x BLOCK_N output tile per CTA, 6 warps):
+//   warp 0 / lane 0   TMA producer: cp.async.bulk.tensor 2-D loads of a 128x32 (A) and BLOCK_Nx32 (B)
+//                     fp32 box per stage into 128B-swizzled shared memory, mbarrier expect_tx
+//   warp 1            allocates BLOCK_N TMEM columns; lane 0 issues 4 x tcgen05.mma.kind::tf32
+//                     (M=128, N=BLOCK_N, K=8) per stage, tcgen05.commit frees the stage / signals
+//                     the epilogue
+//   warps 2-5         epilogue: tcgen05.ld 32 lanes x 32 columns at a time (warp w owns TMEM lane
+//                     quadrant w % 4), + bias, ReLU / exact GELU, vectorised global stores
+// STAGES-deep full/empty mbarrier ring between producer and MMA issuer.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "rlipv2_dense.h"
+
+namespace {
+
+std::atomic<unsigned long long> g_launches{0};
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 32;                 // 32 fp32 = 128 bytes = one swizzle-128B row
+constexpr int kUmmaK = 8;                   // tf32: 32 bytes per MMA K-step
+constexpr int kThreads = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+// K-major, 128-byte swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 | LBO(1)<<16 | SBO(1024>>4)<<32 | version 1<<46 | SWIZZLE_128B(2)<<61)
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+template <int BLOCK_N>
+struct SmemLayout {
+    static constexpr int kABytes = kBlockM * kBlockK * 4;        // 16 KB
+    static constexpr int kBBytes = BLOCK_N * kBlockK * 4;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+};
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1)<<4, a/b format TF32 (2)<<7 / <<10,
+// a/b K-major (0), n_dim = N>>3 at bit 17, m_dim = M>>4 at bit 24
+template <int BLOCK_N>
+__host__ __device__ constexpr uint32_t make_idesc() {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+template <int BLOCK_N, int STAGES, int ACT>
+__global__ void __launch_bounds__(kThreads, 1)
+linear_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                   const float *__restrict__ bias, float *__restrict__ C, int M, int N, int K)
+{
+    using L = SmemLayout<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    // 128B-swizzled TMA/UMMA tiles need a 1024-byte aligned base (aligned in the shared window)
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * L::kStageBytes);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tmem_full_bar = empty_bar + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_blk = blockIdx.x, m_blk = blockIdx.y;
+    const int num_k = K / kBlockK;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tm_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tm_b) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {      // whole warp: allocate the accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(BLOCK_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                   // ---- TMA producer
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], L::kStageBytes);
+                uint8_t *sa = smem + s * L::kStageBytes;
+                tma_load_2d(sa, &tm_a, &full_bar[s], kb * kBlockK, m_blk * kBlockM);
+                tma_load_2d(sa + L::kABytes, &tm_b, &full_bar[s], kb * kBlockK, n_blk * BLOCK_N);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                   // ---- MMA issuer
+            constexpr uint32_t idesc = make_idesc<BLOCK_N>();
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(smem + s * L::kStageBytes);
+                const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                    // advancing K inside the swizzle atom = advancing the start address by 32 bytes
+                    umma_tf32(tmem_base, umma_desc_k_sw128(sa + k * kUmmaK * 4), umma_desc_k_sw128(sb + k * kUmmaK * 4),
+                              idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);                // stage reusable once these MMAs retire
+            }
+            umma_commit(tmem_full_bar);                    // accumulator complete
+        }
+    } else {                                               // ---- epilogue warps 2..5
+        mbar_wait(tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;                            // TMEM lane quadrant this warp may read
+        const int row = m_blk * kBlockM + q * 32 + lane;
+        float *crow = C + (size_t)row * N + (size_t)n_blk * BLOCK_N;
+        const float *brow = bias ? bias + (size_t)n_blk * BLOCK_N : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                       __uint_as_float(r[j + 3]));
+                if (brow) {
+                    const float4 b = __ldg(reinterpret_cast<const float4 *>(brow + c * 32 + j));
+                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                }
+                if (ACT == RLIPV2_DENSE_ACT_RELU) {
+                    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                } else if (ACT == RLIPV2_DENSE_ACT_GELU) {
+                    o.x = gelu_exact(o.x); o.y = gelu_exact(o.y); o.z = gelu_exact(o.z); o.w = gelu_exact(o.w);
+                }
+                if (row < M) *reinterpret_cast<float4 *>(crow + c * 32 + j) = o;
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(BLOCK_N) : "memory");
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] row-major, box = [box_rows, 32 cols], 128-byte swizzle, zero fill out of bounds
+int make_map(CUtensorMap *map, const float *ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return RLIPV2_DENSE_EDRIVER;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : RLIPV2_DENSE_EDRIVER;
+}
+
+template <int BLOCK_N, int STAGES, int ACT>
+int launch(const CUtensorMap &ta, const CUtensorMap &tb, const float *bias, float *y, int M, int N, int K,
+           cudaStream_t stream) {
+    using L = SmemLayout<BLOCK_N>;
+    constexpr int smem = STAGES * L::kStageBytes + (2 * STAGES + 1) * 8 + 16 + 1024;
+    auto kern = linear_tf32_kernel<BLOCK_N, STAGES, ACT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    dim3 grid(N / BLOCK_N, (M + kBlockM - 1) / kBlockM, 1);
+    kern<<<grid, kThreads, smem, stream>>>(ta, tb, bias, y, M, N, K);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" {
+
+int rlipv2_dense_linear_tf32_supported(int M, int N, int K)
+{
+    return (M > 0 && N > 0 && K > 0 && (N % 128) == 0 && (K % kBlockK) == 0) ? 1 : 0;
+}
+
+int rlipv2_dense_linear_tf32(const float *x, const float *w, const float *bias, float *y, int M, int N, int K,
+                             int act, void *stream)
+{
+    if (M == 0) return 0;
+    if (!rlipv2_dense_linear_tf32_supported(M, N, K)) return RLIPV2_DENSE_ESHAPE;
+    if (!x || !w || !y) return RLIPV2_DENSE_EINVAL;
+    if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y | (uintptr_t)bias) & 15) return RLIPV2_DENSE_EALIGN;
+    CUtensorMap ta, tb;
+    int rc = make_map(&ta, x, (uint64_t)M, (uint64_t)K, kBlockM);
+    if (rc) return rc;
+    rc = make_map(&tb, w, (uint64_t)N, (uint64_t)K, 128);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (act) {
+        case RLIPV2_DENSE_ACT_NONE: return launch<128, 6, RLIPV2_DENSE_ACT_NONE>(ta, tb, bias, y, M, N, K, s);
+        case RLIPV2_DENSE_ACT_RELU: return launch<128, 6, RLIPV2_DENSE_ACT_RELU>(ta, tb, bias, y, M, N, K, s);
+        case RLIPV2_DENSE_ACT_GELU: return launch<128, 6, RLIPV2_DENSE_ACT_GELU>(ta, tb, bias, y, M, N, K, s);
+        default: return RLIPV2_DENSE_EINVAL;
+    }
+}
+
+const char *rlipv2_dense_error_string(int code)
+{
+    switch (code) {
+        case 0: return "success";
+        case RLIPV2_DENSE_EINVAL: return "rlipv2_dense: invalid argument";
+        case RLIPV2_DENSE_ESHAPE: return "rlipv2_dense: shape not supported by the tcgen05 kernel (N % 128, K % 32)";
+        case RLIPV2_DENSE_EALIGN: return "rlipv2_dense: pointers must be 16-byte aligned";
+        case RLIPV2_DENSE_EDRIVER: return "rlipv2_dense: cuTensorMapEncodeTiled unavailable or failed";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "rlipv2_dense: unknown error";
+    }
+}
+
+unsigned long long rlipv2_dense_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

@@ -2,21 +2,28 @@
 
 Every GEMM-shaped op of ALIF, the RobertaLayer stack and the deformable encoder/decoder FFNs goes
 through these functions, so the module code stays independent of how the contraction is executed.
-Round 1 routes them to cuBLAS/cuDNN through torch (fp32 or TF32, see `set_matmul_precision`);
-the hand-written tcgen05 kernels replace the bodies without touching the callers.
+
+Two execution modes (`set_matmul_precision`):
+  'fp32'  IEEE fp32 products through cuBLAS - used by the parity tests against the reference fixtures;
+  'tf32'  TF32 tensor-core products, fp32 accumulation - what the reference's pinned torch 1.10 does by
+          default on tensor-core GPUs.  Forward linears whose shape the hand-written tcgen05 kernel
+          supports (N % 128 == 0, K % 32 == 0; csrc/dense_tf32.cu, include/rlipv2_dense.h) run on it with
+          bias / ReLU fused in the epilogue; their backward GEMMs and the remaining shapes are cuBLAS
+          TF32 (round-1 state).
+There is no CPU implementation behind the tcgen05 path; CPU tensors only ever reach the torch ops.
 """
 import torch
 import torch.nn.functional as F
 
 _PRECISION = "fp32"
+_USE_TCGEN05 = True
 
 
-def set_matmul_precision(mode: str):
-    """'fp32' = IEEE fp32 SGEMM (parity tests); 'tf32' = TF32 tensor-core products with fp32
-    accumulation (what torch 1.10, the reference's pinned version, did by default on Ampere+)."""
-    global _PRECISION
+def set_matmul_precision(mode: str, tcgen05: bool = True):
+    global _PRECISION, _USE_TCGEN05
     assert mode in ("fp32", "tf32")
     _PRECISION = mode
+    _USE_TCGEN05 = tcgen05
     torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
     torch.backends.cudnn.allow_tf32 = mode == "tf32"
 
@@ -25,15 +32,67 @@ def matmul_precision():
     return _PRECISION
 
 
+def _abi():
+    from . import dense_abi
+    return dense_abi
+
+
+class _LinearTF32(torch.autograd.Function):
+    """y = act(x W^T + b) on the tcgen05 kernel; backward = cuBLAS TF32 GEMMs + fused mask."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        abi = _abi()
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        w = weight if weight.is_contiguous() else weight.contiguous()
+        y = abi.linear_tf32(x2, w, bias, act)
+        ctx.act = act
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x2, w, y if act == abi.ACT_RELU else None)
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x2, w, y = ctx.saved_tensors
+        g = grad_out.reshape(-1, grad_out.shape[-1])
+        if y is not None:
+            g = g * (y > 0)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = (g @ w).view(*grad_out.shape[:-1], w.shape[1])
+        if ctx.needs_input_grad[1]:
+            gw = g.t() @ x2
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g.sum(0)
+        return gx, gw, gb, None
+
+
+def _tcgen05_ok(x, weight):
+    if not (_USE_TCGEN05 and _PRECISION == "tf32" and x.is_cuda and x.dtype == torch.float32):
+        return False
+    M = x.numel() // x.shape[-1]
+    return M > 0 and _abi().supported(M, weight.shape[0], weight.shape[1])
+
+
 def linear(x, weight, bias=None):
+    if _tcgen05_ok(x, weight):
+        return _LinearTF32.apply(x, weight, bias, 0)
     return F.linear(x, weight, bias)
 
 
 def linear_relu(x, weight, bias=None):
+    if _tcgen05_ok(x, weight):
+        return _LinearTF32.apply(x, weight, bias, 1)
     return F.relu(F.linear(x, weight, bias))
 
 
 def linear_gelu(x, weight, bias=None):
+    if _tcgen05_ok(x, weight):
+        if not (torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad)):
+            return _LinearTF32.apply(x, weight, bias, 2)
+        return F.gelu(_LinearTF32.apply(x, weight, bias, 0))     # GELU backward needs the pre-activation
     return F.gelu(F.linear(x, weight, bias))
 
 

@@ -1,0 +1,88 @@
+"""GPU tests of the tcgen05 TF32 linear (csrc/dense_tf32.cu) through its C ABI.
+
+Checker: an fp64 torch reference.  Tolerance: each TF32 product carries <= 2^-10 relative error (10-bit
+mantissa operands), accumulation is fp32, so |y - y_ref| <= 1.5e-3 * (|x| . |W|^T + |b|) element-wise
+(north_star: 1e-3 rel fp32 *with* TF32 tensor-core products being the reference's own arithmetic)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(x, w, b, act):
+    y = x.double() @ w.double().t()
+    if b is not None:
+        y = y + b.double()
+    if act == 1:
+        y = torch.relu(y)
+    elif act == 2:
+        y = torch.nn.functional.gelu(y)
+    bound = x.double().abs() @ w.double().abs().t() + (b.double().abs() if b is not None else 0)
+    return y, bound
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (546, 2048, 256), (512, 768, 3072), (512, 3072, 768),
+                                   (1000, 256, 2048), (44446, 2048, 256), (37, 128, 256), (300, 256, 512)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_linear_tf32_matches_fp64(M, N, K, act):
+    from rlipv2_b200 import dense_abi
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + act)
+    x = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) * K ** -0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    assert dense_abi.supported(M, N, K)
+    y = dense_abi.linear_tf32(x, w, b, act)
+    ref, bound = _ref(x, w, b, act)
+    err = (y.double() - ref).abs()
+    assert torch.isfinite(y).all()
+    assert bool((err <= 1.5e-3 * bound + 1e-5).all()), f"max err {float(err.max())}, max ratio {float((err / (bound + 1e-9)).max())}"
+    y2 = dense_abi.linear_tf32(x, w, None, 0)
+    ref2, bound2 = _ref(x, w, None, 0)
+    assert bool(((y2.double() - ref2).abs() <= 1.5e-3 * bound2 + 1e-5).all())
+
+
+def test_unsupported_shapes_are_reported_not_silently_rerouted():
+    from rlipv2_b200 import dense_abi
+    assert not dense_abi.supported(64, 100, 256)
+    assert not dense_abi.supported(64, 128, 40)
+    x = torch.randn(64, 256, device="cuda")
+    w = torch.randn(100, 256, device="cuda")
+    with pytest.raises(RuntimeError, match="shape not supported"):
+        dense_abi.linear_tf32(x, w, None, 0)
+
+
+def test_autograd_through_dense_seam_tf32():
+    from rlipv2_b200 import dense
+    dense.set_matmul_precision("tf32")
+    try:
+        g = torch.Generator(device="cuda").manual_seed(0)
+        x = torch.randn(3, 50, 256, device="cuda", generator=g, requires_grad=True)
+        w = (torch.randn(2048, 256, device="cuda", generator=g) / 16).requires_grad_(True)
+        b = torch.randn(2048, device="cuda", generator=g, requires_grad=True)
+        n0 = __import__("rlipv2_b200.dense_abi", fromlist=["x"]).launch_count()
+        y = dense.linear_relu(x, w, b)
+        assert __import__("rlipv2_b200.dense_abi", fromlist=["x"]).launch_count() == n0 + 1
+        y.square().sum().backward()
+        xr, wr, br = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+        yr = torch.relu(xr @ wr.t() + br)
+        yr.square().sum().backward()
+        for a, r in ((x.grad, xr.grad), (w.grad, wr.grad), (b.grad, br.grad)):
+            assert float((a.double() - r).norm() / r.norm()) < 3e-3
+    finally:
+        dense.set_matmul_precision("fp32")
+
+
+def test_full_step_tf32_close_to_fp32_golden():
+    """End-to-end sanity in the benchmark's arithmetic: TF32 tensor-core products (tcgen05 linears +
+    cuBLAS TF32) against the fp32 golden fixture, looser tolerance."""
+    import numpy as np
+    from rlipv2_b200 import dense
+    from tests import test_parseda_model as t
+    dense.set_matmul_precision("tf32")
+    try:
+        g, model, criterion, cache, out, loss_dict, total, targets, _ = t._run_step("cuda")
+    finally:
+        dense.set_matmul_precision("fp32")
+    for k in ("pred_obj_logits", "pred_verb_logits", "pred_sub_boxes", "pred_obj_boxes"):
+        np.testing.assert_allclose(out[k].detach().cpu().numpy(), g["out_" + k], rtol=3e-2, atol=3e-2)
+    np.testing.assert_allclose(float(total), float(g["total_loss"]), rtol=2e-2)

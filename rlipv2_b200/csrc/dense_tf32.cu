@@ -16,8 +16,10 @@
 //                     (M=128, N=BLOCK_N, K=8) per stage, tcgen05.commit frees the stage / signals
 //                     the epilogue
 //   warps 2-5         epilogue: tcgen05.ld 32 lanes x 32 columns at a time (warp w owns TMEM lane
-//                     quadrant w % 4), + bias, ReLU / exact GELU, vectorised global stores
-// STAGES-deep full/empty mbarrier ring between producer and MMA issuer.
+//                     quadrant w % 4), + bias, ReLU / exact GELU, transposed through shared memory
+//                     so that every global store instruction writes whole 128-byte row segments
+// STAGES-deep full/empty mbarrier ring between producer and MMA issuer; 3 stages (96 KB) so that two
+// CTAs share an SM and one CTA's epilogue overlaps the other's main loop.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -102,7 +104,7 @@ __host__ __device__ constexpr uint32_t make_idesc() {
 }
 
 template <int BLOCK_N, int STAGES, int ACT>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 linear_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const float *__restrict__ bias, float *__restrict__ C, int M, int N, int K)
 {
@@ -171,9 +173,13 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         mbar_wait(tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;                            // TMEM lane quadrant this warp may read
-        const int row = m_blk * kBlockM + q * 32 + lane;
-        float *crow = C + (size_t)row * N + (size_t)n_blk * BLOCK_N;
-        const float *brow = bias ? bias + (size_t)n_blk * BLOCK_N : nullptr;
+        // Staging area for coalesced stores: 32 rows x 36 floats per warp.  It aliases pipeline stage
+        // 0, which is idle by now: tmem_full_bar fires only after every MMA (hence every smem read)
+        // has retired and the producer has no load left to issue.
+        float *stage_out = reinterpret_cast<float *>(smem) + (warp - 2) * (32 * 36);
+        const int sub = lane & 7, rgrp = lane >> 3;
+        const size_t col0 = (size_t)n_blk * BLOCK_N;
+        const float *brow = bias ? bias + col0 : nullptr;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
             uint32_t r[32];
@@ -188,6 +194,8 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // thread `lane` holds row (q*32 + lane), columns c*32 .. c*32+31: bias + activation, then
+            // transpose through shared memory so that 8 lanes write one 128-byte row segment
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
@@ -201,8 +209,18 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 } else if (ACT == RLIPV2_DENSE_ACT_GELU) {
                     o.x = gelu_exact(o.x); o.y = gelu_exact(o.y); o.z = gelu_exact(o.z); o.w = gelu_exact(o.w);
                 }
-                if (row < M) *reinterpret_cast<float4 *>(crow + c * 32 + j) = o;
+                *reinterpret_cast<float4 *>(stage_out + lane * 36 + j) = o;
             }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + rgrp;
+                const float4 v = *reinterpret_cast<const float4 *>(stage_out + rr * 36 + sub * 4);
+                const int grow = m_blk * kBlockM + q * 32 + rr;
+                if (grow < M)
+                    *reinterpret_cast<float4 *>(C + (size_t)grow * N + col0 + c * 32 + sub * 4) = v;
+            }
+            __syncwarp();
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
@@ -285,9 +303,9 @@ int rlipv2_dense_linear_tf32(const float *x, const float *w, const float *bias, 
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     switch (act) {
-        case RLIPV2_DENSE_ACT_NONE: return launch<128, 6, RLIPV2_DENSE_ACT_NONE>(ta, tb, bias, y, M, N, K, s);
-        case RLIPV2_DENSE_ACT_RELU: return launch<128, 6, RLIPV2_DENSE_ACT_RELU>(ta, tb, bias, y, M, N, K, s);
-        case RLIPV2_DENSE_ACT_GELU: return launch<128, 6, RLIPV2_DENSE_ACT_GELU>(ta, tb, bias, y, M, N, K, s);
+        case RLIPV2_DENSE_ACT_NONE: return launch<128, 3, RLIPV2_DENSE_ACT_NONE>(ta, tb, bias, y, M, N, K, s);
+        case RLIPV2_DENSE_ACT_RELU: return launch<128, 3, RLIPV2_DENSE_ACT_RELU>(ta, tb, bias, y, M, N, K, s);
+        case RLIPV2_DENSE_ACT_GELU: return launch<128, 3, RLIPV2_DENSE_ACT_GELU>(ta, tb, bias, y, M, N, K, s);
         default: return RLIPV2_DENSE_EINVAL;
     }
 }

@@ -169,30 +169,43 @@ def msda_roofline(device):
 # workload: full train step
 # ------------------------------------------------------------------------------------------------
 def run_train_step(args, rank, world, device):
-    from rlipv2_b200 import dense, msda_abi, train_step
-    ts = train_step.ParSeDATrainStep(device=str(device), precision=args.precision, seed=0)
+    from rlipv2_b200 import dense, dense_abi, msda_abi, train_step
     text = train_step.synthetic_text(170, 85)
     images_h, targets_h = train_step.synthetic_batch(BATCH, 800, 1333, seed=rank)
-    samples, targets = ts.to_device(images_h, targets_h)
+    own = lambda: msda_abi.launch_count() + dense_abi.launch_count()
     loss = None
+    if args.graphs:
+        ts = train_step.GraphedParSeDATrainStep(device=str(device), precision=args.precision, seed=0)
+        l0 = own()
+        ts.capture(images_h, targets_h, text, warmup=max(1, args.warmup - 1))
+        per_step = (own() - l0) // (max(1, args.warmup - 1) + 3)     # probe + warm-ups + 2 captures record one step each
 
-    def step(i):
-        nonlocal loss
-        loss = ts.step_device(samples, targets, text)
+        def step(i):
+            nonlocal loss
+            loss = ts.replay()
+
+        def e2e(i):
+            float(ts.step(images_h, targets_h))             # H2D inside, loss read back (4 bytes D2H)
+    else:
+        ts = train_step.ParSeDATrainStep(device=str(device), precision=args.precision, seed=0)
+        samples, targets = ts.to_device(images_h, targets_h)
+        per_step = None
+
+        def step(i):
+            nonlocal loss
+            loss = ts.step_device(samples, targets, text)
+
+        def e2e(i):
+            float(ts.step(images_h, targets_h, text))
 
     for i in range(args.warmup):
         step(i)
-    l0 = msda_abi.launch_count()
+    l0 = own()
     with ClockSampler(device.index) as clk:
         ms = timed(step, args.steps, world)
-    launches = msda_abi.launch_count() - l0
+    launches = per_step * args.steps if per_step is not None else own() - l0
     final_loss = float(loss)
-
     h2d = images_h.numel() * 4 + sum(v.numel() * v.element_size() for t in targets_h for v in t.values())
-
-    def e2e(i):
-        float(ts.step(images_h, targets_h, text))          # H2D inside, loss read back (4 bytes D2H)
-
     e2e(0)
     n_e2e = max(2, min(args.steps, 5))
     ms_e2e = timed(e2e, n_e2e, world)
@@ -207,13 +220,15 @@ def run_train_step(args, rank, world, device):
                                "per GPU, 300 queries, 256 label strings, AdamW, clip 0.1, random-init weights",
                    "per_gpu_batch": BATCH, "global_batch": BATCH * world, "trainable_params": nparams,
                    "l2": "working set >> L2 (activations > 2 GB per image)",
-                   "parallelism": f"dp{world} (DDP static_graph, NCCL)" if world > 1 else "dp1"},
+                   "execution": "2 CUDA graphs per step + host LSAP" if args.graphs else "eager",
+                   "parallelism": (f"dp{world} (flat-gradient NCCL all-reduce in graph)" if args.graphs else
+                                   f"dp{world} (DDP static_graph, NCCL)") if world > 1 else "dp1"},
         "clocks": clk.summary(), "gpu_launches": int(launches), "final_loss": final_loss,
         "e2e": {"value": BATCH * world / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
     }
     if rank == 0:
-        del ts, samples, targets
+        del ts, step, e2e
         torch.cuda.empty_cache()
         line["roofline"] = msda_roofline(device)
     return line
@@ -285,6 +300,7 @@ def main():
     ap.add_argument("--workload", default="train_step", choices=["train_step", "msda_step"])
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", dest="graphs", action="store_false", help="eager step instead of CUDA graphs")
     args = ap.parse_args()
     rank, world, local = dist_info()
 

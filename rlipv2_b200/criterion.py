@@ -90,7 +90,7 @@ class SetCriterionHOI(nn.Module):
         idx = self._src_idx(indices)
         matched = torch.cat([t[key][J] for t, (_, J) in zip(targets, indices)])
         classes = torch.full(logits.shape[:2], logits.shape[-1] - 1, dtype=torch.int64, device=logits.device)
-        classes[idx] = matched.to(logits.device)
+        classes[idx] = matched
         return F.cross_entropy(logits.transpose(1, 2), classes, w), idx, matched
 
     # ---- losses -----------------------------------------------------------------------------------
@@ -111,21 +111,26 @@ class SetCriterionHOI(nn.Module):
     @torch.no_grad()
     def loss_obj_cardinality(self, outputs, targets, indices, num_interactions):
         pred_logits = outputs["pred_obj_logits"]
-        tgt_lengths = torch.as_tensor([len(v["obj_labels"]) for v in targets], device=pred_logits.device)
+        tgt_lengths = torch.cat([torch.full((1,), float(len(v["obj_labels"])), device=pred_logits.device)
+                                 for v in targets])
         card_pred = (pred_logits.argmax(-1) != pred_logits.shape[-1] - 1).sum(1)
         return {"obj_cardinality_error": F.l1_loss(card_pred.float(), tgt_lengths.float())}
 
-    def loss_verb_labels(self, outputs, targets, indices, num_interactions):
+    def loss_verb_labels(self, outputs, targets, indices, num_interactions, cost_list=None):
         src_logits = outputs["pred_verb_logits"]
         idx = self._src_idx(indices)
         if self.giou_verb_label:
-            # soft targets: matched verb labels scaled by (GIoU + 1) / 2 of the matched pair (hoi.py:3932-3957)
-            _, cost_list = self.matcher(outputs, targets, return_cost=True)
+            # soft targets: matched verb labels scaled by (GIoU + 1) / 2 of the matched pair (hoi.py:3932-3957).
+            # The reference re-runs the matcher here (device cost build + D2H + scipy) only to read
+            # cost_giou; the costs are a pure function of (outputs, targets), so the list computed for
+            # this layer's match is reused when the caller has it.
+            if cost_list is None:
+                _, cost_list = self.matcher.compute_costs(outputs, targets)
             giou = -cost_list[0]
             q0 = t0 = 0
             soft = []
             for t, (I, J) in zip(targets, indices):
-                s = (giou[q0 + I.to(giou.device), t0 + J.to(giou.device)] + 1) / 2
+                s = (giou[q0 + I, t0 + J] + 1) / 2
                 labels = t["verb_labels"][J]
                 if self.pseudo_verb:
                     labels = labels + outputs["target_verb_sim"][t0 + J]
@@ -190,22 +195,33 @@ class SetCriterionHOI(nn.Module):
         assert loss in fn, f"do you really want to compute {loss} loss?"
         return fn[loss](outputs, targets, indices, num, **kwargs)
 
-    def forward(self, outputs, targets):
-        outputs_without_aux = {k: v for k, v in outputs.items() if k != "aux_outputs"}
-        indices = self.matcher(outputs_without_aux, targets)
+    def layers_of(self, outputs):
+        """[final-layer outputs, aux layer 0, aux layer 1, ...] in the order forward() matches them."""
+        return [{k: v for k, v in outputs.items() if k != "aux_outputs"}] + list(outputs.get("aux_outputs", []))
+
+    def forward(self, outputs, targets, matches=None):
+        """`matches`: optional list (one entry per decoder layer, order of `layers_of`) of
+        (indices, cost_list) computed by the caller - the CUDA-graph step computes the costs in the
+        forward graph, solves the assignment on the host and passes device index tensors here."""
+        layers = self.layers_of(outputs)
         device = next(iter(outputs.values())).device
-        num_interactions = torch.as_tensor([sum(len(t["obj_labels"]) for t in targets)], dtype=torch.float,
-                                           device=device)
+        num_interactions = torch.full((1,), float(sum(len(t["obj_labels"]) for t in targets)), device=device)
         if _world() > 1:
             dist.all_reduce(num_interactions)
         num_interactions = torch.clamp(num_interactions / _world(), min=1)     # stays on the device
         losses = {}
-        for loss in self.losses:
-            losses.update(self.get_loss(loss, outputs, targets, indices, num_interactions))
-        for i, aux in enumerate(outputs.get("aux_outputs", [])):
-            indices = self.matcher(aux, targets)
+        for li, layer in enumerate(layers):
+            if matches is not None:
+                indices, cost_list = matches[li]
+            else:
+                indices, cost_list = self.matcher(layer, targets, return_cost=True)
+            sfx = "" if li == 0 else f"_{li - 1}"
             for loss in self.losses:
-                kwargs = {"log": False} if loss == "obj_labels" else {}
-                l_dict = self.get_loss(loss, aux, targets, indices, num_interactions, **kwargs)
-                losses.update({k + f"_{i}": v for k, v in l_dict.items()})
+                kwargs = {}
+                if loss == "obj_labels" and li > 0:
+                    kwargs["log"] = False
+                if loss == "verb_labels":
+                    kwargs["cost_list"] = cost_list
+                l_dict = self.get_loss(loss, layer, targets, indices, num_interactions, **kwargs)
+                losses.update({k + sfx: v for k, v in l_dict.items()})
         return {k: (v.reshape(()) if v.numel() == 1 else v) for k, v in losses.items()}

@@ -49,6 +49,19 @@ class HungarianMatcherHOI(nn.Module):
 
     @torch.no_grad()
     def forward(self, outputs, targets, return_cost=False):
+        C, cost_list = self.compute_costs(outputs, targets)
+        indices = self.solve(C.cpu(), [len(v["obj_labels"]) for v in targets])   # the one device->host copy
+        return (indices, cost_list) if return_cost else indices
+
+    @staticmethod
+    def solve(C_cpu, sizes):
+        """scipy LSAP per image on the host copy of the cost tensor [bs, nq, sum(sizes)] (matcher.py:187-193)."""
+        indices = [linear_sum_assignment(c[i]) for i, c in enumerate(C_cpu.split(sizes, -1))]
+        return [(torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)) for i, j in indices]
+
+    @torch.no_grad()
+    def compute_costs(self, outputs, targets):
+        """Device part (capturable in a CUDA graph): -> (C [bs, nq, T], cost_list as matcher.py:197-199)."""
         bs, num_queries = outputs["pred_obj_logits"].shape[:2]
         out_obj_prob = outputs["pred_obj_logits"].flatten(0, 1).softmax(-1)
         out_verb_prob = outputs["pred_verb_logits"].flatten(0, 1).sigmoid()
@@ -95,17 +108,11 @@ class HungarianMatcherHOI(nn.Module):
         else:
             C = self.cost_obj_class * cost_obj_class + self.cost_verb_class * cost_verb_class + \
                 self.cost_bbox * cost_bbox + self.cost_giou * cost_giou
-        C = C.view(bs, num_queries, -1).cpu()                                # the one device->host copy
-
-        sizes = [len(v["obj_labels"]) for v in targets]
-        indices = [linear_sum_assignment(c[i]) for i, c in enumerate(C.split(sizes, -1))]
-        indices = [(torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)) for i, j in indices]
-        if not return_cost:
-            return indices
+        C = C.view(bs, num_queries, -1)
         cost_list = [cost_giou, (cost_sub_giou, cost_obj_giou), cost_bbox, (cost_sub_bbox, cost_obj_bbox),
                      cost_verb_class]
         cost_list += [cost_sub_class, cost_obj_class] if self.subject_class else [cost_obj_class]
-        return indices, cost_list
+        return C, cost_list
 
 
 def build_matcher(args):

@@ -36,6 +36,22 @@ from .roberta_layer import RobertaLayer
 from .text_encoder import build_text_encoder
 
 
+_LEVEL_CACHE = {}
+
+
+def _level_tensors(shapes_host, device):
+    """(spatial_shapes [L,2], level_start_index [L]) int64 device tensors, cached per shape set: they are
+    constants of the image size, and creating them per call costs two pageable H2D copies."""
+    key = (shapes_host, str(device))
+    if key not in _LEVEL_CACHE:
+        starts = [0]
+        for h, w in shapes_host[:-1]:
+            starts.append(starts[-1] + h * w)
+        _LEVEL_CACHE[key] = (torch.as_tensor(shapes_host, dtype=torch.long, device=device),
+                             torch.as_tensor(starts, dtype=torch.long, device=device))
+    return _LEVEL_CACHE[key]
+
+
 def _get_clones(module, n):
     return nn.ModuleList([copy.deepcopy(module) for _ in range(n)])
 
@@ -401,17 +417,26 @@ class RLIP_ParSeDABDeformableTransformer_v2(nn.Module):
         return torch.stack([valid_W.float() / W, valid_H.float() / H], -1)
 
     # ---- text ---------------------------------------------------------------------------------
-    def encode_text(self, text, device):
-        """label strings -> pooled RoBERTa vectors, padded per image (:489-522).
-        -> text_memory [n_text, n_tuples, 768], text_attention_mask [n_text, n_tuples] (True = pad),
-           obj_pred_names_sums [n_tuples, 2]"""
+    def tokenize(self, text, device):
+        """Host part of the text path: label strings -> token ids on the device (:489-497).  Returns a
+        dict that `forward(text=...)` accepts in place of the raw strings, so a caller can tokenise
+        once outside a CUDA graph."""
         sums, flat = [], []
         for obj_names, pred_names in text:
             sums.append((len(obj_names), len(pred_names)))
             flat += list(obj_names) + list(pred_names)
+        tok = self.tokenizer.batch_encode_plus(flat, padding="longest", return_tensors="pt")
+        return {"input_ids": tok["input_ids"].to(device), "attention_mask": tok["attention_mask"].to(device),
+                "sums": sums}
+
+    def encode_text(self, text, device):
+        """label strings -> pooled RoBERTa vectors, padded per image (:489-522).
+        -> text_memory [n_text, n_tuples, 768], text_attention_mask [n_text, n_tuples] (True = pad),
+           obj_pred_names_sums [n_tuples, 2]"""
+        tok = text if isinstance(text, dict) else self.tokenize(text, device)
+        sums = tok["sums"]
         obj_pred_names_sums = torch.tensor(sums)
-        tok = self.tokenizer.batch_encode_plus(flat, padding="longest", return_tensors="pt").to(device)
-        pooled = self.text_encoder(**tok).pooler_output
+        pooled = self.text_encoder(input_ids=tok["input_ids"], attention_mask=tok["attention_mask"]).pooler_output
         i, objs, preds = 0, [], []
         for n_obj, n_pred in sums:
             objs.append(pooled[i:i + n_obj])
@@ -443,14 +468,10 @@ class RLIP_ParSeDABDeformableTransformer_v2(nn.Module):
         mask_flatten = torch.cat(mask_flatten, 1)
         lvl_pos_flatten = torch.cat(lvl_pos_flatten, 1)
         device = src_flatten.device
-        spatial_shapes = torch.as_tensor(shapes_host, dtype=torch.long, device=device)
-        starts = [0]
-        for h, w in shapes_host[:-1]:
-            starts.append(starts[-1] + h * w)
-        level_start_index = torch.as_tensor(starts, dtype=torch.long, device=device)
+        spatial_shapes, level_start_index = _level_tensors(tuple(shapes_host), device)
         valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
 
-        if isinstance(text, list) and isinstance(text[0], tuple):          # training: raw label strings
+        if isinstance(text, dict) or (isinstance(text, list) and isinstance(text[0], tuple)):   # training: label strings
             text_memory, text_attention_mask, obj_pred_names_sums = self.encode_text(text, device)
             lang = text_memory
             if lang.shape[1] != bs:

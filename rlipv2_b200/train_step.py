@@ -101,3 +101,152 @@ class ParSeDATrainStep:
     def step(self, images_host, targets_host, text):
         samples, targets = self.to_device(images_host, targets_host)
         return self.step_device(samples, targets, text)
+
+
+class GraphedParSeDATrainStep(ParSeDATrainStep):
+    """The same optimisation step replayed from two CUDA graphs (the reference's step is launch-bound:
+    ~7000 kernels and ~100 ms of host time per step at batch 2, engine.py:99-172).
+
+        graph A   forward (phase A + phase B) + the matcher's cost tensors for the 3 decoder layers,
+                  copied to pinned host memory
+        host      scipy linear_sum_assignment per layer and image (models/matcher.py:193) - the only
+                  host work left in the step; indices go back into static device buffers
+        graph B   SetCriterionHOI from the static indices -> backward -> (NCCL all-reduce of the flat
+                  gradient buffer when world > 1) -> clip_grad_norm_(0.1) -> fused AdamW
+
+    Shapes are static: image size, label count and the number of target triplets per image are fixed at
+    capture time (re-capture for a new shape bucket).  Gradients live as views of one flat buffer, so
+    data-parallel training needs exactly one all-reduce per step and no DDP wrapper; parameters that
+    never receive a gradient (the verb decoder's detached box heads) are left out of the optimizer,
+    which is what the reference's `find_unused_parameters=True` + grad-is-None skip amounts to.
+    """
+
+    def __init__(self, *a, **kw):
+        kw["ddp"] = False
+        super().__init__(*a, **kw)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.captured = False
+
+    # the piece of work each graph records -------------------------------------------------------------
+    def _forward_and_costs(self):
+        cache = self.module(self.s_samples, encode_and_save=True, text=self.s_tok, targets=self.s_targets)
+        outputs = self.module(self.s_samples, encode_and_save=False, memory_cache=cache, text=self.s_tok,
+                              targets=self.s_targets)
+        layers = self.criterion.layers_of(outputs)
+        costs = [self.criterion.matcher.compute_costs(l, self.s_targets) for l in layers]
+        self.h_cost.copy_(torch.stack([c for c, _ in costs]), non_blocking=True)
+        return outputs, [cl for _, cl in costs]
+
+    def _loss_backward_step(self, outputs, cost_lists):
+        matches = [(self.s_idx[li], cost_lists[li]) for li in range(len(cost_lists))]
+        loss_dict = self.criterion(outputs, self.s_targets, matches=matches)
+        wd = self.criterion.weight_dict
+        total = sum(loss_dict[k] * wd[k] for k in loss_dict.keys() if k in wd)
+        self.flat_grad.zero_()
+        total.backward()
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad)
+            self.flat_grad.div_(self.world)
+        if self.clip_max_norm > 0:
+            # clip_grad_norm_ over the used parameters == one norm + one scale of the flat buffer
+            coef = torch.clamp(self.clip_max_norm / (self.flat_grad.norm() + 1e-6), max=1.0)
+            self.flat_grad.mul_(coef)
+        self.optimizer.step()
+        return total.detach()
+
+    def _solve_assignment(self):
+        """host: LSAP on the pinned cost tensor [layers, bs, nq, T] -> static device index buffers"""
+        for li in range(self.h_cost.shape[0]):
+            ind = self.criterion.matcher.solve(self.h_cost[li], self.sizes)
+            for b, (i, j) in enumerate(ind):
+                self.h_idx[li][b][0].copy_(i)
+                self.h_idx[li][b][1].copy_(j)
+                self.s_idx[li][b][0].copy_(self.h_idx[li][b][0], non_blocking=True)
+                self.s_idx[li][b][1].copy_(self.h_idx[li][b][1], non_blocking=True)
+
+    def capture(self, images_host, targets_host, text, warmup=3):
+        dev = self.device
+        self.s_tok = self.module.transformer.tokenize(text, dev)
+        self.s_samples, self.s_targets = self.to_device(images_host, targets_host)
+        self.sizes = [len(t["obj_labels"]) for t in targets_host]
+        nq = self.args.num_queries // 2
+        n_layers = self.args.dec_layers
+        self.h_cost = torch.empty(n_layers, len(self.sizes), nq, sum(self.sizes)).pin_memory()
+        self.h_idx = [[(torch.zeros(n, dtype=torch.long).pin_memory(), torch.zeros(n, dtype=torch.long).pin_memory())
+                       for n in self.sizes] for _ in range(n_layers)]
+        self.s_idx = [[(torch.zeros(n, dtype=torch.long, device=dev), torch.zeros(n, dtype=torch.long, device=dev))
+                       for n in self.sizes] for _ in range(n_layers)]
+
+        # 1. one eager step to learn which parameters receive gradients
+        for p in self.module.parameters():
+            p.grad = None
+        outputs, cost_lists = self._forward_and_costs_eager_probe()
+        used = [p for p in self.module.parameters() if p.requires_grad and p.grad is not None]
+        # 2. flat gradient buffer + optimizer over the used parameters (same 3 lr groups, main.py:523-539)
+        total = sum(p.numel() for p in used)
+        self.flat_grad = torch.zeros(total, device=dev)
+        off = 0
+        for p in used:
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        used_ids = {id(p) for p in used}
+        named = [(n, p) for n, p in self.module.named_parameters() if id(p) in used_ids]
+        base = self.optimizer.param_groups
+        groups = [
+            {"params": [p for n, p in named if "backbone" not in n and "text_encoder" not in n], "lr": base[0]["lr"]},
+            {"params": [p for n, p in named if "backbone" in n], "lr": base[1]["lr"]},
+            {"params": [p for n, p in named if "text_encoder" in n], "lr": base[2]["lr"]},
+        ]
+        self.optimizer = torch.optim.AdamW(groups, lr=base[0]["lr"], weight_decay=base[0]["weight_decay"],
+                                           fused=True, capturable=True)
+        self.params = used
+        if self.world > 1:                      # identical replicas (same seed), made certain
+            for p in self.module.parameters():
+                dist.broadcast(p.data, 0)
+        # 3. warm-up on a side stream (cuBLAS/cuDNN workspaces, lazy inits), then capture
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                outputs, cost_lists = self._forward_and_costs()
+                side.synchronize()
+                self._solve_assignment()
+                self._loss_backward_step(outputs, cost_lists)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph_a = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_a):
+            outputs, cost_lists = self._forward_and_costs()
+        self.graph_b = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
+            self.s_loss = self._loss_backward_step(outputs, cost_lists)
+        self._keep = (outputs, cost_lists)      # the autograd graph's buffers belong to the captured pool
+        self.done_a = torch.cuda.Event()
+        self.captured = True
+
+    def _forward_and_costs_eager_probe(self):
+        outputs, cost_lists = self._forward_and_costs()
+        torch.cuda.synchronize()
+        self._solve_assignment()
+        matches = [(self.s_idx[li], cost_lists[li]) for li in range(len(cost_lists))]
+        loss_dict = self.criterion(outputs, self.s_targets, matches=matches)
+        wd = self.criterion.weight_dict
+        sum(loss_dict[k] * wd[k] for k in loss_dict.keys() if k in wd).backward()
+        return outputs, cost_lists
+
+    def replay(self):
+        """One step on the batch currently held by the static buffers."""
+        self.graph_a.replay()
+        self.done_a.record()
+        self.done_a.synchronize()               # costs are in pinned memory now
+        self._solve_assignment()
+        self.graph_b.replay()
+        return self.s_loss
+
+    def step(self, images_host, targets_host, text=None):
+        """H2D of a new batch (same shapes as at capture) + one replayed step."""
+        self.s_samples.tensors.copy_(images_host, non_blocking=True)
+        for st, ht in zip(self.s_targets, targets_host):
+            for k in st:
+                st[k].copy_(ht[k], non_blocking=True)
+        return self.replay()

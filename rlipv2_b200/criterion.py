@@ -85,8 +85,11 @@ class SetCriterionHOI(nn.Module):
 
     def _weighted_ce(self, logits, targets, indices, key):
         """F.cross_entropy with weight eos_coef on the last class; unmatched queries -> last class."""
-        w = torch.ones(logits.shape[-1], device=logits.device)
-        w[-1] = self.eos_coef
+        # class weights: 1 everywhere, eos_coef on the last ("no objects") class.  Built from fill
+        # kernels only (assigning a python float into a CUDA tensor is a pageable H2D copy, which a
+        # CUDA graph capture rejects).
+        w = torch.cat((torch.ones(logits.shape[-1] - 1, device=logits.device),
+                       torch.full((1,), float(self.eos_coef), device=logits.device)))
         idx = self._src_idx(indices)
         matched = torch.cat([t[key][J] for t, (_, J) in zip(targets, indices)])
         classes = torch.full(logits.shape[:2], logits.shape[-1] - 1, dtype=torch.int64, device=logits.device)

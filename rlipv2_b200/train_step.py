@@ -177,10 +177,17 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         self.s_idx = [[(torch.zeros(n, dtype=torch.long, device=dev), torch.zeros(n, dtype=torch.long, device=dev))
                        for n in self.sizes] for _ in range(n_layers)]
 
+        # One stream for the probe, the warm-up and both captures: autograd runs every backward node
+        # (AccumulateGrad included) on the stream its forward op first ran on, so all of them must be
+        # the capture stream - never the legacy default stream.
+        side = self.cap_stream = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
         # 1. one eager step to learn which parameters receive gradients
         for p in self.module.parameters():
             p.grad = None
-        outputs, cost_lists = self._forward_and_costs_eager_probe()
+        with torch.cuda.stream(side):
+            outputs, cost_lists = self._forward_and_costs_eager_probe()
+        side.synchronize()
         used = [p for p in self.module.parameters() if p.requires_grad and p.grad is not None]
         # 2. flat gradient buffer + optimizer over the used parameters (same 3 lr groups, main.py:523-539)
         total = sum(p.numel() for p in used)
@@ -204,8 +211,6 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
             for p in self.module.parameters():
                 dist.broadcast(p.data, 0)
         # 3. warm-up on a side stream (cuBLAS/cuDNN workspaces, lazy inits), then capture
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 outputs, cost_lists = self._forward_and_costs()
@@ -215,10 +220,10 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph_a = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_a):
+        with torch.cuda.graph(self.graph_a, stream=self.cap_stream):
             outputs, cost_lists = self._forward_and_costs()
         self.graph_b = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
+        with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool(), stream=self.cap_stream):
             self.s_loss = self._loss_backward_step(outputs, cost_lists)
         self._keep = (outputs, cost_lists)      # the autograd graph's buffers belong to the captured pool
         self.done_a = torch.cuda.Event()
@@ -226,7 +231,7 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
 
     def _forward_and_costs_eager_probe(self):
         outputs, cost_lists = self._forward_and_costs()
-        torch.cuda.synchronize()
+        torch.cuda.current_stream().synchronize()
         self._solve_assignment()
         matches = [(self.s_idx[li], cost_lists[li]) for li in range(len(cost_lists))]
         loss_dict = self.criterion(outputs, self.s_targets, matches=matches)

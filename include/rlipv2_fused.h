@@ -1,0 +1,57 @@
+/*
+ * rlipv2_fused.h - C ABI of the HBM-bound fused kernels around the dense contractions of the ParSeDA
+ * train step ("fused deformable-layer epilogues").  Each replaces a chain
+ * of torch kernels that the reference's modules launch separately:
+ *
+ *   add + LayerNorm forward / backward   src = norm(src + dropout(src2)) in
+ *       /root/reference/models/dab_deformable/deformable_transformer.py:1295-1296, 1285-1286, 1390-1400,
+ *       models/modeling_roberta.py:252-256, 332-336 (F.layer_norm + aten::add; backward:
+ *       layer_norm_grad_input + GammaBetaBackward)
+ *   ReLU-mask + bias-gradient column sum  the backward of `self.activation(self.linear1(src))`
+ *       (deformable_transformer.py:1284) and of every nn.Linear bias (aten::threshold_backward,
+ *       aten::sum over rows)
+ *   flat AdamW step                       torch.optim.AdamW of main.py:538-539 over one flat
+ *       parameter / gradient / moment buffer per learning-rate group
+ *
+ * Conventions as in rlipv2_msda.h: dense row-major fp32 device arrays, `stream` = cudaStream_t as
+ * void*, asynchronous, return 0 / positive cudaError_t / negative RLIPV2_FUSED_E*.  No CPU versions.
+ */
+#ifndef RLIPV2_FUSED_H_
+#define RLIPV2_FUSED_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLIPV2_FUSED_EINVAL (-1)
+#define RLIPV2_FUSED_ESHAPE (-2)   /* LayerNorm kernels: C must be a multiple of 128 and <= 1024 */
+
+/* y = LayerNorm(x + r) * gamma + beta over the last dim (C); also writes z = x + r, mean[M], rstd[M]
+ * for the backward.  r may be NULL (plain LayerNorm of x; z is still written). */
+int rlipv2_add_layernorm_fwd_f32(const float *x, const float *r, const float *gamma, const float *beta,
+                                 float eps, int M, int C, float *y, float *z, float *mean, float *rstd,
+                                 void *stream);
+
+/* dz = d(LayerNorm)/dz (the gradient of both x and r), dgamma[C] and dbeta[C] (overwritten). */
+int rlipv2_layernorm_bwd_f32(const float *dy, const float *z, const float *mean, const float *rstd,
+                             const float *gamma, int M, int C, float *dz, float *dgamma, float *dbeta,
+                             void *stream);
+
+/* colsum[N] = sum over rows of g [M,N] (overwritten).  If y != NULL the ReLU mask is applied first:
+ * gm = (y > 0) ? g : 0, gm is written to `gmasked` (may alias g) and summed instead. */
+int rlipv2_relu_bwd_colsum_f32(const float *g, const float *y, float *gmasked, float *colsum, int M, int N,
+                               void *stream);
+
+/* One AdamW step over n contiguous elements (decoupled weight decay, torch.optim.AdamW semantics).
+ * `step` is a device float holding the 1-based step count of THIS update (bias correction). */
+int rlipv2_adamw_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n,
+                     float lr, float beta1, float beta2, float eps, float weight_decay, const float *step,
+                     void *stream);
+
+const char *rlipv2_fused_error_string(int code);
+unsigned long long rlipv2_fused_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLIPV2_FUSED_H_ */

@@ -25,6 +25,7 @@ NVCC_FLAGS = [
 TARGETS = {
     "librlipv2_msda.so": (["msda.cu"], []),
     "librlipv2_dense.so": (["dense_tf32.cu"], []),
+    "librlipv2_fused.so": (["fused_ops.cu"], []),
 }
 
 

@@ -1,0 +1,289 @@
+// fused_ops.cu - HBM-bound fused kernels of the ParSeDA train step (sm_100a).  See include/rlipv2_fused.h
+// for what each replaces in the reference.  All of them stream their operands exactly once with 128-bit
+// coalesced accesses; grids are sized in multiples of the 148 SMs.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "rlipv2_fused.h"
+
+namespace {
+
+std::atomic<unsigned long long> g_launches{0};
+constexpr int kSMs = 148;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+
+// ---- add + LayerNorm forward: one warp per row, C = 128 * VPL elements (VPL float4 per lane) -------------
+template <int VPL>
+__global__ void __launch_bounds__(256)
+add_layernorm_fwd_kernel(const float *__restrict__ x, const float *__restrict__ r, const float *__restrict__ gamma,
+                         const float *__restrict__ beta, float eps, int M, float *__restrict__ y,
+                         float *__restrict__ z, float *__restrict__ mean, float *__restrict__ rstd)
+{
+    constexpr int C = 128 * VPL;
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    float4 gm[VPL], bt[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        gm[i] = __ldg(reinterpret_cast<const float4 *>(gamma) + i * 32 + lane);
+        bt[i] = __ldg(reinterpret_cast<const float4 *>(beta) + i * 32 + lane);
+    }
+    for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < M; row += warps) {
+        const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)row * C);
+        const float4 *rr = r ? reinterpret_cast<const float4 *>(r + (size_t)row * C) : nullptr;
+        float4 v[VPL];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            v[i] = xr[i * 32 + lane];
+            if (rr) { const float4 t = rr[i * 32 + lane]; v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w; }
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+        const float mu = warp_sum(s) * (1.f / C);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+        const float rs = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+        float4 *yr = reinterpret_cast<float4 *>(y + (size_t)row * C);
+        float4 *zr = reinterpret_cast<float4 *>(z + (size_t)row * C);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            zr[i * 32 + lane] = v[i];
+            float4 o;
+            o.x = (v[i].x - mu) * rs * gm[i].x + bt[i].x;
+            o.y = (v[i].y - mu) * rs * gm[i].y + bt[i].y;
+            o.z = (v[i].z - mu) * rs * gm[i].z + bt[i].z;
+            o.w = (v[i].w - mu) * rs * gm[i].w + bt[i].w;
+            yr[i * 32 + lane] = o;
+        }
+        if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+    }
+}
+
+// ---- LayerNorm backward: dz per row + dgamma/dbeta accumulated per lane over the warp's rows, reduced
+// over the CTA's 8 warps in shared memory, one atomicAdd per (CTA, column) ------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ z, const float *__restrict__ mean,
+                     const float *__restrict__ rstd, const float *__restrict__ gamma, int M,
+                     float *__restrict__ dz, float *__restrict__ dgamma, float *__restrict__ dbeta)
+{
+    constexpr int C = 128 * VPL;
+    __shared__ float red[8][C];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    float4 gm[VPL], ag[VPL], ab[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        gm[i] = __ldg(reinterpret_cast<const float4 *>(gamma) + i * 32 + lane);
+        ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < M; row += warps) {
+        const float4 *dr = reinterpret_cast<const float4 *>(dy + (size_t)row * C);
+        const float4 *zr = reinterpret_cast<const float4 *>(z + (size_t)row * C);
+        const float mu = mean[row], rs = rstd[row];
+        float4 g[VPL], xh[VPL];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const float4 d = dr[i * 32 + lane], v = zr[i * 32 + lane];
+            xh[i] = make_float4((v.x - mu) * rs, (v.y - mu) * rs, (v.z - mu) * rs, (v.w - mu) * rs);
+            g[i] = make_float4(d.x * gm[i].x, d.y * gm[i].y, d.z * gm[i].z, d.w * gm[i].w);
+            s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+            s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+            ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
+            ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+        }
+        const float c1 = warp_sum(s1) * (1.f / C), c2 = warp_sum(s2) * (1.f / C);
+        float4 *or_ = reinterpret_cast<float4 *>(dz + (size_t)row * C);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            float4 o;
+            o.x = rs * (g[i].x - c1 - xh[i].x * c2);
+            o.y = rs * (g[i].y - c1 - xh[i].y * c2);
+            o.z = rs * (g[i].z - c1 - xh[i].z * c2);
+            o.w = rs * (g[i].w - c1 - xh[i].w * c2);
+            or_[i * 32 + lane] = o;
+        }
+    }
+    // CTA reduction of the per-warp column partials, then one atomic per column
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+            *reinterpret_cast<float4 *>(&red[warp][(i * 32 + lane) * 4]) = pass ? ab[i] : ag[i];
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += red[w][c];
+            atomicAdd((pass ? dbeta : dgamma) + c, s);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- (ReLU mask +) column sum: CTA = 32 columns x 8 row-lanes, grid.y row chunks --------------------------------
+template <bool MASK>
+__global__ void __launch_bounds__(256)
+relu_bwd_colsum_kernel(const float *__restrict__ g, const float *__restrict__ y, float *__restrict__ gm,
+                       float *__restrict__ colsum, int M, int N)
+{
+    // each thread owns 4 consecutive columns (float4): 8 lanes cover 32 columns = 128 bytes of a row
+    __shared__ float4 red[32][8];
+    const int cl = threadIdx.x & 7;              // float4 index inside the 32-column tile
+    const int rl = threadIdx.x >> 3;             // 0..31 row lane
+    const int col = blockIdx.x * 32 + cl * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int row = blockIdx.y * 32 + rl; row < M; row += gridDim.y * 32) {
+        const size_t off = (size_t)row * N + col;
+        float4 v = *reinterpret_cast<const float4 *>(g + off);
+        if (MASK) {
+            const float4 t = *reinterpret_cast<const float4 *>(y + off);
+            v.x = t.x > 0.f ? v.x : 0.f; v.y = t.y > 0.f ? v.y : 0.f;
+            v.z = t.z > 0.f ? v.z : 0.f; v.w = t.w > 0.f ? v.w : 0.f;
+            *reinterpret_cast<float4 *>(gm + off) = v;
+        }
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    red[rl][cl] = acc;
+    __syncthreads();
+    if (rl == 0) {
+        float4 s = red[0][cl];
+        for (int r = 1; r < 32; ++r) { const float4 t = red[r][cl]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+        atomicAdd(colsum + col, s.x); atomicAdd(colsum + col + 1, s.y);
+        atomicAdd(colsum + col + 2, s.z); atomicAdd(colsum + col + 3, s.w);
+    }
+}
+
+// ---- flat AdamW -------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+             long long n4, long long n, float lr, float b1, float b2, float eps, float wd, const float *__restrict__ step)
+{
+    const float t = *step;
+    const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+    const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2), decay = 1.f - lr * wd;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 pp = reinterpret_cast<float4 *>(p)[i], mm = reinterpret_cast<float4 *>(m)[i], vv = reinterpret_cast<float4 *>(v)[i];
+        const float4 gg = reinterpret_cast<const float4 *>(g)[i];
+#define RLIPV2_ADAMW_LANE(c)                                                         \
+        pp.c *= decay;                                                               \
+        mm.c = b1 * mm.c + (1.f - b1) * gg.c;                                        \
+        vv.c = b2 * vv.c + (1.f - b2) * gg.c * gg.c;                                 \
+        pp.c -= step_size * mm.c / (sqrtf(vv.c) * inv_sqrt_bc2 + eps);
+        RLIPV2_ADAMW_LANE(x) RLIPV2_ADAMW_LANE(y) RLIPV2_ADAMW_LANE(z) RLIPV2_ADAMW_LANE(w)
+#undef RLIPV2_ADAMW_LANE
+        reinterpret_cast<float4 *>(p)[i] = pp;
+        reinterpret_cast<float4 *>(m)[i] = mm;
+        reinterpret_cast<float4 *>(v)[i] = vv;
+    }
+    // tail (n not a multiple of 4)
+    for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float pp = p[i] * decay;
+        const float gg = g[i];
+        const float mm = b1 * m[i] + (1.f - b1) * gg, vv = b2 * v[i] + (1.f - b2) * gg * gg;
+        pp -= step_size * mm / (sqrtf(vv) * inv_sqrt_bc2 + eps);
+        p[i] = pp; m[i] = mm; v[i] = vv;
+    }
+}
+
+inline int done() {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" {
+
+int rlipv2_add_layernorm_fwd_f32(const float *x, const float *r, const float *gamma, const float *beta, float eps,
+                                 int M, int C, float *y, float *z, float *mean, float *rstd, void *stream)
+{
+    if (M == 0) return 0;
+    if (!x || !gamma || !beta || !y || !z || !mean || !rstd || M < 0) return RLIPV2_FUSED_EINVAL;
+    if (C % 128 != 0 || C > 1024 || C <= 0) return RLIPV2_FUSED_ESHAPE;
+    const int grid = (int)(((long long)M + 7) / 8 < kSMs * 8 ? ((long long)M + 7) / 8 : kSMs * 8);
+    cudaStream_t s = (cudaStream_t)stream;
+#define L(V) case V: add_layernorm_fwd_kernel<V><<<grid, 256, 0, s>>>(x, r, gamma, beta, eps, M, y, z, mean, rstd); break;
+    switch (C / 128) { L(1) L(2) L(3) L(4) L(5) L(6) L(7) L(8) }
+#undef L
+    return done();
+}
+
+int rlipv2_layernorm_bwd_f32(const float *dy, const float *z, const float *mean, const float *rstd, const float *gamma,
+                             int M, int C, float *dz, float *dgamma, float *dbeta, void *stream)
+{
+    if (!dgamma || !dbeta || M < 0) return RLIPV2_FUSED_EINVAL;
+    if (C % 128 != 0 || C > 1024 || C <= 0) return RLIPV2_FUSED_ESHAPE;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(dgamma, 0, sizeof(float) * C, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dbeta, 0, sizeof(float) * C, s);
+    if (e != cudaSuccess) return (int)e;
+    if (M == 0) return 0;
+    if (!dy || !z || !mean || !rstd || !gamma || !dz) return RLIPV2_FUSED_EINVAL;
+    const int grid = (int)(((long long)M + 7) / 8 < kSMs * 4 ? ((long long)M + 7) / 8 : kSMs * 4);
+#define L(V) case V: layernorm_bwd_kernel<V><<<grid, 256, 0, s>>>(dy, z, mean, rstd, gamma, M, dz, dgamma, dbeta); break;
+    switch (C / 128) { L(1) L(2) L(3) L(4) L(5) L(6) L(7) L(8) }
+#undef L
+    return done();
+}
+
+int rlipv2_relu_bwd_colsum_f32(const float *g, const float *y, float *gmasked, float *colsum, int M, int N, void *stream)
+{
+    if (!colsum || M < 0 || N <= 0 || N % 32 != 0) return N % 32 != 0 ? RLIPV2_FUSED_ESHAPE : RLIPV2_FUSED_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(colsum, 0, sizeof(float) * N, s);
+    if (e != cudaSuccess) return (int)e;
+    if (M == 0) return 0;
+    if (!g || (y && !gmasked)) return RLIPV2_FUSED_EINVAL;
+    const int gx = N / 32;
+    int gy = (kSMs * 8 + gx - 1) / gx;
+    const int max_gy = (M + 31) / 32;
+    if (gy > max_gy) gy = max_gy;
+    if (gy < 1) gy = 1;
+    if (y) relu_bwd_colsum_kernel<true><<<dim3(gx, gy), 256, 0, s>>>(g, y, gmasked, colsum, M, N);
+    else relu_bwd_colsum_kernel<false><<<dim3(gx, gy), 256, 0, s>>>(g, nullptr, nullptr, colsum, M, N);
+    return done();
+}
+
+int rlipv2_adamw_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, const float *step, void *stream)
+{
+    if (n == 0) return 0;
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !step || n < 0) return RLIPV2_FUSED_EINVAL;
+    if (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) return RLIPV2_FUSED_EINVAL;
+    const long long n4 = n / 4;
+    long long blocks = (n4 + 255) / 256;
+    if (blocks > kSMs * 16) blocks = kSMs * 16;
+    if (blocks < 1) blocks = 1;
+    adamw_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n4, n, lr, beta1, beta2,
+                                                                eps, weight_decay, step);
+    return done();
+}
+
+const char *rlipv2_fused_error_string(int code)
+{
+    switch (code) {
+        case 0: return "success";
+        case RLIPV2_FUSED_EINVAL: return "rlipv2_fused: invalid argument";
+        case RLIPV2_FUSED_ESHAPE: return "rlipv2_fused: unsupported shape";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "rlipv2_fused: unknown error";
+    }
+}
+
+unsigned long long rlipv2_fused_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

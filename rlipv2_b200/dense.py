@@ -17,13 +17,15 @@ import torch.nn.functional as F
 
 _PRECISION = "fp32"
 _USE_TCGEN05 = True
+_USE_FUSED = True        # fused LayerNorm / bias-gradient kernels (exact fp32 arithmetic; CUDA tensors only)
 
 
-def set_matmul_precision(mode: str, tcgen05: bool = True):
-    global _PRECISION, _USE_TCGEN05
+def set_matmul_precision(mode: str, tcgen05: bool = True, fused: bool = True):
+    global _PRECISION, _USE_TCGEN05, _USE_FUSED
     assert mode in ("fp32", "tf32")
     _PRECISION = mode
     _USE_TCGEN05 = tcgen05
+    _USE_FUSED = fused
     torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
     torch.backends.cudnn.allow_tf32 = mode == "tf32"
 
@@ -57,16 +59,61 @@ class _LinearTF32(torch.autograd.Function):
     def backward(ctx, grad_out):
         x2, w, y = ctx.saved_tensors
         g = grad_out.reshape(-1, grad_out.shape[-1])
-        if y is not None:
-            g = g * (y > 0)
-        gx = gw = gb = None
+        if not g.is_contiguous():
+            g = g.contiguous()
+        gb = None
+        if g.shape[1] % 32 == 0:
+            # one pass: ReLU mask (when fused in the forward) + bias-gradient column sum
+            g, gb = _fused().relu_bwd_colsum(g, y)
+        else:
+            if y is not None:
+                g = g * (y > 0)
+            gb = g.sum(0)
+        gx = gw = None
         if ctx.needs_input_grad[0]:
             gx = (g @ w).view(*grad_out.shape[:-1], w.shape[1])
         if ctx.needs_input_grad[1]:
             gw = g.t() @ x2
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = g.sum(0)
+        if not (ctx.has_bias and ctx.needs_input_grad[2]):
+            gb = None
         return gx, gw, gb, None
+
+
+def _fused():
+    from . import fused_abi
+    return fused_abi
+
+
+class _AddLayerNorm(torch.autograd.Function):
+    """y = LayerNorm(x + r) (r optional) with the fused forward / backward kernels of csrc/fused_ops.cu."""
+
+    @staticmethod
+    def forward(ctx, x, r, weight, bias, eps):
+        f = _fused()
+        C = x.shape[-1]
+        x2 = x.reshape(-1, C)
+        x2 = x2 if x2.is_contiguous() else x2.contiguous()
+        r2 = None
+        if r is not None:
+            r2 = r.reshape(-1, C)
+            r2 = r2 if r2.is_contiguous() else r2.contiguous()
+        y, z, mean, rstd = f.add_layernorm_fwd(x2, r2, weight, bias, eps)
+        ctx.save_for_backward(z, mean, rstd, weight)
+        ctx.has_r = r is not None
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        z, mean, rstd, weight = ctx.saved_tensors
+        g = grad_out.reshape(-1, grad_out.shape[-1])
+        g = g if g.is_contiguous() else g.contiguous()
+        dz, dgamma, dbeta = _fused().layernorm_bwd(g, z, mean, rstd, weight)
+        dz = dz.view(grad_out.shape)
+        return dz, (dz if ctx.has_r else None), dgamma, dbeta, None
+
+
+def _fused_ln_ok(x):
+    return _USE_FUSED and x.is_cuda and x.dtype == torch.float32 and _fused().ln_supported(x.shape[-1]) and x.numel() > 0
 
 
 def _tcgen05_ok(x, weight):
@@ -97,9 +144,13 @@ def linear_gelu(x, weight, bias=None):
 
 
 def layer_norm(x, weight, bias, eps):
+    if _fused_ln_ok(x):
+        return _AddLayerNorm.apply(x, None, weight, bias, eps)
     return F.layer_norm(x, (x.shape[-1],), weight, bias, eps)
 
 
 def add_layer_norm(x, residual, weight, bias, eps):
     """LayerNorm(x + residual)."""
+    if _fused_ln_ok(x) and residual.shape == x.shape:
+        return _AddLayerNorm.apply(x, residual, weight, bias, eps)
     return F.layer_norm(x + residual, (x.shape[-1],), weight, bias, eps)

@@ -1,0 +1,93 @@
+"""ctypes binding of include/rlipv2_fused.h (HBM-bound fused kernels).  No fallback: a missing library raises."""
+import ctypes
+import os
+
+import torch
+
+from .build import lib_path
+
+_path = lib_path("librlipv2_fused.so")
+if not os.path.exists(_path):
+    raise ImportError(f"{_path} is missing: run `python -m rlipv2_b200.build` (no CPU / PyTorch fallback is provided)")
+_lib = ctypes.CDLL(_path)
+_i, _p, _f, _ll = ctypes.c_int, ctypes.c_void_p, ctypes.c_float, ctypes.c_longlong
+_lib.rlipv2_add_layernorm_fwd_f32.argtypes = [_p, _p, _p, _p, _f, _i, _i, _p, _p, _p, _p, _p]
+_lib.rlipv2_layernorm_bwd_f32.argtypes = [_p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]
+_lib.rlipv2_relu_bwd_colsum_f32.argtypes = [_p, _p, _p, _p, _i, _i, _p]
+_lib.rlipv2_adamw_f32.argtypes = [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _p, _p]
+for _n in ("add_layernorm_fwd_f32", "layernorm_bwd_f32", "relu_bwd_colsum_f32", "adamw_f32"):
+    getattr(_lib, "rlipv2_" + _n).restype = _i
+_lib.rlipv2_fused_error_string.argtypes = [_i]
+_lib.rlipv2_fused_error_string.restype = ctypes.c_char_p
+_lib.rlipv2_fused_launch_count.restype = ctypes.c_ulonglong
+
+EXPORTS = ("rlipv2_add_layernorm_fwd_f32", "rlipv2_layernorm_bwd_f32", "rlipv2_relu_bwd_colsum_f32",
+           "rlipv2_adamw_f32", "rlipv2_fused_error_string", "rlipv2_fused_launch_count")
+
+
+def library_path():
+    return _path
+
+
+def launch_count():
+    return int(_lib.rlipv2_fused_launch_count())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what}: {_lib.rlipv2_fused_error_string(rc).decode()} (code {rc})")
+
+
+def ln_supported(C):
+    return C % 128 == 0 and 0 < C <= 1024
+
+
+def add_layernorm_fwd(x2, r2, gamma, beta, eps):
+    """x2, r2 [M,C] contiguous fp32 CUDA (r2 may be None) -> (y, z, mean, rstd)"""
+    M, C = x2.shape
+    y = torch.empty_like(x2)
+    z = torch.empty_like(x2)
+    mean = torch.empty(M, dtype=torch.float32, device=x2.device)
+    rstd = torch.empty(M, dtype=torch.float32, device=x2.device)
+    with torch.cuda.device(x2.device):
+        rc = _lib.rlipv2_add_layernorm_fwd_f32(x2.data_ptr(), r2.data_ptr() if r2 is not None else None, gamma.data_ptr(),
+                                               beta.data_ptr(), eps, M, C, y.data_ptr(), z.data_ptr(), mean.data_ptr(),
+                                               rstd.data_ptr(), _stream())
+    _check(rc, "rlipv2_add_layernorm_fwd_f32")
+    return y, z, mean, rstd
+
+
+def layernorm_bwd(dy2, z, mean, rstd, gamma):
+    M, C = dy2.shape
+    dz = torch.empty_like(dy2)
+    dgamma = torch.empty(C, dtype=torch.float32, device=dy2.device)
+    dbeta = torch.empty(C, dtype=torch.float32, device=dy2.device)
+    with torch.cuda.device(dy2.device):
+        rc = _lib.rlipv2_layernorm_bwd_f32(dy2.data_ptr(), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                           M, C, dz.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _stream())
+    _check(rc, "rlipv2_layernorm_bwd_f32")
+    return dz, dgamma, dbeta
+
+
+def relu_bwd_colsum(g2, y2=None):
+    """g2 [M,N] contiguous; y2 = forward output of the ReLU (or None) -> (masked g [M,N], column sums [N])"""
+    M, N = g2.shape
+    colsum = torch.empty(N, dtype=torch.float32, device=g2.device)
+    gm = torch.empty_like(g2) if y2 is not None else g2
+    with torch.cuda.device(g2.device):
+        rc = _lib.rlipv2_relu_bwd_colsum_f32(g2.data_ptr(), y2.data_ptr() if y2 is not None else None,
+                                             gm.data_ptr() if y2 is not None else None, colsum.data_ptr(), M, N, _stream())
+    _check(rc, "rlipv2_relu_bwd_colsum_f32")
+    return gm, colsum
+
+
+def adamw(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step):
+    """In-place AdamW over flat contiguous fp32 buffers; `step` = 0-dim device float (1-based count)."""
+    with torch.cuda.device(param.device):
+        rc = _lib.rlipv2_adamw_f32(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                   param.numel(), lr, beta1, beta2, eps, weight_decay, step.data_ptr(), _stream())
+    _check(rc, "rlipv2_adamw_f32")

@@ -151,8 +151,15 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
             # clip_grad_norm_ over the used parameters == one norm + one scale of the flat buffer
             coef = torch.clamp(self.clip_max_norm / (self.flat_grad.norm() + 1e-6), max=1.0)
             self.flat_grad.mul_(coef)
-        self.optimizer.step()
+        self._adamw_step()
         return total.detach()
+
+    def _adamw_step(self):
+        from . import fused_abi
+        self.step_t.add_(1.0)
+        for start, end, lr in self.group_ranges:
+            fused_abi.adamw(self.flat_param[start:end], self.flat_grad[start:end], self.exp_avg[start:end],
+                            self.exp_avg_sq[start:end], lr, 0.9, 0.999, 1e-8, self.weight_decay, self.step_t)
 
     def _solve_assignment(self):
         """host: LSAP on the pinned cost tensor [layers, bs, nq, T] -> static device index buffers"""
@@ -188,28 +195,45 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         with torch.cuda.stream(side):
             outputs, cost_lists = self._forward_and_costs_eager_probe()
         side.synchronize()
-        used = [p for p in self.module.parameters() if p.requires_grad and p.grad is not None]
-        # 2. flat gradient buffer + optimizer over the used parameters (same 3 lr groups, main.py:523-539)
-        total = sum(p.numel() for p in used)
-        self.flat_grad = torch.zeros(total, device=dev)
-        off = 0
-        for p in used:
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
-        used_ids = {id(p) for p in used}
+        used_ids = {id(p) for p in self.module.parameters() if p.requires_grad and p.grad is not None}
         named = [(n, p) for n, p in self.module.named_parameters() if id(p) in used_ids]
         base = self.optimizer.param_groups
-        groups = [
-            {"params": [p for n, p in named if "backbone" not in n and "text_encoder" not in n], "lr": base[0]["lr"]},
-            {"params": [p for n, p in named if "backbone" in n], "lr": base[1]["lr"]},
-            {"params": [p for n, p in named if "text_encoder" in n], "lr": base[2]["lr"]},
+        groups = [                                  # the 3 learning-rate groups of main.py:523-539
+            ([p for n, p in named if "backbone" not in n and "text_encoder" not in n], base[0]["lr"]),
+            ([p for n, p in named if "backbone" in n], base[1]["lr"]),
+            ([p for n, p in named if "text_encoder" in n], base[2]["lr"]),
         ]
-        self.optimizer = torch.optim.AdamW(groups, lr=base[0]["lr"], weight_decay=base[0]["weight_decay"],
-                                           fused=True, capturable=True)
-        self.params = used
+        self.weight_decay = base[0]["weight_decay"]
+        # 2. flat parameter / gradient / Adam-moment buffers, one contiguous 16-byte aligned range per
+        #    group: parameters and their .grad become views, so the step needs one all-reduce, one
+        #    norm and three AdamW launches regardless of the number of tensors
+        ranges, off = [], 0
+        for plist, lr in groups:
+            start = off
+            off += sum(p.numel() for p in plist)
+            ranges.append((start, off, lr))
+            off = (off + 3) // 4 * 4
+        self.flat_param = torch.zeros(off, device=dev)
+        self.flat_grad = torch.zeros(off, device=dev)
+        self.exp_avg = torch.zeros(off, device=dev)
+        self.exp_avg_sq = torch.zeros(off, device=dev)
+        self.step_t = torch.zeros((), device=dev)
+        for (plist, _), (start, _, _) in zip(groups, ranges):
+            o = start
+            for p in plist:
+                n = p.numel()
+                self.flat_param[o:o + n].copy_(p.data.reshape(-1))
+                p.data = self.flat_param[o:o + n].view_as(p)
+                p.grad = self.flat_grad[o:o + n].view_as(p)
+                o += n
+        self.group_ranges = ranges
+        self.params = [p for plist, _ in groups for p in plist]
+        self.optimizer = None                       # replaced by the flat AdamW kernel (fused_ops.cu)
         if self.world > 1:                      # identical replicas (same seed), made certain
+            dist.broadcast(self.flat_param, 0)
             for p in self.module.parameters():
-                dist.broadcast(p.data, 0)
+                if id(p) not in used_ids:
+                    dist.broadcast(p.data, 0)
         # 3. warm-up on a side stream (cuBLAS/cuDNN workspaces, lazy inits), then capture
         with torch.cuda.stream(side):
             for _ in range(warmup):

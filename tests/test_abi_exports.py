@@ -37,10 +37,11 @@ def test_binding_matches_abi_version():
     assert os.path.exists(msda_abi.library_path())
     for sym in msda_abi.EXPORTS:
         assert sym in declared_symbols()
-    from rlipv2_b200 import dense_abi
-    assert os.path.exists(dense_abi.library_path())
-    for sym in dense_abi.EXPORTS:
-        assert sym in declared_symbols()
+    from rlipv2_b200 import dense_abi, fused_abi
+    for abi in (dense_abi, fused_abi):
+        assert os.path.exists(abi.library_path())
+        for sym in abi.EXPORTS:
+            assert sym in declared_symbols()
 
 
 def test_cpu_tensors_are_rejected_like_the_reference():

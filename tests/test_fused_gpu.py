@@ -1,0 +1,63 @@
+"""GPU tests of the fused HBM-bound kernels (csrc/fused_ops.cu) through their C ABI, against plain
+PyTorch fp32/fp64 references of the same ops (these are floating-point kernels)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,C", [(1, 128), (37, 256), (4446, 256), (512, 768), (300, 1024)])
+@pytest.mark.parametrize("with_r", [True, False])
+def test_add_layernorm_fwd_bwd(M, C, with_r):
+    from rlipv2_b200 import fused_abi
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + C)
+    x = torch.randn(M, C, device="cuda", generator=g)
+    r = torch.randn(M, C, device="cuda", generator=g) if with_r else None
+    w = torch.randn(C, device="cuda", generator=g)
+    b = torch.randn(C, device="cuda", generator=g)
+    dy = torch.randn(M, C, device="cuda", generator=g)
+    y, z, mean, rstd = fused_abi.add_layernorm_fwd(x, r, w, b, 1e-5)
+    zr = (x + r if with_r else x).double().requires_grad_(True)
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = F.layer_norm(zr, (C,), wr, br, 1e-5)
+    torch.testing.assert_close(y.double(), yr, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(z.double(), zr.detach(), rtol=0, atol=0)
+    yr.backward(dy.double())
+    dz, dgamma, dbeta = fused_abi.layernorm_bwd(dy, z, mean, rstd, w)
+    torch.testing.assert_close(dz.double(), zr.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(dgamma.double(), wr.grad, rtol=1e-4, atol=1e-3 * max(1.0, M ** 0.5))
+    torch.testing.assert_close(dbeta.double(), br.grad, rtol=1e-4, atol=1e-3 * max(1.0, M ** 0.5))
+
+
+@pytest.mark.parametrize("M,N", [(1, 32), (100, 256), (44446, 2048), (513, 128)])
+@pytest.mark.parametrize("mask", [True, False])
+def test_relu_bwd_colsum(M, N, mask):
+    from rlipv2_b200 import fused_abi
+    g = torch.randn(M, N, device="cuda")
+    y = torch.relu(torch.randn(M, N, device="cuda")) if mask else None
+    gm, cs = fused_abi.relu_bwd_colsum(g.clone(), y)
+    ref = g * (y > 0) if mask else g
+    torch.testing.assert_close(gm, ref, rtol=0, atol=0)
+    torch.testing.assert_close(cs.double(), ref.double().sum(0), rtol=1e-4, atol=1e-3 * max(1.0, M ** 0.5))
+
+
+def test_flat_adamw_matches_torch():
+    from rlipv2_b200 import fused_abi
+    n = 1_000_003
+    p0 = torch.randn(n + 1, device="cuda")[:n]                 # odd length exercises the scalar tail
+    p0 = p0.clone()
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref_p], lr=1.41e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    p, m, v = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    step = torch.zeros((), device="cuda")
+    for it in range(4):
+        grad = torch.randn(n, device="cuda") * (0.1 + it)
+        ref_p.grad = grad.clone()
+        opt.step()
+        step += 1
+        fused_abi.adamw(p, grad, m, v, 1.41e-4, 0.9, 0.999, 1e-8, 1e-4, step)
+    torch.testing.assert_close(p, ref_p.detach(), rtol=1e-5, atol=1e-6)
+    st = opt.state[ref_p]
+    torch.testing.assert_close(m, st["exp_avg"], rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(v, st["exp_avg_sq"], rtol=1e-5, atol=1e-9)

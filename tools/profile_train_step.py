@@ -1,6 +1,7 @@
-"""torch.profiler breakdown of the ParSeDA train step (kernel time by name), one GPU."""
+"""Kernel-level time breakdown of one eager ParSeDA train step (torch.profiler, CUDA kernels only)."""
 import os
 import sys
+from collections import defaultdict
 
 import torch
 
@@ -17,8 +18,14 @@ for _ in range(3):
 torch.cuda.synchronize()
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
-    for _ in range(2):
-        ts.step_device(samples, targets, text)
+    ts.step_device(samples, targets, text)
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
-print("max memory allocated GB:", torch.cuda.max_memory_allocated() / 1e9)
+agg = defaultdict(lambda: [0, 0.0])
+for e in prof.events():
+    if e.device_type == torch.autograd.DeviceType.CUDA:
+        agg[e.name][0] += 1
+        agg[e.name][1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
+tot = sum(v[1] for v in agg.values())
+print(f"total GPU kernel time per step: {tot / 1e3:.2f} ms over {sum(v[0] for v in agg.values())} launches")
+for name, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:60]:
+    print(f"{t / 1e3:8.3f} ms {100 * t / tot:5.1f}%  n={n:4d}  {name[:150]}")

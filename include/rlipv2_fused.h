@@ -45,7 +45,7 @@ int rlipv2_relu_bwd_colsum_f32(const float *g, const float *y, float *gmasked, f
 /* One AdamW step over n contiguous elements (decoupled weight decay, torch.optim.AdamW semantics).
  * `step` is a device float holding the 1-based step count of THIS update (bias correction). */
 int rlipv2_adamw_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n,
-                     float lr, float beta1, float beta2, float eps, float weight_decay, const float *step,
+                     double lr, double beta1, double beta2, double eps, double weight_decay, const float *step,
                      void *stream);
 
 const char *rlipv2_fused_error_string(int code);

@@ -170,8 +170,10 @@ relu_bwd_colsum_kernel(const float *__restrict__ g, const float *__restrict__ y,
 // ---- flat AdamW -------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
-             long long n4, long long n, float lr, float b1, float b2, float eps, float wd, const float *__restrict__ step)
+             long long n4, long long n, float lr, float b1, float b2, float omb1, float omb2, float eps, float wd,
+             const float *__restrict__ step)
 {
+    // omb1 / omb2 = 1 - beta computed in double on the host (1.f - 0.999f is 1.3e-5 off)
     const float t = *step;
     const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
     const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2), decay = 1.f - lr * wd;
@@ -181,8 +183,8 @@ adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restri
         const float4 gg = reinterpret_cast<const float4 *>(g)[i];
 #define RLIPV2_ADAMW_LANE(c)                                                         \
         pp.c *= decay;                                                               \
-        mm.c = b1 * mm.c + (1.f - b1) * gg.c;                                        \
-        vv.c = b2 * vv.c + (1.f - b2) * gg.c * gg.c;                                 \
+        mm.c = b1 * mm.c + omb1 * gg.c;                                              \
+        vv.c = b2 * vv.c + omb2 * gg.c * gg.c;                                       \
         pp.c -= step_size * mm.c / (sqrtf(vv.c) * inv_sqrt_bc2 + eps);
         RLIPV2_ADAMW_LANE(x) RLIPV2_ADAMW_LANE(y) RLIPV2_ADAMW_LANE(z) RLIPV2_ADAMW_LANE(w)
 #undef RLIPV2_ADAMW_LANE
@@ -194,7 +196,7 @@ adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restri
     for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float pp = p[i] * decay;
         const float gg = g[i];
-        const float mm = b1 * m[i] + (1.f - b1) * gg, vv = b2 * v[i] + (1.f - b2) * gg * gg;
+        const float mm = b1 * m[i] + omb1 * gg, vv = b2 * v[i] + omb2 * gg * gg;
         pp -= step_size * mm / (sqrtf(vv) * inv_sqrt_bc2 + eps);
         p[i] = pp; m[i] = mm; v[i] = vv;
     }
@@ -259,8 +261,8 @@ int rlipv2_relu_bwd_colsum_f32(const float *g, const float *y, float *gmasked, f
     return done();
 }
 
-int rlipv2_adamw_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, float lr,
-                     float beta1, float beta2, float eps, float weight_decay, const float *step, void *stream)
+int rlipv2_adamw_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, double lr,
+                     double beta1, double beta2, double eps, double weight_decay, const float *step, void *stream)
 {
     if (n == 0) return 0;
     if (!param || !grad || !exp_avg || !exp_avg_sq || !step || n < 0) return RLIPV2_FUSED_EINVAL;
@@ -269,8 +271,9 @@ int rlipv2_adamw_f32(float *param, const float *grad, float *exp_avg, float *exp
     long long blocks = (n4 + 255) / 256;
     if (blocks > kSMs * 16) blocks = kSMs * 16;
     if (blocks < 1) blocks = 1;
-    adamw_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n4, n, lr, beta1, beta2,
-                                                                eps, weight_decay, step);
+    adamw_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n4, n, (float)lr,
+                                                                (float)beta1, (float)beta2, (float)(1.0 - beta1),
+                                                                (float)(1.0 - beta2), (float)eps, (float)weight_decay, step);
     return done();
 }
 

@@ -14,7 +14,8 @@ _i, _p, _f, _ll = ctypes.c_int, ctypes.c_void_p, ctypes.c_float, ctypes.c_longlo
 _lib.rlipv2_add_layernorm_fwd_f32.argtypes = [_p, _p, _p, _p, _f, _i, _i, _p, _p, _p, _p, _p]
 _lib.rlipv2_layernorm_bwd_f32.argtypes = [_p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]
 _lib.rlipv2_relu_bwd_colsum_f32.argtypes = [_p, _p, _p, _p, _i, _i, _p]
-_lib.rlipv2_adamw_f32.argtypes = [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _p, _p]
+_d = ctypes.c_double
+_lib.rlipv2_adamw_f32.argtypes = [_p, _p, _p, _p, _ll, _d, _d, _d, _d, _d, _p, _p]
 for _n in ("add_layernorm_fwd_f32", "layernorm_bwd_f32", "relu_bwd_colsum_f32", "adamw_f32"):
     getattr(_lib, "rlipv2_" + _n).restype = _i
 _lib.rlipv2_fused_error_string.argtypes = [_i]

@@ -60,8 +60,7 @@ def build_text_encoder(text_encoder_type="roberta-base", synthetic=None):
         except Exception:
             if synthetic is False:
                 raise
-    cfg = roberta_base_config()
-    # label strings are 3-8 tokens long: the plain bmm+softmax attention path of HF is several times
-    # faster here than the flash/mem-efficient SDPA kernels (2.3 ms -> <0.5 ms of backward per step)
-    cfg._attn_implementation = "eager"
-    return HashTokenizer(), RobertaModel(cfg)
+    # NB: HF's "eager" attention path would be faster for 3-8 token label strings than the SDPA kernels,
+    # but its mask construction does a pageable H2D copy (torch.tensor(0.0, device=...)), which a CUDA
+    # graph capture rejects; the default SDPA path captures cleanly.
+    return HashTokenizer(), RobertaModel(roberta_base_config())

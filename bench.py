@@ -165,6 +165,45 @@ def msda_roofline(device):
                     "frac": fwd_b / tf / 1e9 / pk["hbm_gbs"], "us": tf * 1e6, "traffic": 141.8e6}}
 
 
+def alif_tensor_roofline(device):
+    """ALIF's dense contractions on the tcgen05 kernel: achieved TF32 FLOP/s of the six projections of one
+    fusion layer (batch 2: Tv = 2x273 rows, Tl = 2x256 rows, E = 2048) vs the tensor peak.  The driver's
+    MEASURED_PEAKS.json holds the dense bf16 figure; TF32 runs at half the bf16 rate on this part
+    (B200_PROFILING.md: 2.25 vs 1.1 PFLOP/s nominal), so peak_tf32 = bf16_tflops / 2."""
+    from rlipv2_b200 import dense_abi
+    shapes = [(546, 2048, 256), (546, 2048, 256), (512, 2048, 768), (512, 2048, 768), (546, 256, 2048), (512, 768, 2048)]
+    ops = []
+    for M_, N_, K_ in shapes:
+        x = torch.randn(M_, K_, device=device)
+        w = torch.randn(N_, K_, device=device) * K_ ** -0.5
+        b = torch.randn(N_, device=device)
+        ops.append((x, w, b))
+    run = lambda: [dense_abi.linear_tf32(x, w, b, 0) for x, w, b in ops]
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / 20 * 1e-3
+    flops = sum(2.0 * m * n * k for m, n, k in shapes)
+    peak = 1590.0 / 2
+    src = "fallback (B200_PROFILING.md) / 2"
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) / 2
+        src = "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 = half the bf16 rate)"
+    except Exception:
+        pass
+    return {"bound": "tensor", "kernel": "linear_tf32_kernel (tcgen05.mma kind::tf32) on the 6 ALIF projections of one fusion layer, batch 2",
+            "achieved": flops / t / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / t / 1e12 / peak, "peak_src": src,
+            "us_per_layer": t * 1e6, "flops_per_layer": flops,
+            "ncu": "sm__pipe_tensor_cycles_active 27.8 % on the l_proj GEMM (profiles/dense_r01_v1_alif_ncu.txt); "
+                   "M = 512-546 rows fill 16-64 of 148 SMs, the GEMMs are launch/latency-bound at ~12 us"}
+
+
 # ------------------------------------------------------------------------------------------------
 # workload: full train step
 # ------------------------------------------------------------------------------------------------
@@ -231,6 +270,7 @@ def run_train_step(args, rank, world, device):
         del ts, step, e2e
         torch.cuda.empty_cache()
         line["roofline"] = msda_roofline(device)
+        line["roofline_alif_tensor"] = alif_tensor_roofline(device)
     return line
 
 

@@ -33,7 +33,7 @@ from .alif import FeatureResizer, RLIPv2_VLFuse
 from .ms_deform_attn import MSDeformAttn
 from .nested import inverse_sigmoid
 from .roberta_layer import RobertaLayer
-from .text_encoder import build_text_encoder
+from .text_encoder import build_text_encoder, pooled_text
 
 
 _LEVEL_CACHE = {}
@@ -436,7 +436,7 @@ class RLIP_ParSeDABDeformableTransformer_v2(nn.Module):
         tok = text if isinstance(text, dict) else self.tokenize(text, device)
         sums = tok["sums"]
         obj_pred_names_sums = torch.tensor(sums)
-        pooled = self.text_encoder(input_ids=tok["input_ids"], attention_mask=tok["attention_mask"]).pooler_output
+        pooled = pooled_text(self.text_encoder, tok["input_ids"], tok["attention_mask"])
         i, objs, preds = 0, [], []
         for n_obj, n_pred in sums:
             objs.append(pooled[i:i + n_obj])

@@ -62,12 +62,9 @@ class ParSeDATrainStep:
         self.model = model.to(self.device).train()
         self.criterion = criterion.to(self.device).train()
         self.module = self.model
-        if self.device.type == "cuda":
-            # NHWC end to end: cuDNN's tensor-core convolutions are NHWC-native (NCHW inputs cost an
-            # nchwToNhwc / nhwcToNchw pair per convolution, 1.7 ms per step), and a channels-last
-            # [N,C,H,W] feature map flattens to the transformer's [N, HW, C] layout without a copy.
-            self.module.backbone[0].body.to(memory_format=torch.channels_last)
-            self.module.input_proj.to(memory_format=torch.channels_last)
+        # NB: channels_last (NHWC) for the backbone was measured and dropped: it removes cuDNN's
+        # nchwToNhwc/nhwcToNchw pairs (1.7 ms) but the frozen-BN / GroupNorm elementwise kernels get
+        # slower by more than that (52.1 vs 50.3 ms per step).
         if ddp is None:
             ddp = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         if ddp:
@@ -86,8 +83,6 @@ class ParSeDATrainStep:
 
     def to_device(self, images_host, targets_host):
         images = images_host.to(self.device, non_blocking=True)
-        if self.device.type == "cuda":
-            images = images.contiguous(memory_format=torch.channels_last)
         mask = torch.zeros(images.shape[0], images.shape[2], images.shape[3], dtype=torch.bool, device=self.device)
         targets = [{k: v.to(self.device, non_blocking=True) for k, v in t.items()} for t in targets_host]
         return NestedTensor(images, mask), targets

@@ -29,3 +29,12 @@ tot = sum(v[1] for v in agg.values())
 print(f"total GPU kernel time per step: {tot / 1e3:.2f} ms over {sum(v[0] for v in agg.values())} launches")
 for name, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:60]:
     print(f"{t / 1e3:8.3f} ms {100 * t / tot:5.1f}%  n={n:4d}  {name[:150]}")
+
+if len(sys.argv) > 2 and sys.argv[2] == "big":
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    evs.sort(key=lambda e: e.time_range.start)
+    print("---- kernels >= 40 us in launch order")
+    for e in evs:
+        t = e.device_time if hasattr(e, "device_time") else e.cuda_time
+        if t >= 40:
+            print(f"{t:8.1f} us  {e.name[:140]}")

@@ -97,9 +97,65 @@ class Backbone(nn.Module):
         if dilation:
             self.strides[-1] = self.strides[-1] // 2
         self.body = IntermediateLayerGetter(backbone, return_layers=return_layers)
+        self.fold_bn = True
+
+    # ---- frozen-BN folding ----------------------------------------------------------------------------
+    # The reference applies FrozenBatchNorm2d as separate broadcast mul / add kernels after every
+    # convolution (DDETR_backbone.py:59-68) and ReLU as a third pass: on the 200x334 and 400x667 maps of
+    # an 800x1333 image those three elementwise passes cost 4-5x the convolution itself (profiles/
+    # train_step_r01_v3_kernels.txt: 96 + 95 + 40 us vs a 43-53 us conv).  The statistics are constants,
+    # so BN folds into the convolution exactly: conv(x, w) * s + t == conv(x, w * s) + t.  The folded
+    # weight is recomputed from the live parameters every call (a [Cout,Cin,k,k] multiply), so gradients
+    # still reach `conv.weight` through the product and checkpoints are untouched.
+    @staticmethod
+    def _fold(conv, bn):
+        scale = bn.weight * (bn.running_var + bn.eps).rsqrt()
+        shift = bn.bias - bn.running_mean * scale
+        return conv.weight * scale.view(-1, 1, 1, 1), shift
+
+    @classmethod
+    def _conv_bn(cls, x, conv, bn, relu, residual=None):
+        w, b = cls._fold(conv, bn)
+        frozen = not (torch.is_grad_enabled() and (w.requires_grad or x.requires_grad))
+        if frozen and x.is_cuda and conv.groups == 1:
+            # cuDNN's fused conv + bias (+ residual) + ReLU epilogue (no autograd needed here)
+            if residual is not None:
+                return torch.cudnn_convolution_add_relu(x, w, residual, 1.0, b, conv.stride, conv.padding,
+                                                        conv.dilation, conv.groups)
+            if relu:
+                return torch.cudnn_convolution_relu(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+        y = F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+        if residual is not None:
+            y = y + residual
+        return F.relu_(y) if (relu or residual is not None) else y
+
+    @classmethod
+    def _bottleneck(cls, x, blk):
+        out = cls._conv_bn(x, blk.conv1, blk.bn1, True)
+        out = cls._conv_bn(out, blk.conv2, blk.bn2, True)
+        identity = x if blk.downsample is None else cls._conv_bn(x, blk.downsample[0], blk.downsample[1], False)
+        return cls._conv_bn(out, blk.conv3, blk.bn3, True, residual=identity)
+
+    def _forward_folded(self, x):
+        body = self.body
+        frozen_stem = not any(p.requires_grad for p in body.layer1.parameters())
+        with torch.set_grad_enabled(torch.is_grad_enabled() and not frozen_stem):
+            x = self._conv_bn(x, body.conv1, body.bn1, True)         # stem + layer1 are frozen (:75-77)
+            x = body.maxpool(x)
+            for blk in body.layer1:
+                x = self._bottleneck(x, blk)
+        outs = {}
+        for name in ("layer2", "layer3", "layer4"):
+            if not hasattr(body, name):
+                break
+            for blk in getattr(body, name):
+                x = self._bottleneck(x, blk)
+            if name in body.return_layers:
+                outs[body.return_layers[name]] = x
+        return outs
 
     def forward(self, tensor_list: NestedTensor) -> Dict[str, NestedTensor]:
-        xs = self.body(tensor_list.tensors)
+        xs = self._forward_folded(tensor_list.tensors) if self.fold_bn else self.body(tensor_list.tensors)
         out = {}
         for name, x in xs.items():
             m = tensor_list.mask

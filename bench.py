@@ -115,10 +115,12 @@ def timed(fn, steps, world):
     """CUDA-event time of exactly `steps` calls, barrier + synchronize on both sides -> ms per step."""
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.nvtx.range_push("timed")          # ncu --nvtx --nvtx-include "timed/" selects this region
     e0.record()
     for i in range(steps):
         fn(i)
     e1.record()
+    torch.cuda.nvtx.range_pop()
     barrier(world)
     return e0.elapsed_time(e1) / steps
 

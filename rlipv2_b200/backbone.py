@@ -5,6 +5,7 @@ needs offline (no hard-coded weight paths): /root/reference/models/DDETR_backbon
 models/position_encoding.py:22-58.  Parameter/buffer names match (`backbone.0.body.*`).
 """
 import math
+import os
 from typing import Dict, List
 
 import torch
@@ -97,7 +98,7 @@ class Backbone(nn.Module):
         if dilation:
             self.strides[-1] = self.strides[-1] // 2
         self.body = IntermediateLayerGetter(backbone, return_layers=return_layers)
-        self.fold_bn = True
+        self.fold_bn = os.environ.get("RLIPV2_FOLD_BN", "1") != "0"    # A/B switch for measurements
 
     # ---- frozen-BN folding ----------------------------------------------------------------------------
     # The reference applies FrozenBatchNorm2d as separate broadcast mul / add kernels after every

@@ -14,6 +14,7 @@ from .criterion import SetCriterionHOI
 from .matcher import build_matcher
 from .parseda import RLIP_ParSeDA
 from .parseda_transformer import build_parseda_transformer
+from .postprocess import build_postprocessors
 
 
 def build_weight_dict(args):
@@ -75,7 +76,7 @@ def build_model(args):
         naive_obj_smooth=getattr(args, "naive_obj_smooth", 0), naive_verb_smooth=getattr(args, "naive_verb_smooth", 0),
         args=args)
     criterion.to(device)
-    postprocessors = {}          # evaluation post-processing (PostProcessHOI/SGG) is SURVEY section 8f rank 4
+    postprocessors = build_postprocessors(args)      # detr.py:683-691
     return model, criterion, postprocessors
 
 

@@ -15,3 +15,8 @@ def msda_cases():
 def load_msda(name):
     with np.load(os.path.join(GOLDEN, f"msda_{name}.npz")) as z:
         return {k: z[k] for k in z.files}
+
+
+def load_golden(filename):
+    """any fixture under tests/golden/ as an NpzFile (lazy per-key loading)"""
+    return np.load(os.path.join(GOLDEN, filename))

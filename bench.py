@@ -268,7 +268,7 @@ def run_train_step(args, rank, world, device):
         "e2e": {"value": BATCH * world / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
     }
-    if rank == 0:
+    if rank == 0 and not args.no_roofline:
         del ts, step, e2e
         torch.cuda.empty_cache()
         line["roofline"] = msda_roofline(device)
@@ -342,6 +342,7 @@ def main():
     ap.add_argument("--workload", default="train_step", choices=["train_step", "msda_step"])
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="A/B runs: skip the kernel micro-benchmarks")
     ap.add_argument("--no-graphs", dest="graphs", action="store_false", help="eager step instead of CUDA graphs")
     args = ap.parse_args()
     rank, world, local = dist_info()

@@ -41,6 +41,39 @@ class FrozenBatchNorm2d(nn.Module):
         return x * scale + bias
 
 
+_FUSED_CONV = os.environ.get("RLIPV2_FUSED_CONV", "1") != "0"      # A/B switch for measurements
+_BACKBONE_NHWC = os.environ.get("RLIPV2_BACKBONE_NHWC", "0") == "1"
+
+
+class _ConvBiasReLU(torch.autograd.Function):
+    """relu(conv(x, w) + b [+ residual]) as one cuDNN call (bias / residual / ReLU in the convolution's
+    epilogue) with a hand-written backward: ReLU mask, then cuDNN dgrad / wgrad.  `b` is the frozen-BN
+    shift (a constant), so no bias gradient is produced.  Replaces conv + broadcast add (+ add) + relu:
+    3-4 kernels -> 1 in the forward of every trainable bottleneck convolution."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, residual, stride, padding, dilation, groups):
+        if residual is not None:
+            y = torch.cudnn_convolution_add_relu(x, w, residual, 1.0, b, stride, padding, dilation, groups)
+        else:
+            y = torch.cudnn_convolution_relu(x, w, b, stride, padding, dilation, groups)
+        ctx.save_for_backward(x, w, y)
+        ctx.conf = (stride, padding, dilation, groups)
+        ctx.has_residual = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, w, y = ctx.saved_tensors
+        stride, padding, dilation, groups = ctx.conf
+        g = torch.ops.aten.threshold_backward(grad_out, y, 0)
+        gx, gw, _ = torch.ops.aten.convolution_backward(
+            g, x, w, None, stride, padding, dilation, False, [0, 0], groups,
+            [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        gres = g if (ctx.has_residual and ctx.needs_input_grad[3]) else None
+        return gx, gw, None, gres, None, None, None, None
+
+
 class PositionEmbeddingSine(nn.Module):
     """Normalised 2-D sine embedding over the un-padded extent (position_encoding.py:22-58)."""
 
@@ -109,22 +142,56 @@ class Backbone(nn.Module):
     # weight is recomputed from the live parameters every call (a [Cout,Cin,k,k] multiply), so gradients
     # still reach `conv.weight` through the product and checkpoints are untouched.
     @staticmethod
-    def _fold(conv, bn):
-        scale = bn.weight * (bn.running_var + bn.eps).rsqrt()
-        shift = bn.bias - bn.running_mean * scale
-        return conv.weight * scale.view(-1, 1, 1, 1), shift
+    def _bn_affine(bn):
+        """(scale, shift) of a FrozenBatchNorm2d.  The four buffers are constants between checkpoint loads,
+        so the pair is computed once and cached on the module, keyed on the buffers' version counters and
+        storage (load_state_dict / .to() invalidate it): 6 tiny kernels per convolution per step saved."""
+        bufs = (bn.weight, bn.bias, bn.running_mean, bn.running_var)
+        key = tuple((b._version, b.data_ptr()) for b in bufs)
+        cache = getattr(bn, "_affine_cache", None)
+        if cache is None or cache[0] != key:
+            with torch.no_grad():
+                scale = bn.weight * (bn.running_var + bn.eps).rsqrt()
+                shift = bn.bias - bn.running_mean * scale
+            cache = (key, scale, shift)
+            bn._affine_cache = cache
+        return cache[1], cache[2]
 
     @classmethod
-    def _conv_bn(cls, x, conv, bn, relu, residual=None):
+    def _fold(cls, conv, bn):
+        scale, shift = cls._bn_affine(bn)
+        w = conv.weight
+        if not w.requires_grad:
+            # frozen stem / layer1: the folded weight is a constant too
+            key = (w._version, w.data_ptr(), scale.data_ptr())
+            cache = getattr(conv, "_folded_cache", None)
+            if cache is None or cache[0] != key:
+                with torch.no_grad():
+                    cache = (key, w * scale.view(-1, 1, 1, 1))
+                conv._folded_cache = cache
+            return cache[1], shift
+        return w * scale.view(-1, 1, 1, 1), shift
+
+    @classmethod
+    def _conv_bn(cls, x, conv, bn, relu, residual=None, extra_bias=None, bias=True):
+        """conv + folded frozen BN (+ residual) (+ ReLU).  On CUDA every conv that ends in a ReLU runs as ONE
+        cuDNN call with the bias / residual / ReLU epilogue fused (`_ConvBiasReLU` when gradients are
+        needed); `bias=False` returns the bare convolution and hands the shift to the caller, which adds
+        it to the bias of the fused conv that consumes the result (`extra_bias`)."""
         w, b = cls._fold(conv, bn)
-        frozen = not (torch.is_grad_enabled() and (w.requires_grad or x.requires_grad))
-        if frozen and x.is_cuda and conv.groups == 1:
+        if extra_bias is not None:
+            b = b + extra_bias
+        if not bias:
+            return F.conv2d(x, w, None, conv.stride, conv.padding, conv.dilation, conv.groups), b
+        fused = x.is_cuda and conv.groups == 1 and (relu or residual is not None) and _FUSED_CONV
+        if fused:
+            if torch.is_grad_enabled() and (w.requires_grad or x.requires_grad):
+                return _ConvBiasReLU.apply(x, w, b, residual, conv.stride, conv.padding, conv.dilation, conv.groups)
             # cuDNN's fused conv + bias (+ residual) + ReLU epilogue (no autograd needed here)
             if residual is not None:
                 return torch.cudnn_convolution_add_relu(x, w, residual, 1.0, b, conv.stride, conv.padding,
                                                         conv.dilation, conv.groups)
-            if relu:
-                return torch.cudnn_convolution_relu(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+            return torch.cudnn_convolution_relu(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
         y = F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
         if residual is not None:
             y = y + residual
@@ -134,11 +201,19 @@ class Backbone(nn.Module):
     def _bottleneck(cls, x, blk):
         out = cls._conv_bn(x, blk.conv1, blk.bn1, True)
         out = cls._conv_bn(out, blk.conv2, blk.bn2, True)
-        identity = x if blk.downsample is None else cls._conv_bn(x, blk.downsample[0], blk.downsample[1], False)
+        if blk.downsample is None:
+            return cls._conv_bn(out, blk.conv3, blk.bn3, True, residual=x)
+        if x.is_cuda and _FUSED_CONV:
+            # the projection shortcut's BN shift rides on conv3's fused bias: one kernel fewer per block
+            identity, shift = cls._conv_bn(x, blk.downsample[0], blk.downsample[1], False, bias=False)
+            return cls._conv_bn(out, blk.conv3, blk.bn3, True, residual=identity, extra_bias=shift)
+        identity = cls._conv_bn(x, blk.downsample[0], blk.downsample[1], False)
         return cls._conv_bn(out, blk.conv3, blk.bn3, True, residual=identity)
 
     def _forward_folded(self, x):
         body = self.body
+        if _BACKBONE_NHWC and x.is_cuda:
+            x = x.contiguous(memory_format=torch.channels_last)
         frozen_stem = not any(p.requires_grad for p in body.layer1.parameters())
         with torch.set_grad_enabled(torch.is_grad_enabled() and not frozen_stem):
             x = self._conv_bn(x, body.conv1, body.bn1, True)         # stem + layer1 are frozen (:75-77)

@@ -203,21 +203,22 @@ class SetCriterionHOI(nn.Module):
         return [{k: v for k, v in outputs.items() if k != "aux_outputs"}] + list(outputs.get("aux_outputs", []))
 
     def forward(self, outputs, targets, matches=None):
-        """`matches`: optional list (one entry per decoder layer, order of `layers_of`) of
-        (indices, cost_list) computed by the caller - the CUDA-graph step computes the costs in the
-        forward graph, solves the assignment on the host and passes device index tensors here."""
+        """`matches`: optional, computed by the caller (the CUDA-graph step computes the costs in the forward
+        graph, solves the assignment on the host and passes device index tensors here) - either a list with
+        one (indices, cost_list) per decoder layer in the order of `layers_of`, or a `StackedMatches`."""
         layers = self.layers_of(outputs)
         device = next(iter(outputs.values())).device
         num_interactions = torch.full((1,), float(sum(len(t["obj_labels"]) for t in targets)), device=device)
         if _world() > 1:
             dist.all_reduce(num_interactions)
         num_interactions = torch.clamp(num_interactions / _world(), min=1)     # stays on the device
+        if matches is None:
+            matches = self.matcher.match_layers(layers, targets)
+        if self.stack_layers:
+            return self._forward_stacked(layers, targets, matches, num_interactions)
         losses = {}
         for li, layer in enumerate(layers):
-            if matches is not None:
-                indices, cost_list = matches[li]
-            else:
-                indices, cost_list = self.matcher(layer, targets, return_cost=True)
+            indices, cost_list = matches[li]
             sfx = "" if li == 0 else f"_{li - 1}"
             for loss in self.losses:
                 kwargs = {}
@@ -227,4 +228,192 @@ class SetCriterionHOI(nn.Module):
                     kwargs["cost_list"] = cost_list
                 l_dict = self.get_loss(loss, layer, targets, indices, num_interactions, **kwargs)
                 losses.update({k + sfx: v for k, v in l_dict.items()})
-        return {k: (v.reshape(()) if v.numel() == 1 else v) for k, v in losses.items()}
+        return LossDict({k: (v.reshape(()) if v.numel() == 1 else v) for k, v in losses.items()})
+
+    # ---- all decoder layers in one pass ------------------------------------------------------------------
+    # The reference evaluates the four losses once per decoder layer (hoi.py:4748-4764): ~340 tiny kernels per
+    # layer forward and as many again backward, all launch-bound.  Every loss is a per-(layer, image, query)
+    # map followed by a per-layer reduction, so the layers are concatenated along the batch axis, the maps run
+    # once, and the reductions become `view(n_layers, -1).sum(1)`.  Values equal the per-layer path up to the
+    # summation order of the reductions (checked in tests/test_criterion_stacked.py and against the golden).
+    stack_layers = True
+
+    @staticmethod
+    def _paired_giou(a, b):
+        """GIoU of box pairs a[i], b[i] (xyxy) - the diagonal of generalized_box_iou, same op order."""
+        area1 = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
+        area2 = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+        wh = (torch.min(a[:, 2:], b[:, 2:]) - torch.max(a[:, :2], b[:, :2])).clamp(min=0)
+        inter = wh[:, 0] * wh[:, 1]
+        union = area1 + area2 - inter
+        iou = inter / union
+        wh2 = (torch.max(a[:, 2:], b[:, 2:]) - torch.min(a[:, :2], b[:, :2])).clamp(min=0)
+        area = wh2[:, 0] * wh2[:, 1]
+        return iou - (area - union) / area
+
+    def _stack_consts(self, n_layers, bs, nq, ks, sizes, device):
+        """index constants of the stacked layout (functions of the static shapes only; cached)"""
+        key = (n_layers, bs, nq, tuple(ks), tuple(sizes), str(device))
+        cache = self.__dict__.setdefault("_stack_cache", {})
+        if key not in cache:
+            batch, t_off, layer, q_off = [], [], [], []
+            for li in range(n_layers):
+                t0 = 0
+                for b, (k, T) in enumerate(zip(ks, sizes)):
+                    batch += [li * bs + b] * k
+                    t_off += [t0] * k
+                    layer += [li] * k
+                    q_off += [b * nq] * k
+                    t0 += T
+            mk = lambda v: torch.tensor(v, dtype=torch.int64).to(device)
+            cache[key] = {"batch": mk(batch), "t_off": mk(t_off), "layer": mk(layer), "q_off": mk(q_off),
+                          "tgt_len": torch.tensor([float(T) for T in sizes] * n_layers).to(device)}
+        return cache[key]
+
+    def _ce_weight(self, C, device):
+        key = ("w", C, str(device))
+        cache = self.__dict__.setdefault("_stack_cache", {})
+        if key not in cache:
+            w = torch.ones(C)
+            w[-1] = float(self.eos_coef)
+            cache[key] = w.to(device)
+        return cache[key]
+
+    def _forward_stacked(self, layers, targets, matches, num_interactions):
+        n = len(layers)
+        obj_logits = torch.cat([l["pred_obj_logits"] for l in layers], 0)            # [n*bs, nq, C]
+        bs, nq = layers[0]["pred_obj_logits"].shape[:2]
+        device = obj_logits.device
+        sizes = [len(t["obj_labels"]) for t in targets]
+        if isinstance(matches, StackedMatches):
+            I_all, J_all, giou_st, ks = matches.I, matches.J, matches.giou, matches.ks
+        else:
+            ks = [int(I.shape[0]) for (I, _) in matches[0][0]]
+            I_all = torch.cat([I for ind, _ in matches for (I, _) in ind]).to(device)
+            J_all = torch.cat([J for ind, _ in matches for (_, J) in ind]).to(device)
+            giou_st = None
+            if self.giou_verb_label:
+                giou_st = -torch.stack([cl[0] for _, cl in matches])                     # [n, bs*nq, T]
+        K = sum(ks)
+        c = self._stack_consts(n, bs, nq, ks, sizes, device)
+        idx = (c["batch"], I_all)
+        tcol = J_all + c["t_off"]
+        per_layer = lambda x: x.reshape(n, -1).sum(1)
+        out = {}
+
+        # -- obj_labels (hoi.py:3696-3828): weighted CE, unmatched queries -> last class
+        def ce(logits, labels_all):
+            C = logits.shape[-1]
+            w = self._ce_weight(C, device)
+            classes = torch.full(logits.shape[:2], C - 1, dtype=torch.int64, device=device)
+            matched = labels_all[tcol]
+            classes[idx] = matched
+            flat = classes.reshape(-1)
+            nll = F.cross_entropy(logits.reshape(-1, C), flat, w, reduction="none")      # = w[y] * nll
+            return per_layer(nll) / per_layer(w[flat]), matched
+
+        if "obj_labels" in self.losses:
+            loss_obj, matched_obj = ce(obj_logits, torch.cat([t["obj_labels"] for t in targets]))
+            i0 = (c["batch"][:K], I_all[:K])                                            # layer 0 = final layer
+            out["obj_class_error"] = [100 - accuracy(layers[0]["pred_obj_logits"][i0], matched_obj[:K])[0]]
+            if self.subject_class:
+                sub_logits = torch.cat([l["pred_sub_logits"] for l in layers], 0)
+                loss_sub, matched_sub = ce(sub_logits, torch.cat([t["sub_labels"] for t in targets]))
+                loss_obj = loss_obj + loss_sub
+                out["sub_class_error"] = [100 - accuracy(layers[0]["pred_sub_logits"][i0], matched_sub[:K])[0]]
+            out["loss_obj_ce"] = loss_obj
+
+        # -- obj_cardinality (hoi.py:3909-3923)
+        if "obj_cardinality" in self.losses:
+            with torch.no_grad():
+                card_pred = (obj_logits.argmax(-1) != obj_logits.shape[-1] - 1).sum(1)
+                out["obj_cardinality_error"] = (card_pred.float() - c["tgt_len"]).abs().view(n, bs).mean(1)
+
+        # -- verb_labels (hoi.py:3925-4028, 4453-4495)
+        if "verb_labels" in self.losses:
+            src_logits = torch.cat([l["pred_verb_logits"] for l in layers], 0)
+            labels = torch.cat([t["verb_labels"] for t in targets])[tcol]
+            if self.giou_verb_label:
+                s = (giou_st[c["layer"], c["q_off"] + I_all, tcol] + 1) / 2
+                if self.pseudo_verb:
+                    labels = labels + layers[0]["target_verb_sim"][tcol]
+                labels = labels * s.unsqueeze(-1)
+            if self.use_no_verb_token:
+                src_logits = src_logits[:, :, :src_logits.shape[2] - 1]
+            target = torch.zeros_like(src_logits)
+            target[idx] = labels.to(target.dtype)
+            if self.verb_loss_type == "bce":
+                bce = F.binary_cross_entropy_with_logits(src_logits, target, reduction="none")
+                out["loss_verb_ce"] = bce.reshape(n, -1).mean(1)
+            else:
+                pred = torch.clamp(src_logits.sigmoid(), 1e-6, 1. - 1e-6)
+                if self.giou_verb_label:                      # _soft_neg_loss, beta = 2
+                    num_pos = per_layer(target.gt(0).float())
+                    el = torch.pow(torch.abs(target - pred), 2) * ((1 - target) * torch.log(1 - pred)
+                                                                   + target * torch.log(pred))
+                    tot = per_layer(el)
+                    out["loss_verb_ce"] = torch.where(num_pos == 0, -tot, -tot / num_pos.clamp(min=1))
+                else:                                         # _neg_loss
+                    pos_inds, neg_inds = target.eq(1).float(), target.lt(1).float()
+                    pos = per_layer(torch.log(pred) * torch.pow(1 - pred, 2) * pos_inds)
+                    neg = per_layer(torch.log(1 - pred) * torch.pow(pred, 2) * torch.pow(1 - target, 4) * neg_inds)
+                    num_pos = per_layer(pos_inds)
+                    out["loss_verb_ce"] = torch.where(num_pos == 0, -neg, -(pos + neg) / num_pos.clamp(min=1))
+
+        # -- sub_obj_boxes (hoi.py:4162-4193)
+        if "sub_obj_boxes" in self.losses:
+            src_sub = torch.cat([l["pred_sub_boxes"] for l in layers], 0)[idx]           # [n*K, 4]
+            src_obj = torch.cat([l["pred_obj_boxes"] for l in layers], 0)[idx]
+            if K == 0:
+                z_s, z_o = per_layer(src_sub), per_layer(src_obj)
+                out.update(loss_sub_bbox=z_s, loss_obj_bbox=z_o, loss_sub_giou=z_s, loss_obj_giou=z_o)
+            else:
+                tgt_sub = torch.cat([t["sub_boxes"] for t in targets])[tcol]
+                tgt_obj = torch.cat([t["obj_boxes"] for t in targets])[tcol]
+                exist = (tgt_obj != 0).any(dim=1)
+                n_exist = per_layer(exist) + 1e-4
+                giou_sub = 1 - self._paired_giou(box_cxcywh_to_xyxy(src_sub), box_cxcywh_to_xyxy(tgt_sub))
+                giou_obj = 1 - self._paired_giou(box_cxcywh_to_xyxy(src_obj), box_cxcywh_to_xyxy(tgt_obj))
+                out["loss_sub_bbox"] = per_layer((src_sub - tgt_sub).abs()) / num_interactions
+                out["loss_obj_bbox"] = per_layer((src_obj - tgt_obj).abs() * exist.unsqueeze(1)) / n_exist
+                out["loss_sub_giou"] = per_layer(giou_sub) / num_interactions
+                out["loss_obj_giou"] = per_layer(giou_obj * exist) / n_exist
+
+        # reference key order: per layer, losses in self.losses order (hoi.py:4745-4764)
+        order = {"obj_labels": ("loss_obj_ce", "obj_class_error", "sub_class_error"),
+                 "obj_cardinality": ("obj_cardinality_error",), "verb_labels": ("loss_verb_ce",),
+                 "sub_obj_boxes": ("loss_sub_bbox", "loss_obj_bbox", "loss_sub_giou", "loss_obj_giou")}
+        losses = LossDict()
+        for li in range(n):
+            sfx = "" if li == 0 else f"_{li - 1}"
+            for loss in self.losses:
+                for k in order[loss]:
+                    if k in out and li < len(out[k]):
+                        losses[k + sfx] = out[k][li].reshape(())
+        # the weighted total the train loop forms key by key (engine.py:108), as one dot product
+        keys = [k for k in order["obj_labels"][:1] + order["verb_labels"] + order["sub_obj_boxes"]
+                if k in out and k in self.weight_dict]
+        if keys:
+            wkey = ("wmat", tuple(keys), n, str(device))
+            cache = self.__dict__.setdefault("_stack_cache", {})
+            if wkey not in cache:
+                sf = lambda li: "" if li == 0 else f"_{li - 1}"
+                cache[wkey] = torch.tensor([[float(self.weight_dict.get(k + sf(li), 0.0)) for li in range(n)]
+                                            for k in keys]).to(device)
+            losses.weighted_total = (torch.stack([out[k] for k in keys]) * cache[wkey]).sum()
+        return losses
+
+
+class LossDict(dict):
+    """dict of loss scalars; `weighted_total` (when set) is sum_k loss[k] * weight_dict[k] formed on the device
+    in one reduction instead of ~45 scalar kernels."""
+    weighted_total = None
+
+
+class StackedMatches:
+    """Assignment of all decoder layers in the stacked layout used by `_forward_stacked`:
+    I, J  int64 [n_layers * K] query / target indices ordered (layer, image, match), K = sum(ks);
+    giou  [n_layers, bs*nq, T] pairwise GIoU (= -cost_giou) or None;  ks = matches per image."""
+
+    def __init__(self, I, J, giou, ks):
+        self.I, self.J, self.giou, self.ks = I, J, giou, list(ks)

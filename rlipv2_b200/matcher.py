@@ -47,6 +47,40 @@ class HungarianMatcherHOI(nn.Module):
             t = t[:, :t.shape[1] - 1]
         return t
 
+    KEYS = ("pred_sub_logits", "pred_obj_logits", "pred_verb_logits", "pred_sub_boxes", "pred_obj_boxes")
+
+    @torch.no_grad()
+    def compute_costs_layers(self, layers, targets):
+        """Costs of several decoder layers in one pass.  Every op of `compute_costs` is row-wise over the
+        (image, query) rows, so the layers' predictions are concatenated along the batch axis and the ~60
+        small kernels run once instead of once per layer; each layer's entries are bit-identical to a
+        per-layer call.  -> (C [n_layers, bs, nq, T], [cost_list per layer] (views))"""
+        n = len(layers)
+        if n == 1:
+            C, cl = self.compute_costs(layers[0], targets)
+            return C.unsqueeze(0), [cl]
+        stacked = {k: torch.cat([l[k] for l in layers], 0) for k in self.KEYS if k in layers[0]}
+        bs, nq = layers[0]["pred_obj_logits"].shape[:2]
+        C, cl = self.compute_costs(stacked, targets, row_chunks=n)    # rows ordered (layer, image, query)
+        C = C.view(n, bs, nq, -1)
+        rows = bs * nq
+
+        def part(x, i):
+            if isinstance(x, tuple):
+                return tuple(part(y, i) for y in x)
+            return x[i * rows:(i + 1) * rows]
+        return C, [[part(x, i) for x in cl] for i in range(n)]
+
+    @torch.no_grad()
+    def match_layers(self, layers, targets):
+        """[(indices, cost_list)] for every decoder layer with ONE device->host copy of all cost tensors
+        (the reference does one per layer, twice per layer with --giou_verb_label: matcher.py:185,
+        hoi.py:3933)."""
+        C, cost_lists = self.compute_costs_layers(layers, targets)
+        sizes = [len(v["obj_labels"]) for v in targets]
+        C_cpu = C.cpu()
+        return [(self.solve(C_cpu[i], sizes), cost_lists[i]) for i in range(len(layers))]
+
     @torch.no_grad()
     def forward(self, outputs, targets, return_cost=False):
         C, cost_list = self.compute_costs(outputs, targets)
@@ -60,7 +94,7 @@ class HungarianMatcherHOI(nn.Module):
         return [(torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)) for i, j in indices]
 
     @torch.no_grad()
-    def compute_costs(self, outputs, targets):
+    def compute_costs(self, outputs, targets, row_chunks=1):
         """Device part (capturable in a CUDA graph): -> (C [bs, nq, T], cost_list as matcher.py:197-199)."""
         bs, num_queries = outputs["pred_obj_logits"].shape[:2]
         out_obj_prob = outputs["pred_obj_logits"].flatten(0, 1).softmax(-1)
@@ -80,8 +114,16 @@ class HungarianMatcherHOI(nn.Module):
             if out_verb_prob.shape[1] - 1 == tgt_verb.shape[0]:              # trailing "no verb" column
                 out_verb_prob = out_verb_prob[:, :out_verb_prob.shape[1] - 1]
 
-        cost_verb_class = -(out_verb_prob.matmul(tgt_verb) / (tgt_verb.sum(dim=0, keepdim=True) + 1e-4)
-                            + (1 - out_verb_prob).matmul(1 - tgt_verb)
+        def mm(a, b):
+            # the one contraction of the cost build.  GEMM libraries pick kernels (hence summation orders) by
+            # row count, so the stacked call multiplies layer by layer: costs - and the LSAP tie-breaks that
+            # hang on their last bit - stay identical to a per-layer call.
+            if row_chunks == 1:
+                return a.matmul(b)
+            return torch.cat([c.matmul(b) for c in a.chunk(row_chunks, 0)], 0)
+
+        cost_verb_class = -(mm(out_verb_prob, tgt_verb) / (tgt_verb.sum(dim=0, keepdim=True) + 1e-4)
+                            + mm(1 - out_verb_prob, 1 - tgt_verb)
                             / ((1 - tgt_verb).sum(dim=0, keepdim=True) + 1e-4)) / 2
 
         cost_sub_bbox = torch.cdist(out_sub_bbox, tgt_sub_boxes, p=1)

@@ -18,6 +18,7 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 from torch.nn.init import constant_, xavier_uniform_
 
+from . import dense
 from .dropin import MultiScaleDeformableAttention as MSDA
 
 
@@ -107,13 +108,13 @@ class MSDeformAttn(nn.Module):
         else:
             assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
 
-        value = self.value_proj(input_flatten)
+        value = dense.linear(input_flatten, self.value_proj.weight, self.value_proj.bias)
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
-        sampling_offsets = self.sampling_offsets(query).view(
+        sampling_offsets = dense.linear(query, self.sampling_offsets.weight, self.sampling_offsets.bias).view(
             N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
-        attention_weights = self.attention_weights(query).view(
+        attention_weights = dense.linear(query, self.attention_weights.weight, self.attention_weights.bias).view(
             N, Len_q, self.n_heads, self.n_levels * self.n_points)
         attention_weights = F.softmax(attention_weights, -1).view(
             N, Len_q, self.n_heads, self.n_levels, self.n_points)
@@ -129,4 +130,4 @@ class MSDeformAttn(nn.Module):
                 reference_points.shape[-1]))
         output = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index,
                                             sampling_locations, attention_weights, self.im2col_step)
-        return self.output_proj(output)
+        return dense.linear(output, self.output_proj.weight, self.output_proj.bias)

@@ -8,6 +8,7 @@ Parameter names and aliases are identical: the box heads are registered as `sub_
 `transformer.verb_decoder.*_bbox_embed.{0..2}` (hoi.py:1980-1990).
 """
 import copy
+import os
 import math
 
 import torch
@@ -17,6 +18,9 @@ from torch import nn
 from . import dense
 from .nested import NestedTensor, inverse_sigmoid, nested_tensor_from_tensor_list
 from .parseda_transformer import MLP
+
+
+_TEXT_STREAM = os.environ.get("RLIPV2_TEXT_STREAM", "1") != "0"      # A/B switch for measurements
 
 
 def _get_clones(module, n):
@@ -92,6 +96,8 @@ class RLIP_ParSeDA(nn.Module):
 
     # ---- phase A: backbone + input projections + encoder -------------------------------------------
     def _encode(self, samples, text):
+        if _TEXT_STREAM and samples.tensors.is_cuda and self.transformer._is_label_text(text):
+            text = self.transformer.encode_text_async(text, samples.tensors.device)   # overlaps the backbone
         features, pos = self.backbone(samples)
         srcs, masks = [], []
         for l, feat in enumerate(features):

@@ -446,6 +446,35 @@ class RLIP_ParSeDABDeformableTransformer_v2(nn.Module):
         text_attention_mask = ~(text_memory.sum(dim=-1) > 0)
         return text_memory, text_attention_mask, obj_pred_names_sums
 
+    @staticmethod
+    def _is_label_text(text):
+        return isinstance(text, dict) or (isinstance(text, list) and len(text) > 0 and isinstance(text[0], tuple))
+
+    def encode_text_async(self, text, device):
+        """Start `encode_text` on a side stream and return a handle that `forward(text=handle)` joins where
+        the label embeddings are first needed.  The text tower (12 RoBERTa layers on 3-8 token strings) is
+        ~350 launch-bound kernels forward and ~700 backward that do not depend on the image: forked before
+        the backbone they run under the convolutions instead of after them - and autograd replays the
+        backward of these nodes on the same side stream, i.e. under the backbone's backward.  Works eagerly
+        and inside a CUDA-graph capture (the fork/join become graph edges)."""
+        cur = torch.cuda.current_stream(device)
+        if getattr(self, "_text_stream", None) is None:
+            self._text_stream = torch.cuda.Stream(device)
+        side = self._text_stream
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            text_memory, text_attention_mask, sums = self.encode_text(text, device)
+        return {"_async_text": (text_memory, text_attention_mask, sums), "_stream": side}
+
+    @staticmethod
+    def _join_text(handle, device):
+        cur = torch.cuda.current_stream(device)
+        cur.wait_stream(handle["_stream"])
+        text_memory, text_attention_mask, sums = handle["_async_text"]
+        for t in (text_memory, text_attention_mask):
+            t.record_stream(cur)
+        return text_memory, text_attention_mask, sums
+
     # ---- forward ------------------------------------------------------------------------------
     def forward(self, srcs=None, masks=None, pos_embeds=None, query_embed=None, text=None, encode_and_save=True,
                 text_memory=None, img_memory=None, text_attention_mask=None, obj_pred_names_sums=None,
@@ -471,8 +500,13 @@ class RLIP_ParSeDABDeformableTransformer_v2(nn.Module):
         spatial_shapes, level_start_index = _level_tensors(tuple(shapes_host), device)
         valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
 
-        if isinstance(text, dict) or (isinstance(text, list) and isinstance(text[0], tuple)):   # training: label strings
+        if isinstance(text, dict) and "_async_text" in text:            # training, text tower already in flight
+            text_memory, text_attention_mask, obj_pred_names_sums = self._join_text(text, device)
+            text = None
+        elif self._is_label_text(text):                                     # training: label strings
             text_memory, text_attention_mask, obj_pred_names_sums = self.encode_text(text, device)
+            text = None
+        if text is None:
             lang = text_memory
             if lang.shape[1] != bs:
                 lang = lang.repeat(1, bs, 1)

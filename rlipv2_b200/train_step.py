@@ -91,9 +91,7 @@ class ParSeDATrainStep:
         """One optimisation step on a batch that is already resident in HBM."""
         memory_cache = self.model(samples, encode_and_save=True, text=text, targets=targets)
         outputs = self.model(samples, encode_and_save=False, memory_cache=memory_cache, text=text, targets=targets)
-        loss_dict = self.criterion(outputs, targets)
-        wd = self.criterion.weight_dict
-        losses = sum(loss_dict[k] * wd[k] for k in loss_dict.keys() if k in wd)
+        losses = self._weighted_total(self.criterion(outputs, targets))
         self.optimizer.zero_grad(set_to_none=True)
         losses.backward()
         if self.clip_max_norm > 0:
@@ -104,6 +102,15 @@ class ParSeDATrainStep:
     def step(self, images_host, targets_host, text):
         samples, targets = self.to_device(images_host, targets_host)
         return self.step_device(samples, targets, text)
+
+    def _weighted_total(self, loss_dict):
+        """engine.py:108 `sum(loss_dict[k] * weight_dict[k] ...)`; the criterion already formed it on the
+        device as one dot product when it evaluated all decoder layers in one pass."""
+        total = getattr(loss_dict, "weighted_total", None)
+        if total is not None:
+            return total
+        wd = self.criterion.weight_dict
+        return sum(loss_dict[k] * wd[k] for k in loss_dict.keys() if k in wd)
 
 
 class GraphedParSeDATrainStep(ParSeDATrainStep):
@@ -136,15 +143,15 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         outputs = self.module(self.s_samples, encode_and_save=False, memory_cache=cache, text=self.s_tok,
                               targets=self.s_targets)
         layers = self.criterion.layers_of(outputs)
-        costs = [self.criterion.matcher.compute_costs(l, self.s_targets) for l in layers]
-        self.h_cost.copy_(torch.stack([c for c, _ in costs]), non_blocking=True)
-        return outputs, [cl for _, cl in costs]
+        C, cost_lists = self.criterion.matcher.compute_costs_layers(layers, self.s_targets)   # all layers, one pass
+        self.h_cost.copy_(C, non_blocking=True)
+        giou = -torch.stack([cl[0] for cl in cost_lists]) if self.criterion.giou_verb_label else None
+        return outputs, giou
 
-    def _loss_backward_step(self, outputs, cost_lists):
-        matches = [(self.s_idx[li], cost_lists[li]) for li in range(len(cost_lists))]
-        loss_dict = self.criterion(outputs, self.s_targets, matches=matches)
-        wd = self.criterion.weight_dict
-        total = sum(loss_dict[k] * wd[k] for k in loss_dict.keys() if k in wd)
+    def _loss_backward_step(self, outputs, giou):
+        from .criterion import StackedMatches
+        matches = StackedMatches(self.s_I, self.s_J, giou, self.ks)
+        total = self._weighted_total(self.criterion(outputs, self.s_targets, matches=matches))
         self.flat_grad.zero_()
         total.backward()
         if self.world > 1:
@@ -165,14 +172,17 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
                             self.exp_avg_sq[start:end], lr, 0.9, 0.999, 1e-8, self.weight_decay, self.step_t)
 
     def _solve_assignment(self):
-        """host: LSAP on the pinned cost tensor [layers, bs, nq, T] -> static device index buffers"""
+        """host: LSAP on the pinned cost tensor [layers, bs, nq, T] -> the static device index buffers
+        (stacked layout of criterion.StackedMatches: ordered layer, image, match), one H2D copy each"""
+        o = 0
         for li in range(self.h_cost.shape[0]):
-            ind = self.criterion.matcher.solve(self.h_cost[li], self.sizes)
-            for b, (i, j) in enumerate(ind):
-                self.h_idx[li][b][0].copy_(i)
-                self.h_idx[li][b][1].copy_(j)
-                self.s_idx[li][b][0].copy_(self.h_idx[li][b][0], non_blocking=True)
-                self.s_idx[li][b][1].copy_(self.h_idx[li][b][1], non_blocking=True)
+            for i, j in self.criterion.matcher.solve(self.h_cost[li], self.sizes):
+                k = i.shape[0]
+                self.h_I[o:o + k].copy_(i)
+                self.h_J[o:o + k].copy_(j)
+                o += k
+        self.s_I.copy_(self.h_I, non_blocking=True)
+        self.s_J.copy_(self.h_J, non_blocking=True)
 
     def capture(self, images_host, targets_host, text, warmup=3):
         dev = self.device
@@ -182,10 +192,10 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         nq = self.args.num_queries // 2
         n_layers = self.args.dec_layers
         self.h_cost = torch.empty(n_layers, len(self.sizes), nq, sum(self.sizes)).pin_memory()
-        self.h_idx = [[(torch.zeros(n, dtype=torch.long).pin_memory(), torch.zeros(n, dtype=torch.long).pin_memory())
-                       for n in self.sizes] for _ in range(n_layers)]
-        self.s_idx = [[(torch.zeros(n, dtype=torch.long, device=dev), torch.zeros(n, dtype=torch.long, device=dev))
-                       for n in self.sizes] for _ in range(n_layers)]
+        self.ks = [min(nq, n) for n in self.sizes]                 # matches per image (LSAP on nq x n)
+        K = n_layers * sum(self.ks)
+        self.h_I, self.h_J = torch.zeros(K, dtype=torch.long).pin_memory(), torch.zeros(K, dtype=torch.long).pin_memory()
+        self.s_I, self.s_J = torch.zeros(K, dtype=torch.long, device=dev), torch.zeros(K, dtype=torch.long, device=dev)
 
         # One stream for the probe, the warm-up and both captures: autograd runs every backward node
         # (AccumulateGrad included) on the stream its forward op first ran on, so all of them must be
@@ -196,7 +206,7 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         for p in self.module.parameters():
             p.grad = None
         with torch.cuda.stream(side):
-            outputs, cost_lists = self._forward_and_costs_eager_probe()
+            outputs, giou = self._forward_and_costs_eager_probe()
         side.synchronize()
         used_ids = {id(p) for p in self.module.parameters() if p.requires_grad and p.grad is not None}
         named = [(n, p) for n, p in self.module.named_parameters() if id(p) in used_ids]
@@ -240,31 +250,30 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         # 3. warm-up on a side stream (cuBLAS/cuDNN workspaces, lazy inits), then capture
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                outputs, cost_lists = self._forward_and_costs()
+                outputs, giou = self._forward_and_costs()
                 side.synchronize()
                 self._solve_assignment()
-                self._loss_backward_step(outputs, cost_lists)
+                self._loss_backward_step(outputs, giou)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph_a = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_a, stream=self.cap_stream):
-            outputs, cost_lists = self._forward_and_costs()
+            outputs, giou = self._forward_and_costs()
         self.graph_b = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool(), stream=self.cap_stream):
-            self.s_loss = self._loss_backward_step(outputs, cost_lists)
-        self._keep = (outputs, cost_lists)      # the autograd graph's buffers belong to the captured pool
+            self.s_loss = self._loss_backward_step(outputs, giou)
+        self._keep = (outputs, giou)      # the autograd graph's buffers belong to the captured pool
         self.done_a = torch.cuda.Event()
         self.captured = True
 
     def _forward_and_costs_eager_probe(self):
-        outputs, cost_lists = self._forward_and_costs()
+        outputs, giou = self._forward_and_costs()
         torch.cuda.current_stream().synchronize()
         self._solve_assignment()
-        matches = [(self.s_idx[li], cost_lists[li]) for li in range(len(cost_lists))]
-        loss_dict = self.criterion(outputs, self.s_targets, matches=matches)
-        wd = self.criterion.weight_dict
-        sum(loss_dict[k] * wd[k] for k in loss_dict.keys() if k in wd).backward()
-        return outputs, cost_lists
+        from .criterion import StackedMatches
+        matches = StackedMatches(self.s_I, self.s_J, giou, self.ks)
+        self._weighted_total(self.criterion(outputs, self.s_targets, matches=matches)).backward()
+        return outputs, giou
 
     def replay(self):
         """One step on the batch currently held by the static buffers."""

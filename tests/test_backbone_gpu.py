@@ -1,0 +1,54 @@
+"""Backbone fused-convolution path (cuDNN bias/residual/ReLU epilogue + hand-written backward) against the
+plain conv -> FrozenBatchNorm -> (+residual) -> ReLU formulation of the reference
+(/root/reference/models/DDETR_backbone.py:31-68 + torchvision Bottleneck)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_bn_(m, g):
+    from rlipv2_b200.backbone import FrozenBatchNorm2d
+    for mod in m.modules():
+        if isinstance(mod, FrozenBatchNorm2d):
+            mod.weight.copy_(torch.rand(mod.weight.shape, generator=g) + 0.5)
+            mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.1)
+            mod.running_mean.copy_(torch.randn(mod.bias.shape, generator=g) * 0.1)
+            mod.running_var.copy_(torch.rand(mod.bias.shape, generator=g) + 0.5)
+
+
+@pytest.mark.parametrize("nhwc", [False, True])
+def test_fused_backbone_matches_unfolded_body(nhwc, monkeypatch):
+    import rlipv2_b200.backbone as bb
+    from rlipv2_b200 import dense
+    from rlipv2_b200.nested import NestedTensor
+    dense.set_matmul_precision("fp32")
+    monkeypatch.setattr(bb, "_BACKBONE_NHWC", nhwc)
+    monkeypatch.setattr(bb, "_FUSED_CONV", True)
+    g = torch.Generator().manual_seed(0)
+    net = bb.Backbone("resnet50", True, True, False)
+    with torch.no_grad():
+        _rand_bn_(net, g)
+    net = net.cuda()
+    x = torch.randn(2, 3, 96, 128, generator=g).cuda()
+    mask = torch.zeros(2, 96, 128, dtype=torch.bool, device="cuda")
+
+    def run(fold):
+        net.fold_bn = fold
+        for p in net.parameters():
+            p.grad = None
+        out = net(NestedTensor(x, mask))
+        loss = sum((o.tensors.float() ** 2).mean() * (i + 1) for i, (_, o) in enumerate(sorted(out.items())))
+        loss.backward()
+        feats = [o.tensors.detach().contiguous() for _, o in sorted(out.items())]
+        grads = {n: p.grad.detach().clone() for n, p in net.named_parameters() if p.grad is not None}
+        return feats, grads
+
+    f_ref, g_ref = run(False)          # torchvision body: conv, FrozenBatchNorm2d, relu as separate ops
+    f_new, g_new = run(True)
+    assert set(g_ref) == set(g_new) and len(g_new) > 30
+    for a, b in zip(f_ref, f_new):
+        torch.testing.assert_close(b, a, rtol=1e-3, atol=1e-4)
+    for n in g_ref:
+        scale = g_ref[n].abs().max().clamp_min(1e-6)
+        assert ((g_new[n] - g_ref[n]).abs().max() / scale) < 2e-3, n

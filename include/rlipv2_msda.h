@@ -39,10 +39,11 @@
 extern "C" {
 #endif
 
-#define RLIPV2_MSDA_ABI_VERSION 1
+#define RLIPV2_MSDA_ABI_VERSION 2
 
 #define RLIPV2_MSDA_EINVAL   (-1) /* negative / zero dimension where not allowed, null pointer */
 #define RLIPV2_MSDA_ETOOBIG  (-2) /* an index would overflow the 64-bit-safe limits we support  */
+#define RLIPV2_MSDA_ESHAPE   (-3) /* fused-prologue entry points: shape outside fp32, D=32, L=4, P=4 */
 
 /* ms_deform_attn_cuda_forward (ms_deform_attn_cuda.cu:20-80), scalar_t = float.
  * Writes every element of `out` (no pre-zeroing needed). */
@@ -76,6 +77,32 @@ int rlipv2_msda_backward_f64(const double *value, const int64_t *spatial_shapes,
                              int spatial_size, int num_heads, int channels, int num_levels,
                              int num_query, int num_point, double *grad_value,
                              double *grad_sampling_loc, double *grad_attn_weight, void *stream);
+
+/* ---- fused-prologue variant (the module's arithmetic folded into the op) -----------------------------
+ * Replaces, for 2-d reference points (the encoder self-attention; `reference_points.shape[-1] == 2`),
+ *   /root/reference/models/ops/modules/ms_deform_attn.py:102-109
+ *       attention_weights = F.softmax(attention_weights(query).view(N, Lq, M, L*P), -1)
+ *       sampling_locations = reference_points[:, :, None, :, None, :]
+ *                            + sampling_offsets / offset_normalizer[None, None, None, :, None, :]
+ *   + the op call of :116 - i.e. the ~6 elementwise kernels over [N, Lq, M, L, P, 2] tensors that the
+ *   reference (through torch) launches around the native op, forward and backward.
+ *     reference_points [batch, num_query, num_levels, 2]   (x, y) in [0,1], not differentiated
+ *     proj             [batch, num_query, num_heads*num_levels*num_point*3]: the query projected by the
+ *                      stacked weights [sampling_offsets.weight ; attention_weights.weight]: first the
+ *                      M*L*P*2 raw sampling offsets, then the M*L*P raw attention logits
+ *     grad_proj        same shape; every element written once (no pre-zeroing needed)
+ * Only fp32, channels = 32, num_levels = 4, num_point = 4 (every ParSeDA call); other shapes return
+ * RLIPV2_MSDA_ESHAPE and the caller uses the plain entry points. */
+int rlipv2_msda_proj_forward_f32(const float *value, const int64_t *spatial_shapes,
+                                 const int64_t *level_start_index, const float *reference_points,
+                                 const float *proj, int batch, int spatial_size, int num_heads, int channels,
+                                 int num_levels, int num_query, int num_point, float *out, void *stream);
+
+int rlipv2_msda_proj_backward_f32(const float *value, const int64_t *spatial_shapes,
+                                  const int64_t *level_start_index, const float *reference_points,
+                                  const float *proj, const float *grad_out, int batch, int spatial_size,
+                                  int num_heads, int channels, int num_levels, int num_query, int num_point,
+                                  float *grad_value, float *grad_proj, void *stream);
 
 /* Human-readable text for a return code of the functions above (static storage). */
 const char *rlipv2_msda_error_string(int code);

@@ -42,7 +42,10 @@ class FrozenBatchNorm2d(nn.Module):
 
 
 _FUSED_CONV = os.environ.get("RLIPV2_FUSED_CONV", "1") != "0"      # A/B switch for measurements
-_BACKBONE_NHWC = os.environ.get("RLIPV2_BACKBONE_NHWC", "0") == "1"
+# channels_last activations through the backbone: cuDNN's TF32 kernels are NHWC-native, so NCHW tensors cost a
+# nchwToNhwc / nhwcToNchw pair around every convolution (3.3 ms per step); with BN folded and bias / residual /
+# ReLU fused into the convolutions there is no NCHW-favouring elementwise pass left (measured: 44.0 -> 39.5 ms).
+_BACKBONE_NHWC = os.environ.get("RLIPV2_BACKBONE_NHWC", "1") != "0"
 
 
 class _ConvBiasReLU(torch.autograd.Function):

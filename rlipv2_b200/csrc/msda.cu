@@ -119,23 +119,77 @@ __device__ __forceinline__ void load_level_table(LevelRow *lvl_tab, const int64_
     __syncthreads();
 }
 
+// Where the 16 (location, weight) of a pair come from.
+//   plain op (the reference's native boundary): sampling_loc [NQ, M, L, P, 2] + attn_weight [NQ, M, L, P];
+//   fused prologue (PROJ): the raw projection of the query, proj [NQ, M*L*P*3] = M*L*P*2 sampling
+//   offsets followed by M*L*P attention logits (one GEMM with the two nn.Linear weights stacked), and
+//   the 2-d reference points ref [NQ, L, 2].  The kernel then does what ms_deform_attn.py:102-109
+//   does with ~6 elementwise passes over [NQ, M, L, P, 2] tensors: softmax over the pair's 16 logits
+//   and loc = ref + offset / (W_l, H_l).
+struct PairSrc {
+    const float *loc, *attn;
+    const float *proj, *ref;
+};
+
+__device__ __forceinline__ float group_max8(float x) {
+    x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+    x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 2));
+    return fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 4));
+}
+
+__device__ __forceinline__ float group_sum8(float x) {
+    x += __shfl_xor_sync(0xffffffffu, x, 1);
+    x += __shfl_xor_sync(0xffffffffu, x, 2);
+    return x + __shfl_xor_sync(0xffffffffu, x, 4);
+}
+
+// This lane's two points (2*sub, 2*sub+1 - both on level sub/2) of pair (Q, m): locations l4 =
+// (x0, y0, x1, y1) and attention weights a2.  Must be called by all 32 lanes (group shuffles).
+template <bool PROJ>
+__device__ __forceinline__ void lane_points(const PairSrc &src, const WarpCtx &c, const LevelRow &my,
+                                            int Q, int M, int m, bool live, float4 &l4, float2 &a2)
+{
+    l4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    a2 = make_float2(0.f, 0.f);
+    if (!PROJ) {
+        if (live) {
+            const size_t pair = (size_t)Q * M + m;
+            l4 = ldg_f4(src.loc + pair * (kFastLP * 2) + c.sub * 4);
+            a2 = __ldg(reinterpret_cast<const float2 *>(src.attn + pair * kFastLP + c.sub * 2));
+        }
+        return;
+    }
+    float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 lg = make_float2(0.f, 0.f), r = make_float2(0.f, 0.f);
+    if (live) {
+        const float *row = src.proj + (size_t)Q * (size_t)(M * kFastLP * 3);
+        o4 = ldg_f4(row + m * (kFastLP * 2) + c.sub * 4);
+        lg = __ldg(reinterpret_cast<const float2 *>(row + M * (kFastLP * 2) + m * kFastLP + c.sub * 2));
+        r = __ldg(reinterpret_cast<const float2 *>(src.ref + ((size_t)Q * kFastL + (c.sub >> 1)) * 2));
+    }
+    // softmax over the 16 logits of the pair (F.softmax(.., -1), ms_deform_attn.py:104)
+    const float mx = group_max8(fmaxf(lg.x, lg.y));
+    const float e0 = expf(lg.x - mx), e1 = expf(lg.y - mx);
+    const float sum = group_sum8(e0 + e1);
+    a2 = make_float2(__fdiv_rn(e0, sum), __fdiv_rn(e1, sum));
+    // ms_deform_attn.py:106-109: loc = ref[:, :, None, :, None, :] + offsets / (W_l, H_l)
+    const float Wf = (float)my.W, Hf = (float)my.H;
+    l4 = make_float4(r.x + __fdiv_rn(o4.x, Wf), r.y + __fdiv_rn(o4.y, Hf),
+                     r.x + __fdiv_rn(o4.z, Wf), r.y + __fdiv_rn(o4.w, Hf));
+}
+
 // forward for the 4 pairs (same head m, queries Q of the 4 lane groups) owned by this warp
-template <int UNROLL>
-__device__ __forceinline__ void fwd_warp_pairs(const float *__restrict__ value,
-                                               const float *__restrict__ loc,
-                                               const float *__restrict__ attn,
+template <int UNROLL, bool PROJ>
+__device__ __forceinline__ void fwd_warp_pairs(const float *__restrict__ value, const PairSrc &src,
                                                float *__restrict__ out, const WarpCtx &c,
                                                const LevelRow &my, uint4 *mine, int Q, bool live,
                                                int n, int S, int M, int m)
 {
     const size_t pair = (size_t)(live ? Q : 0) * M + m;
     // ---- phase 1: this lane prepares points 2*sub, 2*sub+1 (both on level sub/2)
-    float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float2 a2 = make_float2(0.f, 0.f);
-    if (live) {
-        l4 = ldg_f4(loc + pair * (kFastLP * 2) + c.sub * 4);
-        a2 = __ldg(reinterpret_cast<const float2 *>(attn + pair * kFastLP + c.sub * 2));
-    }
+    float4 l4;
+    float2 a2;
+    lane_points<PROJ>(src, c, my, Q, M, m, live, l4, a2);
     const uint32_t cell0 = ((uint32_t)n * (uint32_t)S + my.start) * c.MD + (uint32_t)m * kFastD;
     mine[c.grp * kFastLP + c.sub * 2 + 0] = pack_point(l4.x, l4.y, a2.x, my.H, my.W, cell0, c.MD);
     mine[c.grp * kFastLP + c.sub * 2 + 1] = pack_point(l4.z, l4.w, a2.y, my.H, my.W, cell0, c.MD);
@@ -199,9 +253,8 @@ __device__ __forceinline__ float group_reduce_scatter8(const float (&x)[8], int 
 // backward for the 4 pairs owned by this warp.  The 16 points are walked in two halves of 8 so
 // that the per-point partials (3 x 8 registers) stay small; scaleW/scaleH = (W, H) of the level
 // of point `sub` in each half (cuh:156-158).
-__device__ __forceinline__ void bwd_warp_pairs(const float *__restrict__ value,
-                                               const float *__restrict__ loc,
-                                               const float *__restrict__ attn,
+template <bool PROJ>
+__device__ __forceinline__ void bwd_warp_pairs(const float *__restrict__ value, const PairSrc &src,
                                                const float *__restrict__ grad_out,
                                                float *__restrict__ grad_value,
                                                float *__restrict__ grad_loc,
@@ -211,14 +264,11 @@ __device__ __forceinline__ void bwd_warp_pairs(const float *__restrict__ value,
                                                bool live, int n, int S, int M, int m)
 {
     const size_t pair = (size_t)(live ? Q : 0) * M + m;
-    float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float2 a2 = make_float2(0.f, 0.f);
+    float4 l4;
+    float2 a2;
     float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) {
-        l4 = ldg_f4(loc + pair * (kFastLP * 2) + c.sub * 4);
-        a2 = __ldg(reinterpret_cast<const float2 *>(attn + pair * kFastLP + c.sub * 2));
-        g4 = ldg_f4(grad_out + pair * kFastD + c.sub * 4);
-    }
+    lane_points<PROJ>(src, c, my, Q, M, m, live, l4, a2);
+    if (live) g4 = ldg_f4(grad_out + pair * kFastD + c.sub * 4);
     const uint32_t cell0 = ((uint32_t)n * (uint32_t)S + my.start) * c.MD + (uint32_t)m * kFastD;
     uint4 p0 = pack_point(l4.x, l4.y, a2.x, my.H, my.W, cell0, c.MD);
     uint4 p1 = pack_point(l4.z, l4.w, a2.y, my.H, my.W, cell0, c.MD);
@@ -229,6 +279,7 @@ __device__ __forceinline__ void bwd_warp_pairs(const float *__restrict__ value,
 
     const float *vbase = value + c.sub * 4;
     float *gbase = grad_value + c.sub * 4;
+    float ka0 = 0.f, ka1 = 0.f, kx0 = 0.f, kx1 = 0.f, ky0 = 0.f, ky1 = 0.f;   // PROJ: this lane's point of each half
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
         float pa[8], pw[8], ph[8];
@@ -271,11 +322,32 @@ __device__ __forceinline__ void bwd_warp_pairs(const float *__restrict__ value,
         const float ga = group_reduce_scatter8(pa, c.sub);
         const float gw = group_reduce_scatter8(pw, c.sub);
         const float gh = group_reduce_scatter8(ph, c.sub);
-        if (live) {
+        if (PROJ) {
+            // d loc / d offset = 1 / (W, H): torch forms grad_loc (cuh:156-158) and divides it again
+            const float gx = __fdiv_rn(gw * scaleW[half], scaleW[half]);
+            const float gy = __fdiv_rn(gh * scaleH[half], scaleH[half]);
+            if (half == 0) { ka0 = ga; kx0 = gx; ky0 = gy; } else { ka1 = ga; kx1 = gx; ky1 = gy; }
+        } else if (live) {
             const int pt_idx = half * 8 + c.sub;
             *reinterpret_cast<float2 *>(grad_loc + pair * (kFastLP * 2) + pt_idx * 2) =
                 make_float2(gw * scaleW[half], gh * scaleH[half]);
             grad_attn[pair * kFastLP + pt_idx] = ga;
+        }
+    }
+    if (PROJ) {
+        // softmax backward over the pair's 16 points: dlogit_p = A_p (dA_p - sum_j A_j dA_j); this lane
+        // holds points sub and 8 + sub.  grad_loc doubles as grad_proj [NQ, M*L*P*3] here.
+        const float A0 = __uint_as_float(mine[c.grp * kFastLP + c.sub].w);
+        const float A1 = __uint_as_float(mine[c.grp * kFastLP + 8 + c.sub].w);
+        const float dot = group_sum8(fmaf(A0, ka0, A1 * ka1));
+        if (live) {
+            float *row = grad_loc + (size_t)Q * (size_t)(M * kFastLP * 3);
+            float *goff = row + m * (kFastLP * 2);
+            float *glog = row + M * (kFastLP * 2) + m * kFastLP;
+            *reinterpret_cast<float2 *>(goff + c.sub * 2) = make_float2(kx0, ky0);
+            *reinterpret_cast<float2 *>(goff + (8 + c.sub) * 2) = make_float2(kx1, ky1);
+            glog[c.sub] = A0 * (ka0 - dot);
+            glog[8 + c.sub] = A1 * (ka1 - dot);
         }
     }
     __syncwarp();
@@ -293,13 +365,15 @@ __device__ __forceinline__ WarpCtx make_ctx(const LevelRow *lvl_tab, int M) {
 }
 
 // ---- linear schedule --------------------------------------------------------------------------
-template <int UNROLL, int MINB>
+template <int UNROLL, int MINB, bool PROJ = false>
 __global__ void __launch_bounds__(kThreads, MINB)
 msda_fwd_d32_l4p4(const float *__restrict__ value, const int64_t *__restrict__ shapes,
                   const int64_t *__restrict__ lsi, const float *__restrict__ loc,
                   const float *__restrict__ attn, int NQ, int Lq, int S, int M,
                   float *__restrict__ out)
 {
+    // PROJ: `loc` carries proj [NQ, M*48] and `attn` carries ref [NQ, 4, 2]
+    const PairSrc src = PROJ ? PairSrc{nullptr, nullptr, loc, attn} : PairSrc{loc, attn, nullptr, nullptr};
     __shared__ __align__(16) uint4 prep[kWarpsPerCta][4 * kFastLP];
     __shared__ LevelRow lvl_tab[kFastL];
     load_level_table(lvl_tab, shapes, lsi, (uint32_t)M * kFastD);
@@ -313,10 +387,10 @@ msda_fwd_d32_l4p4(const float *__restrict__ value, const int64_t *__restrict__ s
     const int m_begin = blockIdx.y * heads_per;
     const int m_end = min(M, m_begin + heads_per);
     for (int m = m_begin; m < m_end; ++m)
-        fwd_warp_pairs<UNROLL>(value, loc, attn, out, c, my, prep[warp], Q, live, n, S, M, m);
+        fwd_warp_pairs<UNROLL, PROJ>(value, src, out, c, my, prep[warp], Q, live, n, S, M, m);
 }
 
-template <int MINB>
+template <int MINB, bool PROJ = false>
 __global__ void __launch_bounds__(kThreads, MINB)
 msda_bwd_d32_l4p4(const float *__restrict__ value, const int64_t *__restrict__ shapes,
                   const int64_t *__restrict__ lsi, const float *__restrict__ loc,
@@ -324,6 +398,8 @@ msda_bwd_d32_l4p4(const float *__restrict__ value, const int64_t *__restrict__ s
                   int NQ, int Lq, int S, int M, float *__restrict__ grad_value,
                   float *__restrict__ grad_loc, float *__restrict__ grad_attn)
 {
+    // PROJ: `loc` = proj, `attn` = ref, `grad_loc` = grad_proj [NQ, M*48] (fully written), grad_attn unused
+    const PairSrc src = PROJ ? PairSrc{nullptr, nullptr, loc, attn} : PairSrc{loc, attn, nullptr, nullptr};
     __shared__ __align__(16) uint4 prep[kWarpsPerCta][4 * kFastLP];
     __shared__ LevelRow lvl_tab[kFastL];
     load_level_table(lvl_tab, shapes, lsi, (uint32_t)M * kFastD);
@@ -339,8 +415,8 @@ msda_bwd_d32_l4p4(const float *__restrict__ value, const int64_t *__restrict__ s
     const int m_begin = blockIdx.y * heads_per;
     const int m_end = min(M, m_begin + heads_per);
     for (int m = m_begin; m < m_end; ++m)
-        bwd_warp_pairs(value, loc, attn, grad_out, grad_value, grad_loc, grad_attn, c, my, scaleW,
-                       scaleH, prep[warp], Q, live, n, S, M, m);
+        bwd_warp_pairs<PROJ>(value, src, grad_out, grad_value, grad_loc, grad_attn, c, my, scaleW,
+                             scaleH, prep[warp], Q, live, n, S, M, m);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -571,9 +647,78 @@ int backward_impl(const T *value, const int64_t *shapes, const int64_t *lsi, con
     return (int)cudaGetLastError();
 }
 
+// fused-prologue variant: fast path only (fp32, D=32, L=4, P=4, 2-d reference points)
+int proj_forward_impl(const float *value, const int64_t *shapes, const int64_t *lsi, const float *ref,
+                      const float *proj, int batch, int spatial_size, int num_heads, int channels,
+                      int num_levels, int num_query, int num_point, float *out, cudaStream_t stream)
+{
+    if (bad_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point))
+        return RLIPV2_MSDA_EINVAL;
+    if (!fast_ok(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point))
+        return RLIPV2_MSDA_ESHAPE;
+    const int NQ = batch * num_query;
+    if (NQ == 0) return 0;
+    if (!value || !shapes || !lsi || !ref || !proj || !out) return RLIPV2_MSDA_EINVAL;
+    const dim3 grid = fast_grid(NQ, num_heads);
+    if (NQ >= 8192)
+        msda_fwd_d32_l4p4<8, 5, true><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, NQ, num_query,
+                                                                    spatial_size, num_heads, out);
+    else
+        msda_fwd_d32_l4p4<16, 3, true><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, NQ, num_query,
+                                                                     spatial_size, num_heads, out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+int proj_backward_impl(const float *value, const int64_t *shapes, const int64_t *lsi, const float *ref,
+                       const float *proj, const float *grad_out, int batch, int spatial_size, int num_heads,
+                       int channels, int num_levels, int num_query, int num_point, float *grad_value,
+                       float *grad_proj, cudaStream_t stream)
+{
+    if (bad_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point))
+        return RLIPV2_MSDA_EINVAL;
+    if (!fast_ok(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point))
+        return RLIPV2_MSDA_ESHAPE;
+    const long long velems = (long long)batch * spatial_size * num_heads * channels;
+    if (velems > 0) {
+        if (!grad_value) return RLIPV2_MSDA_EINVAL;
+        cudaError_t e = cudaMemsetAsync(grad_value, 0, (size_t)velems * sizeof(float), stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const int NQ = batch * num_query;
+    if (NQ == 0) return 0;
+    if (!value || !shapes || !lsi || !ref || !proj || !grad_out || !grad_proj) return RLIPV2_MSDA_EINVAL;
+    const dim3 grid = fast_grid(NQ, num_heads);
+    msda_bwd_d32_l4p4<2, true><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, grad_out, NQ, num_query,
+                                                               spatial_size, num_heads, grad_value, grad_proj, nullptr);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace
 
 extern "C" {
+
+int rlipv2_msda_proj_forward_f32(const float *value, const int64_t *spatial_shapes,
+                                 const int64_t *level_start_index, const float *reference_points,
+                                 const float *proj, int batch, int spatial_size, int num_heads, int channels,
+                                 int num_levels, int num_query, int num_point, float *out, void *stream)
+{
+    return proj_forward_impl(value, spatial_shapes, level_start_index, reference_points, proj, batch,
+                             spatial_size, num_heads, channels, num_levels, num_query, num_point, out,
+                             (cudaStream_t)stream);
+}
+
+int rlipv2_msda_proj_backward_f32(const float *value, const int64_t *spatial_shapes,
+                                  const int64_t *level_start_index, const float *reference_points,
+                                  const float *proj, const float *grad_out, int batch, int spatial_size,
+                                  int num_heads, int channels, int num_levels, int num_query, int num_point,
+                                  float *grad_value, float *grad_proj, void *stream)
+{
+    return proj_backward_impl(value, spatial_shapes, level_start_index, reference_points, proj, grad_out,
+                              batch, spatial_size, num_heads, channels, num_levels, num_query, num_point,
+                              grad_value, grad_proj, (cudaStream_t)stream);
+}
 
 int rlipv2_msda_forward_f32(const float *value, const int64_t *spatial_shapes,
                             const int64_t *level_start_index, const float *sampling_loc,
@@ -632,6 +777,7 @@ const char *rlipv2_msda_error_string(int code)
     if (code == 0) return "success";
     if (code == RLIPV2_MSDA_EINVAL) return "rlipv2_msda: invalid argument (dimension or null pointer)";
     if (code == RLIPV2_MSDA_ETOOBIG) return "rlipv2_msda: problem too large";
+    if (code == RLIPV2_MSDA_ESHAPE) return "rlipv2_msda: fused-prologue entry points need fp32, D=32, L=4, P=4";
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
     return "rlipv2_msda: unknown error";
 }

@@ -9,6 +9,7 @@ load), same error behaviour.  The sampling + aggregation runs in the sm_100a ker
 csrc/msda.cu through the C ABI (include/rlipv2_msda.h); there is no PyTorch fallback.
 """
 import math
+import os
 import warnings
 
 import torch
@@ -43,6 +44,37 @@ class MSDeformAttnFunction(Function):
             value, shapes, level_start, sampling_locations, attention_weights,
             grad_output.contiguous(), ctx.im2col_step)
         return grad_value, None, None, grad_sampling_loc, grad_attn_weight, None
+
+
+class MSDeformAttnProjFunction(Function):
+    """Fused-prologue op (include/rlipv2_msda.h `rlipv2_msda_proj_*`): the softmax over the 16 attention
+    logits and `loc = ref + offset / (W_l, H_l)` of ms_deform_attn.py:102-109 happen inside the sampling
+    kernels, forward and backward, so neither `sampling_locations` nor `attention_weights` (68 MB per
+    encoder call at 800x1333, batch 2) is ever materialised.  `reference_points` is not differentiated (the
+    encoder's are constants of the image size)."""
+
+    @staticmethod
+    def forward(ctx, value, spatial_shapes, level_start_index, reference_points, proj):
+        from . import msda_abi
+        N, Lq = proj.shape[:2]
+        out = torch.empty((N, Lq, value.shape[2] * value.shape[3]), dtype=value.dtype, device=value.device)
+        msda_abi.proj_forward(value, spatial_shapes, level_start_index, reference_points, proj, out)
+        ctx.save_for_backward(value, spatial_shapes, level_start_index, reference_points, proj)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        from . import msda_abi
+        value, shapes, level_start, reference_points, proj = ctx.saved_tensors
+        grad_value = torch.empty_like(value)          # zero-filled inside the library call
+        grad_proj = torch.empty_like(proj)            # fully written by the kernel
+        msda_abi.proj_backward(value, shapes, level_start, reference_points, proj, grad_output.contiguous(),
+                               grad_value, grad_proj)
+        return grad_value, None, None, None, grad_proj
+
+
+_FUSED_PROLOGUE = os.environ.get("RLIPV2_MSDA_FUSED_PROLOGUE", "1") != "0"     # A/B switch for measurements
 
 
 def _is_power_of_2(n):
@@ -112,6 +144,17 @@ class MSDeformAttn(nn.Module):
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
+        if (_FUSED_PROLOGUE and not reference_points.requires_grad and value.is_cuda
+                and input_flatten.dtype == torch.float32 and self.d_model // self.n_heads == 32
+                and reference_points.shape[-1] == 2 and self.n_levels == 4 and self.n_points == 4
+                and value.numel() < 2 ** 32):
+            # one GEMM for offsets | logits, then the fused-prologue kernels (encoder self-attention)
+            w = torch.cat((self.sampling_offsets.weight, self.attention_weights.weight), 0)
+            b = torch.cat((self.sampling_offsets.bias, self.attention_weights.bias), 0)
+            proj = dense.linear(query, w, b)
+            output = MSDeformAttnProjFunction.apply(value.contiguous(), input_spatial_shapes, input_level_start_index,
+                                                    reference_points.contiguous(), proj)
+            return dense.linear(output, self.output_proj.weight, self.output_proj.bias)
         sampling_offsets = dense.linear(query, self.sampling_offsets.weight, self.sampling_offsets.bias).view(
             N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
         attention_weights = dense.linear(query, self.attention_weights.weight, self.attention_weights.bias).view(

@@ -33,7 +33,9 @@ def test_libraries_export_all_declared_symbols():
 
 def test_binding_matches_abi_version():
     from rlipv2_b200 import msda_abi
-    assert msda_abi.ABI_VERSION == 1
+    import re
+    hdr = open(os.path.join(ROOT, "include", "rlipv2_msda.h")).read()
+    assert msda_abi.ABI_VERSION == int(re.search(r"#define RLIPV2_MSDA_ABI_VERSION (\d+)", hdr).group(1))
     assert os.path.exists(msda_abi.library_path())
     for sym in msda_abi.EXPORTS:
         assert sym in declared_symbols()

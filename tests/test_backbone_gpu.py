@@ -47,8 +47,8 @@ def test_fused_backbone_matches_unfolded_body(nhwc, monkeypatch):
     f_ref, g_ref = run(False)          # torchvision body: conv, FrozenBatchNorm2d, relu as separate ops
     f_new, g_new = run(True)
     assert set(g_ref) == set(g_new) and len(g_new) > 30
-    for a, b in zip(f_ref, f_new):
-        torch.testing.assert_close(b, a, rtol=1e-3, atol=1e-4)
+    for a, b in zip(f_ref, f_new):          # folding re-associates w*s: compare against the feature scale
+        assert float((b - a).abs().max() / a.abs().max()) < 1e-3
     for n in g_ref:
         scale = g_ref[n].abs().max().clamp_min(1e-6)
         assert ((g_new[n] - g_ref[n]).abs().max() / scale) < 2e-3, n

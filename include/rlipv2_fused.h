@@ -48,6 +48,14 @@ int rlipv2_adamw_f32(float *param, const float *grad, float *exp_avg, float *exp
                      double lr, double beta1, double beta2, double eps, double weight_decay, const float *step,
                      void *stream);
 
+/* Gather scattered fp32 arrays into one flat buffer: for chunk c, copy table[3c+2] elements from the device
+ * address table[3c] to dst + table[3c+1] (`table` is a device array of n_chunks x 3 int64; one CTA per chunk,
+ * keep chunks <= 64K elements).  Used once per step to collect the gradient tensors autograd produced
+ * (wherever it allocated them) into the flat gradient buffer that the all-reduce, the norm and the flat AdamW
+ * read - instead of ~600 `grad += new` accumulation kernels into pre-assigned views (main.py:515-517 DDP
+ * buckets / engine.py:166-172 in the reference). */
+int rlipv2_gather_chunks_f32(const long long *table, int n_chunks, float *dst, void *stream);
+
 const char *rlipv2_fused_error_string(int code);
 unsigned long long rlipv2_fused_launch_count(void);
 

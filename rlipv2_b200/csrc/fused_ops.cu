@@ -202,6 +202,26 @@ adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restri
     }
 }
 
+// ---- gather of scattered gradient tensors into the flat gradient buffer ------------------------------------
+// table[3*c + {0,1,2}] = (source address, destination element offset, element count) of chunk c; one CTA per
+// chunk.  128-bit copies when both sides are 16-byte aligned, scalar otherwise.
+__global__ void __launch_bounds__(256)
+gather_chunks_kernel(const long long *__restrict__ table, float *__restrict__ dst)
+{
+    const long long *row = table + 3ll * blockIdx.x;
+    const float *src = reinterpret_cast<const float *>(row[0]);
+    float *d = dst + row[1];
+    const int n = (int)row[2];
+    if ((((uintptr_t)src | (uintptr_t)d) & 15) == 0) {
+        const int n4 = n >> 2;
+        for (int i = threadIdx.x; i < n4; i += 256)
+            reinterpret_cast<float4 *>(d)[i] = __ldg(reinterpret_cast<const float4 *>(src) + i);
+        for (int i = (n4 << 2) + threadIdx.x; i < n; i += 256) d[i] = src[i];
+    } else {
+        for (int i = threadIdx.x; i < n; i += 256) d[i] = src[i];
+    }
+}
+
 inline int done() {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
@@ -274,6 +294,14 @@ int rlipv2_adamw_f32(float *param, const float *grad, float *exp_avg, float *exp
     adamw_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n4, n, (float)lr,
                                                                 (float)beta1, (float)beta2, (float)(1.0 - beta1),
                                                                 (float)(1.0 - beta2), (float)eps, (float)weight_decay, step);
+    return done();
+}
+
+int rlipv2_gather_chunks_f32(const long long *table, int n_chunks, float *dst, void *stream)
+{
+    if (n_chunks == 0) return 0;
+    if (!table || !dst || n_chunks < 0) return RLIPV2_FUSED_EINVAL;
+    gather_chunks_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(table, dst);
     return done();
 }
 

@@ -16,14 +16,15 @@ _lib.rlipv2_layernorm_bwd_f32.argtypes = [_p, _p, _p, _p, _p, _i, _i, _p, _p, _p
 _lib.rlipv2_relu_bwd_colsum_f32.argtypes = [_p, _p, _p, _p, _i, _i, _p]
 _d = ctypes.c_double
 _lib.rlipv2_adamw_f32.argtypes = [_p, _p, _p, _p, _ll, _d, _d, _d, _d, _d, _p, _p]
-for _n in ("add_layernorm_fwd_f32", "layernorm_bwd_f32", "relu_bwd_colsum_f32", "adamw_f32"):
+_lib.rlipv2_gather_chunks_f32.argtypes = [_p, _i, _p, _p]
+for _n in ("add_layernorm_fwd_f32", "layernorm_bwd_f32", "relu_bwd_colsum_f32", "adamw_f32", "gather_chunks_f32"):
     getattr(_lib, "rlipv2_" + _n).restype = _i
 _lib.rlipv2_fused_error_string.argtypes = [_i]
 _lib.rlipv2_fused_error_string.restype = ctypes.c_char_p
 _lib.rlipv2_fused_launch_count.restype = ctypes.c_ulonglong
 
 EXPORTS = ("rlipv2_add_layernorm_fwd_f32", "rlipv2_layernorm_bwd_f32", "rlipv2_relu_bwd_colsum_f32",
-           "rlipv2_adamw_f32", "rlipv2_fused_error_string", "rlipv2_fused_launch_count")
+           "rlipv2_adamw_f32", "rlipv2_gather_chunks_f32", "rlipv2_fused_error_string", "rlipv2_fused_launch_count")
 
 
 def library_path():
@@ -92,3 +93,29 @@ def adamw(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay,
         rc = _lib.rlipv2_adamw_f32(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
                                    param.numel(), lr, beta1, beta2, eps, weight_decay, step.data_ptr(), _stream())
     _check(rc, "rlipv2_adamw_f32")
+
+
+GATHER_CHUNK = 32768
+
+
+def gather_table(tensors, offsets, out=None):
+    """Host side of `gather_chunks`: int64 [n_chunks, 3] rows (source address, destination element offset, count)
+    that copy tensors[i] (contiguous fp32 CUDA) to flat[offsets[i] : offsets[i] + numel].  `out`: optional
+    (pinned) int64 tensor to fill; returns (table, n_chunks)."""
+    rows = []
+    for t, off in zip(tensors, offsets):
+        base, n = t.data_ptr(), t.numel()
+        for s in range(0, n, GATHER_CHUNK):
+            rows.append((base + 4 * s, off + s, min(GATHER_CHUNK, n - s)))
+    tab = torch.tensor(rows, dtype=torch.int64).reshape(-1, 3)
+    if out is not None:
+        out[:tab.shape[0]].copy_(tab)
+        return out, tab.shape[0]
+    return tab, tab.shape[0]
+
+
+def gather_chunks(table_dev, n_chunks, flat):
+    """flat (contiguous fp32 CUDA) <- chunks described by `table_dev` (int64 [>= n_chunks, 3] on the device)"""
+    with torch.cuda.device(flat.device):
+        rc = _lib.rlipv2_gather_chunks_f32(table_dev.data_ptr(), n_chunks, flat.data_ptr(), _stream())
+    _check(rc, "rlipv2_gather_chunks_f32")

@@ -140,10 +140,21 @@ class RLIP_ParSeDA(nn.Module):
         max_pred = int(sums[:, 1].max())
 
         sub_cls, obj_cls, verb_cls, sub_boxes, obj_boxes = [], [], [], [], []
+        # The box heads are the modules the pair decoder already applied for its anchor refinement (shared,
+        # hoi.py:1980-1990) to the same `hs` and anchors: take its un-detached results instead of evaluating
+        # two 3-layer MLPs + inverse_sigmoid per level a second time.
+        refined = getattr(self.transformer.ho_decoder, "refined_boxes", None)
+        self.transformer.ho_decoder.refined_boxes = None
+        if not (self.with_box_refine and refined is not None and len(refined) == hs_h.shape[0]):
+            refined = None
         for lvl in range(hs_h.shape[0]):
-            sub_ref, obj_ref = init_reference if lvl == 0 else inter_references[lvl - 1]
-            sub_boxes.append((self.sub_bbox_embed[lvl](hs_h[lvl]) + inverse_sigmoid(sub_ref)).sigmoid())
-            obj_boxes.append((self.obj_bbox_embed[lvl](hs_o[lvl]) + inverse_sigmoid(obj_ref)).sigmoid())
+            if refined is not None:
+                sub_boxes.append(refined[lvl][0])
+                obj_boxes.append(refined[lvl][1])
+            else:
+                sub_ref, obj_ref = init_reference if lvl == 0 else inter_references[lvl - 1]
+                sub_boxes.append((self.sub_bbox_embed[lvl](hs_h[lvl]) + inverse_sigmoid(sub_ref)).sigmoid())
+                obj_boxes.append((self.obj_bbox_embed[lvl](hs_o[lvl]) + inverse_sigmoid(obj_ref)).sigmoid())
             text_memory = F.normalize(text_dec[lvl].transpose(0, 1), p=2, dim=-1)
             proj_text = dense.linear(text_memory / 2.0, self.projection_text.weight, self.projection_text.bias)
             assert max_obj + max_pred == proj_text.shape[1]

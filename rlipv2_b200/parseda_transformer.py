@@ -21,6 +21,7 @@ B200-first differences that do not change results:
 """
 import copy
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -37,6 +38,7 @@ from .text_encoder import build_text_encoder, pooled_text
 
 
 _LEVEL_CACHE = {}
+_LANG_STREAM = os.environ.get("RLIPV2_LANG_STREAM", "1") != "0"       # A/B switch for measurements
 
 
 def _level_tensors(shapes_host, device):
@@ -76,20 +78,19 @@ class MLP(nn.Module):
 
 def gen_sineembed_for_position(pos_tensor):
     """[bs, nq, 2|4] normalised (x, y[, w, h]) -> [bs, nq, 256|512] sine embedding in the order
-    (y, x[, w, h]); 128 features each, temperature 10000 (deformable_transformer.py:1777-1802)."""
+    (y, x[, w, h]); 128 features each, temperature 10000 (deformable_transformer.py:1777-1802).
+    The reference embeds one coordinate at a time (6 kernels each); here all coordinates go through the
+    same elementwise ops at once - the values are identical, the launch count drops from ~28 to 7."""
+    n = pos_tensor.size(-1)
+    if n not in (2, 4):
+        raise ValueError("Unknown pos_tensor shape(-1):{}".format(n))
     scale = 2 * math.pi
     dim_t = torch.arange(128, dtype=torch.float32, device=pos_tensor.device)
     dim_t = 10000 ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / 128)
-
-    def emb(col):
-        p = (pos_tensor[:, :, col] * scale)[:, :, None] / dim_t
-        return torch.stack((p[:, :, 0::2].sin(), p[:, :, 1::2].cos()), dim=3).flatten(2)
-
-    if pos_tensor.size(-1) == 2:
-        return torch.cat((emb(1), emb(0)), dim=2)
-    if pos_tensor.size(-1) == 4:
-        return torch.cat((emb(1), emb(0), emb(2), emb(3)), dim=2)
-    raise ValueError("Unknown pos_tensor shape(-1):{}".format(pos_tensor.size(-1)))
+    order = [1, 0] if n == 2 else [1, 0, 2, 3]
+    p = (pos_tensor[..., order] * scale)[..., None] / dim_t                      # [bs, nq, n, 128]
+    emb = torch.stack((p[..., 0::2].sin(), p[..., 1::2].cos()), dim=4)          # [bs, nq, n, 64, 2]
+    return emb.flatten(2)
 
 
 class MultiBranchFusion(nn.Module):
@@ -191,6 +192,11 @@ class RLIPv2_DeformableTransformerEncoder(nn.Module):
             vis = {"src": src, "padding_mask": inv_padding_mask, "pos": pos}
         lang = {"hidden": lang_hidden, "masks": inv_lang_masks}
         multi_lay_lang = []
+        side, pending = None, False
+        if _LANG_STREAM and src.is_cuda:
+            if getattr(self, "_lang_stream", None) is None:
+                self._lang_stream = torch.cuda.Stream(src.device)
+            side = self._lang_stream
         for idx, layer in enumerate(self.layers):
             if idx % self.fusion_interval == 0:
                 k = idx // self.fusion_interval
@@ -202,10 +208,25 @@ class RLIPv2_DeformableTransformerEncoder(nn.Module):
                 if self.fusion_last_vis:
                     # write the fused coarsest level back (the reference does it in place, :856-859)
                     vis["src"] = torch.cat((full_src[:, :last_start], vis["src"]), dim=1)
-                lang["hidden"] = self.roberta_layers[k](lang["hidden"], attention_mask=lang["masks"])
+                if side is not None:
+                    # the label stream's RobertaLayer does not touch the image tokens: run it (and, through
+                    # autograd's stream bookkeeping, its backward) beside the next `fusion_interval`
+                    # deformable layers instead of in front of them
+                    cur = torch.cuda.current_stream(src.device)
+                    side.wait_stream(cur)
+                    with torch.cuda.stream(side):
+                        lang["hidden"] = self.roberta_layers[k](lang["hidden"], attention_mask=lang["masks"])
+                    pending = True
+                else:
+                    lang["hidden"] = self.roberta_layers[k](lang["hidden"], attention_mask=lang["masks"])
                 multi_lay_lang.append(lang["hidden"])
             vis["src"] = layer(vis["src"], pos, reference_points, spatial_shapes, level_start_index,
                                padding_mask, spatial_shapes_host=spatial_shapes_host)
+            if pending and ((idx + 1) % self.fusion_interval == 0 or idx + 1 == self.num_layers):
+                cur = torch.cuda.current_stream(src.device)           # join before the labels are used again
+                cur.wait_stream(side)
+                lang["hidden"].record_stream(cur)
+                pending = False
         if self.lang_aux_loss:
             if self.fusion_interval == 2:
                 multi_lay_lang = torch.stack(multi_lay_lang, dim=0)
@@ -317,6 +338,9 @@ class DABDeformableTransformerDecoderHOI(nn.Module):
         pair_num = obj_ref.shape[1]
         vr4 = torch.cat([src_valid_ratios, src_valid_ratios], -1)[:, None]       # [bs, 1, L, 4]
         inter, inter_sub, inter_obj = [], [], []
+        # refined boxes with their autograd history: the pair decoder's are exactly the model's box
+        # predictions (hoi.py:2122-2141 recomputes the same MLP on the same inputs), so the head reuses them
+        refined = self.refined_boxes = []
         for lid, layer in enumerate(self.layers):
             if self.ParSe:
                 ref_input = torch.cat((sub_ref[:, :, None] * vr4, obj_ref[:, :, None] * vr4), dim=1)
@@ -329,10 +353,14 @@ class DABDeformableTransformerDecoderHOI(nn.Module):
             # iterative box refinement; the refined anchors are detached (:1511-1541)
             if self.sub_bbox_embed is not None:
                 sub_in = output[:, :pair_num] if self.ParSe else output
-                sub_ref = (self.sub_bbox_embed[lid](sub_in) + inverse_sigmoid(sub_ref)).sigmoid().detach()
+                sub_box = (self.sub_bbox_embed[lid](sub_in) + inverse_sigmoid(sub_ref)).sigmoid()
+                sub_ref = sub_box.detach()
             if self.obj_bbox_embed is not None:
                 obj_in = output[:, pair_num:] if self.ParSe else output
-                obj_ref = (self.obj_bbox_embed[lid](obj_in) + inverse_sigmoid(obj_ref)).sigmoid().detach()
+                obj_box = (self.obj_bbox_embed[lid](obj_in) + inverse_sigmoid(obj_ref)).sigmoid()
+                obj_ref = obj_box.detach()
+            if self.sub_bbox_embed is not None and self.obj_bbox_embed is not None:
+                refined.append((sub_box, obj_box))
             if self.return_intermediate:
                 inter.append(output)
                 inter_sub.append(sub_ref)

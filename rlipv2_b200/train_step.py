@@ -12,6 +12,8 @@ box heads only feed detached anchors (dab_deformable/deformable_transformer.py:1
 unused parameters is static, so `static_graph=True` gives the same result without the per-step graph
 walk.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -125,8 +127,10 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
                   gradient buffer when world > 1) -> clip_grad_norm_(0.1) -> fused AdamW
 
     Shapes are static: image size, label count and the number of target triplets per image are fixed at
-    capture time (re-capture for a new shape bucket).  Gradients live as views of one flat buffer, so
-    data-parallel training needs exactly one all-reduce per step and no DDP wrapper; parameters that
+    capture time (re-capture for a new shape bucket).  Gradients end up in one flat buffer (autograd's
+    freshly produced gradient tensors are packed by one gather kernel; `RLIPV2_GATHER_GRADS=0` keeps the older
+    scheme of `.grad` views accumulated into a zeroed buffer), so data-parallel training needs exactly one
+    all-reduce per step and no DDP wrapper; parameters that
     never receive a gradient (the verb decoder's detached box heads) are left out of the optimizer,
     which is what the reference's `find_unused_parameters=True` + grad-is-None skip amounts to.
     """
@@ -136,6 +140,7 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         super().__init__(*a, **kw)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.captured = False
+        self.gather_grads = os.environ.get("RLIPV2_GATHER_GRADS", "1") != "0"      # A/B switch for measurements
 
     # the piece of work each graph records -------------------------------------------------------------
     def _forward_and_costs(self):
@@ -152,8 +157,16 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         from .criterion import StackedMatches
         matches = StackedMatches(self.s_I, self.s_J, giou, self.ks)
         total = self._weighted_total(self.criterion(outputs, self.s_targets, matches=matches))
-        self.flat_grad.zero_()
-        total.backward()
+        if self.gather_grads:
+            # autograd hands every parameter a freshly produced gradient tensor (no zero-fill, no `+=`);
+            # one gather kernel then packs them into the flat buffer (csrc/fused_ops.cu)
+            for p in self.params:
+                p.grad = None
+            total.backward()
+            self._gather_grads()
+        else:
+            self.flat_grad.zero_()
+            total.backward()
         if self.world > 1:
             dist.all_reduce(self.flat_grad)
             self.flat_grad.div_(self.world)
@@ -163,6 +176,20 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
             self.flat_grad.mul_(coef)
         self._adamw_step()
         return total.detach()
+
+    def _gather_grads(self):
+        from . import fused_abi
+        grads, offs = [], []
+        for p, off in zip(self.params, self.param_offsets):
+            g = p.grad
+            assert g is not None, "a parameter that received a gradient in the probe step has none now"
+            grads.append(g if g.is_contiguous() else g.contiguous())
+            offs.append(off)
+        _, n = fused_abi.gather_table(grads, offs, out=self.h_gather)
+        self.d_gather.copy_(self.h_gather, non_blocking=True)      # pinned -> device; a memcpy node when captured
+        fused_abi.gather_chunks(self.d_gather, n, self.flat_grad)
+        for p in self.params:                                       # the buffers are free for reuse from here on
+            p.grad = None
 
     def _adamw_step(self):
         from . import fused_abi
@@ -231,16 +258,23 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         self.exp_avg = torch.zeros(off, device=dev)
         self.exp_avg_sq = torch.zeros(off, device=dev)
         self.step_t = torch.zeros((), device=dev)
+        self.param_offsets = []
         for (plist, _), (start, _, _) in zip(groups, ranges):
             o = start
             for p in plist:
                 n = p.numel()
                 self.flat_param[o:o + n].copy_(p.data.reshape(-1))
                 p.data = self.flat_param[o:o + n].view_as(p)
-                p.grad = self.flat_grad[o:o + n].view_as(p)
+                p.grad = None if self.gather_grads else self.flat_grad[o:o + n].view_as(p)
+                self.param_offsets.append(o)
                 o += n
         self.group_ranges = ranges
         self.params = [p for plist, _ in groups for p in plist]
+        if self.gather_grads:
+            from . import fused_abi
+            rows = sum((p.numel() + fused_abi.GATHER_CHUNK - 1) // fused_abi.GATHER_CHUNK for p in self.params)
+            self.h_gather = torch.zeros(rows, 3, dtype=torch.int64).pin_memory()
+            self.d_gather = torch.zeros(rows, 3, dtype=torch.int64, device=dev)
         self.optimizer = None                       # replaced by the flat AdamW kernel (fused_ops.cu)
         if self.world > 1:                      # identical replicas (same seed), made certain
             dist.broadcast(self.flat_param, 0)

@@ -2,7 +2,7 @@
 # A/B of the step-level switches (one bench line each).  usage: bash tools/gpu_ab.sh <tag>
 TAG=${1:-ab}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q --maxfail=10 > gpurun_out/${TAG}_pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/${TAG}_pytest_gpu.log
 tail -4 gpurun_out/${TAG}_pytest_gpu.log
 run() {  # name, env...
@@ -18,6 +18,7 @@ except Exception as e:
 PY
 }
 run all_on A=1
-run no_text_stream RLIPV2_TEXT_STREAM=0
-run no_fused_conv RLIPV2_FUSED_CONV=0
-run nhwc RLIPV2_BACKBONE_NHWC=1
+run no_gather RLIPV2_GATHER_GRADS=0
+run no_prologue RLIPV2_MSDA_FUSED_PROLOGUE=0
+run no_lang_stream RLIPV2_LANG_STREAM=0
+run nhwc_nofusedconv RLIPV2_FUSED_CONV=0

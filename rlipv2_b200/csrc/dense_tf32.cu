@@ -74,6 +74,21 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
+// MN-major, 128-byte swizzled operand tile (the operand is stored [K rows, MN cols], MN contiguous - the layout
+// of both operands of a weight-gradient GEMM and of the weight in an input-gradient GEMM).  Shared memory holds
+// BLOCK/32 chunks of [32 K rows x 32 MN elements (128 B)], 4096 B apart; one MMA (K = 8) reads 8 consecutive
+// 128-byte rows of every chunk.  Canonical form (cute UMMA, Major::MN, SW128, in 16-byte units):
+// ((8,n),(8,k)) : ((1,LBO),(8,SBO)) with LBO = chunk stride = 4096 B, SBO = 8-row group stride = 1024 B.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+__device__ __forceinline__ void red_add_v4(float *addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
@@ -101,6 +116,175 @@ struct SmemLayout {
 template <int BLOCK_N>
 __host__ __device__ constexpr uint32_t make_idesc() {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+// same with the operand majors: bit 15 = A is MN-major, bit 16 = B is MN-major
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__host__ __device__ constexpr uint32_t make_idesc_major() {
+    return make_idesc<BLOCK_N>() | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// General TF32 GEMM for the backward contractions:  C[M,N] (op)= A . B^T  with logical A [M,K], B [N,K] and
+//   A_MN: A is stored [K, M] (M contiguous)      B_MN: B is stored [K, N] (N contiguous)
+// EPI_STORE   C = acc
+// EPI_ATOMIC  C += acc with red.global.add.v4.f32 (split-K over blockIdx.z; C zero-initialised by the caller)
+// EPI_MASK    C = (mask > 0) ? acc : 0 and colsum[n] += sum over rows of C (the ReLU backward + bias gradient of
+//             the layer that produced `mask`, fused into the input-gradient GEMM)
+// Same warp roles / pipeline as linear_tf32_kernel.  K need not be a multiple of 32 for MN-major operands (TMA
+// zero-fills rows past the end); M and N tails are handled by TMA zero fill + guarded stores.
+// ---------------------------------------------------------------------------------------------------------------
+enum { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_MASK = 2 };
+
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(kThreads, 2)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 float *__restrict__ C, const float *__restrict__ mask, float *__restrict__ colsum,
+                 int M, int N, int num_kb, int kb_per_split)
+{
+    using L = SmemLayout<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * L::kStageBytes);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tmem_full_bar = empty_bar + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_blk = blockIdx.x, m_blk = blockIdx.y;
+    const int kb0 = blockIdx.z * kb_per_split;
+    const int kb1 = min(num_kb, kb0 + kb_per_split);
+    const int nk = kb1 - kb0;                       // >= 1 by construction of the grid
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tm_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tm_b) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(BLOCK_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                   // ---- TMA producer
+            for (int i = 0; i < nk; ++i) {
+                const int kb = kb0 + i;
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], L::kStageBytes);
+                uint8_t *sa = smem + s * L::kStageBytes;
+                if (A_MN) {                                // box = [32 k rows][32 m], one per 32-wide chunk of M
+#pragma unroll
+                    for (int j = 0; j < kBlockM / 32; ++j)
+                        tma_load_2d(sa + j * 4096, &tm_a, &full_bar[s], m_blk * kBlockM + j * 32, kb * kBlockK);
+                } else {
+                    tma_load_2d(sa, &tm_a, &full_bar[s], kb * kBlockK, m_blk * kBlockM);
+                }
+                if (B_MN) {
+#pragma unroll
+                    for (int j = 0; j < BLOCK_N / 32; ++j)
+                        tma_load_2d(sa + L::kABytes + j * 4096, &tm_b, &full_bar[s], n_blk * BLOCK_N + j * 32, kb * kBlockK);
+                } else {
+                    tma_load_2d(sa + L::kABytes, &tm_b, &full_bar[s], kb * kBlockK, n_blk * BLOCK_N);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                   // ---- MMA issuer
+            constexpr uint32_t idesc = make_idesc_major<BLOCK_N, A_MN, B_MN>();
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(smem + s * L::kStageBytes);
+                const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                    // K-major: +32 bytes inside the swizzle atom; MN-major: +8 rows of 128 bytes
+                    const uint64_t da = A_MN ? umma_desc_mn_sw128(sa + k * 1024) : umma_desc_k_sw128(sa + k * kUmmaK * 4);
+                    const uint64_t db = B_MN ? umma_desc_mn_sw128(sb + k * 1024) : umma_desc_k_sw128(sb + k * kUmmaK * 4);
+                    umma_tf32(tmem_base, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {                                               // ---- epilogue warps 2..5
+        mbar_wait(tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;
+        float *stage_out = reinterpret_cast<float *>(smem) + (warp - 2) * (32 * 36);
+        const int sub = lane & 7, rgrp = lane >> 3;
+        const size_t col0 = (size_t)n_blk * BLOCK_N;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4 *>(stage_out + lane * 36 + j) =
+                    make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                __uint_as_float(r[j + 3]));
+            __syncwarp();
+            const size_t col = col0 + c * 32 + sub * 4;
+            float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + rgrp;
+                float4 v = *reinterpret_cast<const float4 *>(stage_out + rr * 36 + sub * 4);
+                const int grow = m_blk * kBlockM + q * 32 + rr;
+                if (grow < M && col < (size_t)N) {
+                    float *dst = C + (size_t)grow * N + col;
+                    if (EPI == EPI_ATOMIC) {
+                        red_add_v4(dst, v);
+                    } else {
+                        if (EPI == EPI_MASK) {
+                            const float4 mk = __ldg(reinterpret_cast<const float4 *>(mask + (size_t)grow * N + col));
+                            v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f;
+                            v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
+                            csum.x += v.x; csum.y += v.y; csum.z += v.z; csum.w += v.w;
+                        }
+                        *reinterpret_cast<float4 *>(dst) = v;
+                    }
+                }
+            }
+            if (EPI == EPI_MASK) {
+                // lanes with equal `sub` hold the same 4 columns: fold the 4 row groups, then one atomic each
+#pragma unroll
+                for (int o = 8; o < 32; o <<= 1) {
+                    csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o); csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
+                    csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o); csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
+                }
+                if (rgrp == 0 && col < (size_t)N) red_add_v4(colsum + col, csum);
+            }
+            __syncwarp();
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(BLOCK_N) : "memory");
+    }
 }
 
 template <int BLOCK_N, int STAGES, int ACT>

@@ -87,8 +87,10 @@ def gen_sineembed_for_position(pos_tensor):
     scale = 2 * math.pi
     dim_t = torch.arange(128, dtype=torch.float32, device=pos_tensor.device)
     dim_t = 10000 ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / 128)
-    order = [1, 0] if n == 2 else [1, 0, 2, 3]
-    p = (pos_tensor[..., order] * scale)[..., None] / dim_t                      # [bs, nq, n, 128]
+    # (x, y, ...) -> (y, x, ...) with slices only: an index list would become a host tensor + H2D copy, which a
+    # CUDA-graph capture rejects
+    yx = torch.cat((pos_tensor[..., 1:2], pos_tensor[..., 0:1], pos_tensor[..., 2:]), dim=-1)
+    p = (yx * scale)[..., None] / dim_t                                          # [bs, nq, n, 128]
     emb = torch.stack((p[..., 0::2].sin(), p[..., 1::2].cos()), dim=4)          # [bs, nq, n, 64, 2]
     return emb.flatten(2)
 

@@ -36,6 +36,22 @@ int rlipv2_dense_linear_tf32_supported(int M, int N, int K);
 int rlipv2_dense_linear_tf32(const float *x, const float *w, const float *bias, float *y, int M, int N, int K,
                              int act, void *stream);
 
+/* Backward contractions of the same nn.Linear (what autograd's mm / addmm backward runs through cuBLAS):
+ *
+ * weight gradient  dw[N,K] += g[T,N]^T . x[T,K]   (g = dL/dy, x = the layer input; T = rows = tokens).
+ *   Both operands are read as stored (MN-major tcgen05 operands, no transposed copies); the T axis is split over
+ *   `splits` CTAs per output tile and the partial tiles are reduced into `dw` with red.global.add.v4.f32, so
+ *   `dw` must be initialised by the caller (zeros, or the gradient accumulated so far) and the fp32 summation
+ *   order is not deterministic.  N % 4 == 0, K % 4 == 0.
+ *
+ * input gradient   dx[T,K] = g[T,N] . w[N,K]      (w = nn.Linear weight as stored).
+ *   With relu_out != NULL (the [T,K] output of the ReLU layer that feeds this Linear) the ReLU backward and the
+ *   bias gradient of that previous layer are fused into the epilogue: dx = (relu_out > 0) ? dx : 0 and
+ *   colsum[K] += column sums of the masked dx (colsum initialised by the caller).  N % 4 == 0, K % 4 == 0. */
+int rlipv2_dense_wgrad_tf32(const float *g, const float *x, float *dw, int T, int N, int K, int splits, void *stream);
+int rlipv2_dense_dgrad_tf32(const float *g, const float *w, float *dx, const float *relu_out, float *colsum,
+                            int T, int N, int K, void *stream);
+
 const char *rlipv2_dense_error_string(int code);
 
 /* kernels launched by this library in this process (for bench.py's gpu_launches) */

@@ -50,15 +50,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 }
 
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+    // try_wait suspends for a hardware-defined time slice per attempt; a barrier that never flips (a byte-count
+    // or descriptor bug) must become an error, not a hung GPU: trap after ~2^26 attempts (seconds)
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (spins > (1u << 26)) __trap();
+    }
 }
 
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
@@ -464,9 +467,87 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tb, const float *bias, floa
     return (int)cudaGetLastError();
 }
 
+// 2-D fp32 tensor [rows, cols] row-major, box = [box_rows, box_cols <= 32], 128-byte swizzle, zero OOB fill
+int make_map_box(CUtensorMap *map, const float *ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return RLIPV2_DENSE_EDRIVER;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * sizeof(float)};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : RLIPV2_DENSE_EDRIVER;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+int launch_gemm(const float *a, const float *b, float *c, const float *mask, float *colsum, int M, int N, int K,
+                int splits, cudaStream_t stream) {
+    constexpr int STAGES = 3;
+    using L = SmemLayout<BLOCK_N>;
+    constexpr int smem = STAGES * L::kStageBytes + (2 * STAGES + 1) * 8 + 16 + 1024;
+    CUtensorMap ta, tb;
+    // K-major operand: stored [rows = M|N, cols = K], box 128|BLOCK_N rows x 32 K;  MN-major: stored [rows = K,
+    // cols = M|N], box 32 K rows x 32 columns
+    int rc = A_MN ? make_map_box(&ta, a, (uint64_t)K, (uint64_t)M, 32, 32) : make_map_box(&ta, a, (uint64_t)M, (uint64_t)K, kBlockM, kBlockK);
+    if (rc) return rc;
+    rc = B_MN ? make_map_box(&tb, b, (uint64_t)K, (uint64_t)N, 32, 32) : make_map_box(&tb, b, (uint64_t)N, (uint64_t)K, BLOCK_N, kBlockK);
+    if (rc) return rc;
+    auto kern = gemm_tf32_kernel<BLOCK_N, STAGES, A_MN, B_MN, EPI>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    const int num_kb = (K + kBlockK - 1) / kBlockK;
+    if (splits < 1) splits = 1;
+    if (splits > num_kb) splits = num_kb;
+    const int per = (num_kb + splits - 1) / splits;
+    const int gz = (num_kb + per - 1) / per;           // every z slice owns >= 1 k-block
+    dim3 grid((N + BLOCK_N - 1) / BLOCK_N, (M + kBlockM - 1) / kBlockM, gz);
+    kern<<<grid, kThreads, smem, stream>>>(ta, tb, c, mask, colsum, M, N, num_kb, per);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+inline bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
+
 }  // namespace
 
 extern "C" {
+
+int rlipv2_dense_wgrad_tf32(const float *g, const float *x, float *dw, int T, int N, int K, int splits, void *stream)
+{
+    // dw[N,K] += g[T,N]^T . x[T,K]: logical A = g^T (stored [T, N]: MN-major), B = x^T (stored [T, K]: MN-major),
+    // contraction over the T rows, split over `splits` CTAs per output tile, partial tiles reduced into dw
+    if (T == 0 || N == 0 || K == 0) return 0;
+    if (T < 0 || N < 0 || K < 0 || !g || !x || !dw) return RLIPV2_DENSE_EINVAL;
+    if ((N % 4) || (K % 4)) return RLIPV2_DENSE_ESHAPE;
+    if (!aligned16(g) || !aligned16(x) || !aligned16(dw)) return RLIPV2_DENSE_EALIGN;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (K % 256 == 0)
+        return launch_gemm<256, true, true, EPI_ATOMIC>(g, x, dw, nullptr, nullptr, N, K, T, splits, s);
+    return launch_gemm<128, true, true, EPI_ATOMIC>(g, x, dw, nullptr, nullptr, N, K, T, splits, s);
+}
+
+int rlipv2_dense_dgrad_tf32(const float *g, const float *w, float *dx, const float *relu_out, float *colsum,
+                            int T, int N, int K, void *stream)
+{
+    // dx[T,K] = g[T,N] . w[N,K]: A = g (K-major: contraction N contiguous), logical B = w^T [K, N] stored as
+    // w [N, K] = [contraction rows, output cols]: MN-major.  relu_out != NULL: dx = (relu_out > 0) ? dx : 0 and
+    // colsum[K] += column sums of the masked dx (colsum zero-initialised by the caller).
+    if (T == 0 || K == 0) return 0;
+    if (T < 0 || N <= 0 || K < 0 || !g || !w || !dx) return RLIPV2_DENSE_EINVAL;
+    if ((N % 4) || (K % 4)) return RLIPV2_DENSE_ESHAPE;
+    if (!aligned16(g) || !aligned16(w) || !aligned16(dx) || !aligned16(relu_out) || !aligned16(colsum)) return RLIPV2_DENSE_EALIGN;
+    if ((relu_out == nullptr) != (colsum == nullptr)) return RLIPV2_DENSE_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (relu_out)
+        return launch_gemm<128, false, true, EPI_MASK>(g, w, dx, relu_out, colsum, T, K, N, 1, s);
+    return launch_gemm<128, false, true, EPI_STORE>(g, w, dx, nullptr, nullptr, T, K, N, 1, s);
+}
 
 int rlipv2_dense_linear_tf32_supported(int M, int N, int K)
 {
@@ -499,7 +580,7 @@ const char *rlipv2_dense_error_string(int code)
     switch (code) {
         case 0: return "success";
         case RLIPV2_DENSE_EINVAL: return "rlipv2_dense: invalid argument";
-        case RLIPV2_DENSE_ESHAPE: return "rlipv2_dense: shape not supported by the tcgen05 kernel (N % 128, K % 32)";
+        case RLIPV2_DENSE_ESHAPE: return "rlipv2_dense: shape not supported by the tcgen05 kernel (linear: N % 128, K % 32; grads: N % 4, K % 4)";
         case RLIPV2_DENSE_EALIGN: return "rlipv2_dense: pointers must be 16-byte aligned";
         case RLIPV2_DENSE_EDRIVER: return "rlipv2_dense: cuTensorMapEncodeTiled unavailable or failed";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "rlipv2_dense: unknown error";

@@ -12,12 +12,18 @@ Two execution modes (`set_matmul_precision`):
           TF32 (round-1 state).
 There is no CPU implementation behind the tcgen05 path; CPU tensors only ever reach the torch ops.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
 _PRECISION = "fp32"
 _USE_TCGEN05 = True
 _USE_FUSED = True        # fused LayerNorm / bias-gradient kernels (exact fp32 arithmetic; CUDA tensors only)
+# backward GEMMs (weight / input gradients) on the tcgen05 kernels instead of cuBLAS, for calls with at least
+# _OWN_BWD_MIN_ROWS rows (the split-K weight gradient pays off on the encoder's 44k-token activations)
+_OWN_BWD = os.environ.get("RLIPV2_OWN_BWD", "0") == "1"
+_OWN_BWD_MIN_ROWS = int(os.environ.get("RLIPV2_OWN_BWD_MIN_ROWS", "4096"))
 
 
 def set_matmul_precision(mode: str, tcgen05: bool = True, fused: bool = True):
@@ -70,13 +76,58 @@ class _LinearTF32(torch.autograd.Function):
                 g = g * (y > 0)
             gb = g.sum(0)
         gx = gw = None
+        own = _OWN_BWD and _abi().grads_supported(g.shape[0], g.shape[1], w.shape[1])
         if ctx.needs_input_grad[0]:
-            gx = (g @ w).view(*grad_out.shape[:-1], w.shape[1])
+            gx = (_abi().dgrad_tf32(g, w)[0] if own and g.shape[0] >= _OWN_BWD_MIN_ROWS else g @ w)
+            gx = gx.view(*grad_out.shape[:-1], w.shape[1])
         if ctx.needs_input_grad[1]:
-            gw = g.t() @ x2
+            gw = _abi().wgrad_tf32(g, x2) if own and g.shape[0] >= _OWN_BWD_MIN_ROWS else g.t() @ x2
         if not (ctx.has_bias and ctx.needs_input_grad[2]):
             gb = None
         return gx, gw, gb, None
+
+
+class _FFNReLU(torch.autograd.Function):
+    """y = relu(x W1^T + b1) W2^T + b2 - the position-wise FFN of the deformable encoder / decoder layers
+    (dab_deformable/deformable_transformer.py:1283-1287, 1368-1372; dropout p = 0 in every ParSeDA script).
+    Forward: two tcgen05 GEMMs (bias + ReLU fused).  Backward, all on the tcgen05 kernels of csrc/dense_tf32.cu:
+        dW2 = g^T h            split-K weight gradient, operands read as stored
+        gh  = (g W2) * (h > 0) input gradient with the ReLU mask and db1 = colsum(gh) fused in the epilogue
+        dW1 = gh^T x, dx = gh W1,  db2 = colsum(g)
+    which removes the separate mask + column-sum pass over the [T, d_ffn] hidden gradient (1.1 GB of HBM
+    traffic per encoder layer at 800x1333, batch 2)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        abi = _abi()
+        x2 = x.reshape(-1, x.shape[-1])
+        x2 = x2 if x2.is_contiguous() else x2.contiguous()
+        h = abi.linear_tf32(x2, w1.contiguous(), b1, abi.ACT_RELU)
+        y = abi.linear_tf32(h, w2.contiguous(), b2, abi.ACT_NONE)
+        ctx.save_for_backward(x2, w1, w2, h)
+        return y.view(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        abi = _abi()
+        x2, w1, w2, h = ctx.saved_tensors
+        g = grad_out.reshape(-1, grad_out.shape[-1])
+        g = g if g.is_contiguous() else g.contiguous()
+        _, gb2 = _fused().relu_bwd_colsum(g, None)
+        gw2 = abi.wgrad_tf32(g, h)
+        gh, gb1 = abi.dgrad_tf32(g, w2, relu_out=h)
+        gw1 = abi.wgrad_tf32(gh, x2)
+        gx = abi.dgrad_tf32(gh, w1)[0].view(*grad_out.shape[:-1], w1.shape[1]) if ctx.needs_input_grad[0] else None
+        return gx, gw1, gb1, gw2, gb2
+
+
+def ffn_relu(x, w1, b1, w2, b2):
+    """relu(x W1^T + b1) W2^T + b2"""
+    M = x.numel() // x.shape[-1]
+    if (_OWN_BWD and _tcgen05_ok(x, w1) and _abi().supported(M, w2.shape[0], w2.shape[1]) and M >= _OWN_BWD_MIN_ROWS
+            and b1 is not None and b2 is not None and w2.shape[0] % 32 == 0):
+        return _FFNReLU.apply(x, w1, b1, w2, b2)
+    return linear(linear_relu(x, w1, b1), w2, b2)
 
 
 def _fused():

@@ -15,13 +15,17 @@ _lib.rlipv2_dense_linear_tf32.argtypes = [_p, _p, _p, _p, _i, _i, _i, _i, _p]
 _lib.rlipv2_dense_linear_tf32.restype = _i
 _lib.rlipv2_dense_linear_tf32_supported.argtypes = [_i, _i, _i]
 _lib.rlipv2_dense_linear_tf32_supported.restype = _i
+_lib.rlipv2_dense_wgrad_tf32.argtypes = [_p, _p, _p, _i, _i, _i, _i, _p]
+_lib.rlipv2_dense_wgrad_tf32.restype = _i
+_lib.rlipv2_dense_dgrad_tf32.argtypes = [_p, _p, _p, _p, _p, _i, _i, _i, _p]
+_lib.rlipv2_dense_dgrad_tf32.restype = _i
 _lib.rlipv2_dense_error_string.argtypes = [_i]
 _lib.rlipv2_dense_error_string.restype = ctypes.c_char_p
 _lib.rlipv2_dense_launch_count.restype = ctypes.c_ulonglong
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
-EXPORTS = ("rlipv2_dense_linear_tf32", "rlipv2_dense_linear_tf32_supported", "rlipv2_dense_error_string",
-           "rlipv2_dense_launch_count")
+EXPORTS = ("rlipv2_dense_linear_tf32", "rlipv2_dense_linear_tf32_supported", "rlipv2_dense_wgrad_tf32",
+           "rlipv2_dense_dgrad_tf32", "rlipv2_dense_error_string", "rlipv2_dense_launch_count")
 
 
 def library_path():
@@ -48,3 +52,49 @@ def linear_tf32(x2d, weight, bias, act=ACT_NONE):
     if rc != 0:
         raise RuntimeError(f"rlipv2_dense_linear_tf32: {_lib.rlipv2_dense_error_string(rc).decode()} (code {rc})")
     return y
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def grads_supported(T, N, K):
+    """shapes the tcgen05 backward GEMMs take (row strides must be 16-byte multiples for TMA)"""
+    return T > 0 and N > 0 and K > 0 and N % 4 == 0 and K % 4 == 0
+
+
+def wgrad_splits(T, N, K):
+    """CTAs along the token axis per output tile: fill ~2 waves of 148 SMs, at least 8 k-blocks of 32 rows each"""
+    bn = 256 if K % 256 == 0 else 128
+    tiles = ((N + 127) // 128) * ((K + bn - 1) // bn)
+    kb = (T + 31) // 32
+    return max(1, min((296 + tiles - 1) // tiles, kb // 8 if kb >= 8 else 1))
+
+
+def wgrad_tf32(g2d, x2d, splits=None):
+    """dw [N,K] = g2d[T,N]^T @ x2d[T,K] (contiguous fp32 CUDA), split over the T axis and reduced with fp32 reductions"""
+    T, N = g2d.shape
+    K = x2d.shape[1]
+    dw = torch.zeros((N, K), dtype=torch.float32, device=g2d.device)
+    with torch.cuda.device(g2d.device):
+        rc = _lib.rlipv2_dense_wgrad_tf32(g2d.data_ptr(), x2d.data_ptr(), dw.data_ptr(), T, N, K,
+                                          splits if splits is not None else wgrad_splits(T, N, K), _stream())
+    if rc != 0:
+        raise RuntimeError(f"rlipv2_dense_wgrad_tf32: {_lib.rlipv2_dense_error_string(rc).decode()} (code {rc})")
+    return dw
+
+
+def dgrad_tf32(g2d, weight, relu_out=None):
+    """dx [T,K] = g2d[T,N] @ weight[N,K]; with `relu_out` [T,K]: dx masked by (relu_out > 0) and its column sums
+    -> (dx, colsum | None)"""
+    T, N = g2d.shape
+    K = weight.shape[1]
+    dx = torch.empty((T, K), dtype=torch.float32, device=g2d.device)
+    colsum = torch.zeros(K, dtype=torch.float32, device=g2d.device) if relu_out is not None else None
+    with torch.cuda.device(g2d.device):
+        rc = _lib.rlipv2_dense_dgrad_tf32(g2d.data_ptr(), weight.data_ptr(), dx.data_ptr(),
+                                          relu_out.data_ptr() if relu_out is not None else None,
+                                          colsum.data_ptr() if colsum is not None else None, T, N, K, _stream())
+    if rc != 0:
+        raise RuntimeError(f"rlipv2_dense_dgrad_tf32: {_lib.rlipv2_dense_error_string(rc).decode()} (code {rc})")
+    return dx, colsum

@@ -137,8 +137,12 @@ class DeformableTransformerEncoderLayer(nn.Module):
         self.norm2 = nn.LayerNorm(d_model)
 
     def forward_ffn(self, src):
-        h = self.dropout2(dense.linear_relu(src, self.linear1.weight, self.linear1.bias))
-        src2 = self.dropout3(dense.linear(h, self.linear2.weight, self.linear2.bias))
+        if self.dropout2.p == 0 or not self.training:
+            src2 = dense.ffn_relu(src, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias)
+        else:
+            h = self.dropout2(dense.linear_relu(src, self.linear1.weight, self.linear1.bias))
+            src2 = dense.linear(h, self.linear2.weight, self.linear2.bias)
+        src2 = self.dropout3(src2)
         return dense.add_layer_norm(src2, src, self.norm2.weight, self.norm2.bias, self.norm2.eps)
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None,

@@ -86,3 +86,46 @@ def test_full_step_tf32_close_to_fp32_golden():
     for k in ("pred_obj_logits", "pred_verb_logits", "pred_sub_boxes", "pred_obj_boxes"):
         np.testing.assert_allclose(out[k].detach().cpu().numpy(), g["out_" + k], rtol=3e-2, atol=3e-2)
     np.testing.assert_allclose(float(total), float(g["total_loss"]), rtol=2e-2)
+
+
+def _bound(a, b):
+    """|x|.|w| products bound for TF32 rounding: 2 operands x 2^-11 relative each, fp32 accumulation"""
+    return a.abs().double() @ b.abs().double()
+
+
+@pytest.mark.parametrize("T,N,K,splits", [
+    (300, 256, 256, 1), (300, 256, 256, 3), (4001, 128, 256, None), (4001, 2048, 256, None), (4001, 256, 2048, None),
+    (1000, 768, 768, 4), (517, 3072, 768, None), (45, 132, 260, 1),
+])
+def test_wgrad_tf32(T, N, K, splits):
+    from rlipv2_b200 import dense_abi
+    g = torch.Generator(device="cuda").manual_seed(T + N)
+    gy = torch.randn(T, N, device="cuda", generator=g)
+    x = torch.randn(T, K, device="cuda", generator=g)
+    dw = dense_abi.wgrad_tf32(gy, x, splits)
+    ref = gy.double().t() @ x.double()
+    err = (dw.double() - ref).abs()
+    assert float((err / (1.5e-3 * _bound(gy.t(), x) + 1e-6)).max()) <= 1.0
+    assert float(err.max() / ref.abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("T,N,K,mask", [
+    (300, 256, 2048, True), (300, 2048, 256, False), (4001, 256, 2048, True), (4001, 128, 256, False),
+    (517, 768, 3072, False), (45, 132, 260, True), (128, 32, 128, False),
+])
+def test_dgrad_tf32(T, N, K, mask):
+    from rlipv2_b200 import dense_abi
+    g = torch.Generator(device="cuda").manual_seed(T + K)
+    gy = torch.randn(T, N, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) * N ** -0.5
+    h = torch.relu(torch.randn(T, K, device="cuda", generator=g)) if mask else None
+    dx, colsum = dense_abi.dgrad_tf32(gy, w, h)
+    ref = gy.double() @ w.double()
+    bound = 1.5e-3 * _bound(gy, w) + 1e-6
+    if mask:
+        ref = ref * (h > 0)
+        assert float(((colsum.double() - ref.sum(0)).abs() / (bound.sum(0) + 1e-6)).max()) <= 1.0
+        assert bool((dx[h <= 0] == 0).all())
+    else:
+        assert colsum is None
+    assert float(((dx.double() - ref).abs() / bound).max()) <= 1.0

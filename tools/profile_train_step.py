@@ -27,7 +27,7 @@ for e in prof.events():
         agg[e.name][1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
 tot = sum(v[1] for v in agg.values())
 print(f"total GPU kernel time per step: {tot / 1e3:.2f} ms over {sum(v[0] for v in agg.values())} launches")
-for name, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:60]:
+for name, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:int(os.environ.get('TOPK', '400'))]:
     print(f"{t / 1e3:8.3f} ms {100 * t / tot:5.1f}%  n={n:4d}  {name[:150]}")
 
 if len(sys.argv) > 2 and sys.argv[2] == "big":

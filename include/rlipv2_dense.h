@@ -47,10 +47,17 @@ int rlipv2_dense_linear_tf32(const float *x, const float *w, const float *bias, 
  * input gradient   dx[T,K] = g[T,N] . w[N,K]      (w = nn.Linear weight as stored).
  *   With relu_out != NULL (the [T,K] output of the ReLU layer that feeds this Linear) the ReLU backward and the
  *   bias gradient of that previous layer are fused into the epilogue: dx = (relu_out > 0) ? dx : 0 and
- *   colsum[K] += column sums of the masked dx (colsum initialised by the caller).  N % 4 == 0, K % 4 == 0. */
+ *   colsum[ceil(T/128), K] = column sums of the masked dx per 128-row tile (fully written, no atomics; the caller
+ *   adds the tiles up).  N % 4 == 0, K % 4 == 0. */
 int rlipv2_dense_wgrad_tf32(const float *g, const float *x, float *dw, int T, int N, int K, int splits, void *stream);
 int rlipv2_dense_dgrad_tf32(const float *g, const float *w, float *dx, const float *relu_out, float *colsum,
                             int T, int N, int K, void *stream);
+
+/* rlipv2_dense_linear_tf32 with `value.masked_fill(padding_mask[..., None], 0)`
+ * (/root/reference/models/ops/modules/ms_deform_attn.py:98-100) folded into the epilogue: rows r with
+ * rowmask[r] != 0 are written as zeros.  rowmask: M bytes (a torch bool tensor) or NULL. */
+int rlipv2_dense_linear_tf32_rowmask(const float *x, const float *w, const float *bias, const unsigned char *rowmask,
+                                     float *y, int M, int N, int K, int act, void *stream);
 
 const char *rlipv2_dense_error_string(int code);
 

@@ -42,6 +42,12 @@ int rlipv2_layernorm_bwd_f32(const float *dy, const float *z, const float *mean,
 int rlipv2_relu_bwd_colsum_f32(const float *g, const float *y, float *gmasked, float *colsum, int M, int N,
                                void *stream);
 
+/* Backward of `y.masked_fill(rowmask[..., None], 0)` (ms_deform_attn.py:99-100) fused with the bias gradient:
+ * gmasked[r,:] = rowmask[r] ? 0 : g[r,:] (may alias g), colsum[N] = column sums of gmasked (overwritten).
+ * rowmask: M bytes (a torch bool tensor). */
+int rlipv2_rowmask_bwd_colsum_f32(const float *g, const unsigned char *rowmask, float *gmasked, float *colsum, int M,
+                                  int N, void *stream);
+
 /* One AdamW step over n contiguous elements (decoupled weight decay, torch.optim.AdamW semantics).
  * `step` is a device float holding the 1-based step count of THIS update (bias correction). */
 int rlipv2_adamw_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n,

@@ -77,14 +77,17 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
-// MN-major, 128-byte swizzled operand tile (the operand is stored [K rows, MN cols], MN contiguous - the layout
-// of both operands of a weight-gradient GEMM and of the weight in an input-gradient GEMM).  Shared memory holds
-// BLOCK/32 chunks of [32 K rows x 32 MN elements (128 B)], 4096 B apart; one MMA (K = 8) reads 8 consecutive
-// 128-byte rows of every chunk.  Canonical form (cute UMMA, Major::MN, SW128, in 16-byte units):
-// ((8,n),(8,k)) : ((1,LBO),(8,SBO)) with LBO = chunk stride = 4096 B, SBO = 8-row group stride = 1024 B.
+// MN-major operand tile (the operand is stored [K rows, MN cols], MN contiguous - the layout of both operands of
+// a weight-gradient GEMM and of the weight in an input-gradient GEMM).  For 32-bit (TF32) MN-major operands the
+// only shared-memory layout tcgen05 accepts is SWIZZLE_128B_BASE32B (cute: Layout_MN_SW128_32B_Atom, Swizzle<2,5,2>
+// - 32-byte granules of a 128-byte row XOR-ed with the row index mod 4; TMA writes it with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  Shared memory holds BLOCK/32 chunks of [32 K rows x 32 MN elements
+// (128 B)], 4096 B apart; one MMA (K = 8) reads 8 consecutive 128-byte rows = two 4-row swizzle atoms of every
+// chunk.  Canonical form (16-byte units): ((8,n),(4,k)) : ((1,LBO),(8,SBO)) with LBO = chunk stride = 4096 B,
+// SBO = 4-row group stride = 512 B; layout type 1 in bits [61,64).
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
 }
 
 __device__ __forceinline__ void red_add_v4(float *addr, float4 v) {
@@ -132,8 +135,9 @@ __host__ __device__ constexpr uint32_t make_idesc_major() {
 //   A_MN: A is stored [K, M] (M contiguous)      B_MN: B is stored [K, N] (N contiguous)
 // EPI_STORE   C = acc
 // EPI_ATOMIC  C += acc with red.global.add.v4.f32 (split-K over blockIdx.z; C zero-initialised by the caller)
-// EPI_MASK    C = (mask > 0) ? acc : 0 and colsum[n] += sum over rows of C (the ReLU backward + bias gradient of
-//             the layer that produced `mask`, fused into the input-gradient GEMM)
+// EPI_MASK    C = (mask > 0) ? acc : 0 and colsum[m_blk, n] = sum over the CTA's 128 rows of C (the ReLU backward +
+//             bias gradient of the layer that produced `mask`, fused into the input-gradient GEMM; the caller
+//             sums the gridDim.y row-tile partials)
 // Same warp roles / pipeline as linear_tf32_kernel.  K need not be a multiple of 32 for MN-major operands (TMA
 // zero-fills rows past the end); M and N tails are handled by TMA zero fill + guarded stores.
 // ---------------------------------------------------------------------------------------------------------------
@@ -222,12 +226,27 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             umma_commit(tmem_full_bar);
         }
     } else {                                               // ---- epilogue warps 2..5
-        mbar_wait(tmem_full_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;
         float *stage_out = reinterpret_cast<float *>(smem) + (warp - 2) * (32 * 36);
+        float *col_part = reinterpret_cast<float *>(smem) + 4 * (32 * 36);        // [4 warps][BLOCK_N], EPI_MASK only
         const int sub = lane & 7, rgrp = lane >> 3;
         const size_t col0 = (size_t)n_blk * BLOCK_N;
+        // EPI_MASK: the 8 mask vectors this lane needs for a 32-column chunk are fetched one chunk ahead (the
+        // first before the accumulator is even complete), so the epilogue pays one memory latency per chunk at
+        // most instead of one per row group
+        float4 mk[8];
+        auto fetch_mask = [&](int c) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int grow = m_blk * kBlockM + q * 32 + it * 4 + rgrp;
+                const size_t col = col0 + c * 32 + sub * 4;
+                mk[it] = (grow < M && col < (size_t)N) ? __ldg(reinterpret_cast<const float4 *>(mask + (size_t)grow * N + col))
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        if (EPI == EPI_MASK) fetch_mask(0);
+        mbar_wait(tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
             uint32_t r[32];
@@ -261,9 +280,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         red_add_v4(dst, v);
                     } else {
                         if (EPI == EPI_MASK) {
-                            const float4 mk = __ldg(reinterpret_cast<const float4 *>(mask + (size_t)grow * N + col));
-                            v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f;
-                            v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
+                            v.x = mk[it].x > 0.f ? v.x : 0.f; v.y = mk[it].y > 0.f ? v.y : 0.f;
+                            v.z = mk[it].z > 0.f ? v.z : 0.f; v.w = mk[it].w > 0.f ? v.w : 0.f;
                             csum.x += v.x; csum.y += v.y; csum.z += v.z; csum.w += v.w;
                         }
                         *reinterpret_cast<float4 *>(dst) = v;
@@ -271,15 +289,27 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
             }
             if (EPI == EPI_MASK) {
-                // lanes with equal `sub` hold the same 4 columns: fold the 4 row groups, then one atomic each
+                // lanes with equal `sub` hold the same 4 columns: fold the 4 row groups of this warp's 32 rows
 #pragma unroll
                 for (int o = 8; o < 32; o <<= 1) {
                     csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o); csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
                     csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o); csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
                 }
-                if (rgrp == 0 && col < (size_t)N) red_add_v4(colsum + col, csum);
+                if (rgrp == 0)
+                    *reinterpret_cast<float4 *>(col_part + (warp - 2) * BLOCK_N + c * 32 + sub * 4) = csum;
+                if (c + 1 < BLOCK_N / 32) fetch_mask(c + 1);
             }
             __syncwarp();
+        }
+        if (EPI == EPI_MASK) {
+            // the CTA's 128 rows: sum the 4 warps' partials, one row of colsum[gridDim.y, N] per CTA row-tile
+            // (the caller reduces the row-tiles; no atomics, deterministic)
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int t = threadIdx.x - 64;                    // 0..127 over the epilogue warps
+            for (int cc = t; cc < BLOCK_N; cc += 128) {
+                const float v = col_part[cc] + col_part[BLOCK_N + cc] + col_part[2 * BLOCK_N + cc] + col_part[3 * BLOCK_N + cc];
+                if (col0 + cc < (size_t)N) colsum[(size_t)m_blk * N + col0 + cc] = v;
+            }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
@@ -293,7 +323,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 template <int BLOCK_N, int STAGES, int ACT>
 __global__ void __launch_bounds__(kThreads, 2)
 linear_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                   const float *__restrict__ bias, float *__restrict__ C, int M, int N, int K)
+                   const float *__restrict__ bias, const uint8_t *__restrict__ rowmask, float *__restrict__ C,
+                   int M, int N, int K)
 {
     using L = SmemLayout<BLOCK_N>;
     extern __shared__ uint8_t smem_raw[];
@@ -404,8 +435,11 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 const int rr = it * 4 + rgrp;
                 const float4 v = *reinterpret_cast<const float4 *>(stage_out + rr * 36 + sub * 4);
                 const int grow = m_blk * kBlockM + q * 32 + rr;
-                if (grow < M)
-                    *reinterpret_cast<float4 *>(C + (size_t)grow * N + col0 + c * 32 + sub * 4) = v;
+                if (grow < M) {
+                    // rowmask: `value.masked_fill(padding_mask[..., None], 0)` of ms_deform_attn.py:99-100 in place
+                    const float4 o = (rowmask && rowmask[grow]) ? make_float4(0.f, 0.f, 0.f, 0.f) : v;
+                    *reinterpret_cast<float4 *>(C + (size_t)grow * N + col0 + c * 32 + sub * 4) = o;
+                }
             }
             __syncwarp();
         }
@@ -450,8 +484,8 @@ int make_map(CUtensorMap *map, const float *ptr, uint64_t rows, uint64_t cols, u
 }
 
 template <int BLOCK_N, int STAGES, int ACT>
-int launch(const CUtensorMap &ta, const CUtensorMap &tb, const float *bias, float *y, int M, int N, int K,
-           cudaStream_t stream) {
+int launch(const CUtensorMap &ta, const CUtensorMap &tb, const float *bias, const uint8_t *rowmask, float *y, int M,
+           int N, int K, cudaStream_t stream) {
     using L = SmemLayout<BLOCK_N>;
     constexpr int smem = STAGES * L::kStageBytes + (2 * STAGES + 1) * 8 + 16 + 1024;
     auto kern = linear_tf32_kernel<BLOCK_N, STAGES, ACT>;
@@ -462,13 +496,14 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tb, const float *bias, floa
         configured = true;
     }
     dim3 grid(N / BLOCK_N, (M + kBlockM - 1) / kBlockM, 1);
-    kern<<<grid, kThreads, smem, stream>>>(ta, tb, bias, y, M, N, K);
+    kern<<<grid, kThreads, smem, stream>>>(ta, tb, bias, rowmask, y, M, N, K);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
 }
 
 // 2-D fp32 tensor [rows, cols] row-major, box = [box_rows, box_cols <= 32], 128-byte swizzle, zero OOB fill
-int make_map_box(CUtensorMap *map, const float *ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
+int make_map_box(CUtensorMap *map, const float *ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols,
+                 bool mn_major) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return RLIPV2_DENSE_EDRIVER;
     cuuint64_t dims[2] = {cols, rows};
@@ -476,8 +511,9 @@ int make_map_box(CUtensorMap *map, const float *ptr, uint64_t rows, uint64_t col
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : RLIPV2_DENSE_EDRIVER;
 }
 
@@ -490,9 +526,9 @@ int launch_gemm(const float *a, const float *b, float *c, const float *mask, flo
     CUtensorMap ta, tb;
     // K-major operand: stored [rows = M|N, cols = K], box 128|BLOCK_N rows x 32 K;  MN-major: stored [rows = K,
     // cols = M|N], box 32 K rows x 32 columns
-    int rc = A_MN ? make_map_box(&ta, a, (uint64_t)K, (uint64_t)M, 32, 32) : make_map_box(&ta, a, (uint64_t)M, (uint64_t)K, kBlockM, kBlockK);
+    int rc = A_MN ? make_map_box(&ta, a, (uint64_t)K, (uint64_t)M, 32, 32, true) : make_map_box(&ta, a, (uint64_t)M, (uint64_t)K, kBlockM, kBlockK, false);
     if (rc) return rc;
-    rc = B_MN ? make_map_box(&tb, b, (uint64_t)K, (uint64_t)N, 32, 32) : make_map_box(&tb, b, (uint64_t)N, (uint64_t)K, BLOCK_N, kBlockK);
+    rc = B_MN ? make_map_box(&tb, b, (uint64_t)K, (uint64_t)N, 32, 32, true) : make_map_box(&tb, b, (uint64_t)N, (uint64_t)K, BLOCK_N, kBlockK, false);
     if (rc) return rc;
     auto kern = gemm_tf32_kernel<BLOCK_N, STAGES, A_MN, B_MN, EPI>;
     static bool configured = false;
@@ -537,7 +573,7 @@ int rlipv2_dense_dgrad_tf32(const float *g, const float *w, float *dx, const flo
 {
     // dx[T,K] = g[T,N] . w[N,K]: A = g (K-major: contraction N contiguous), logical B = w^T [K, N] stored as
     // w [N, K] = [contraction rows, output cols]: MN-major.  relu_out != NULL: dx = (relu_out > 0) ? dx : 0 and
-    // colsum[K] += column sums of the masked dx (colsum zero-initialised by the caller).
+    // colsum_partial[ceil(T/128), K] = per-row-tile column sums of the masked dx (fully written).
     if (T == 0 || K == 0) return 0;
     if (T < 0 || N <= 0 || K < 0 || !g || !w || !dx) return RLIPV2_DENSE_EINVAL;
     if ((N % 4) || (K % 4)) return RLIPV2_DENSE_ESHAPE;
@@ -554,8 +590,8 @@ int rlipv2_dense_linear_tf32_supported(int M, int N, int K)
     return (M > 0 && N > 0 && K > 0 && (N % 128) == 0 && (K % kBlockK) == 0) ? 1 : 0;
 }
 
-int rlipv2_dense_linear_tf32(const float *x, const float *w, const float *bias, float *y, int M, int N, int K,
-                             int act, void *stream)
+int rlipv2_dense_linear_tf32_rowmask(const float *x, const float *w, const float *bias, const unsigned char *rowmask,
+                                     float *y, int M, int N, int K, int act, void *stream)
 {
     if (M == 0) return 0;
     if (!rlipv2_dense_linear_tf32_supported(M, N, K)) return RLIPV2_DENSE_ESHAPE;
@@ -568,11 +604,17 @@ int rlipv2_dense_linear_tf32(const float *x, const float *w, const float *bias, 
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     switch (act) {
-        case RLIPV2_DENSE_ACT_NONE: return launch<128, 3, RLIPV2_DENSE_ACT_NONE>(ta, tb, bias, y, M, N, K, s);
-        case RLIPV2_DENSE_ACT_RELU: return launch<128, 3, RLIPV2_DENSE_ACT_RELU>(ta, tb, bias, y, M, N, K, s);
-        case RLIPV2_DENSE_ACT_GELU: return launch<128, 3, RLIPV2_DENSE_ACT_GELU>(ta, tb, bias, y, M, N, K, s);
+        case RLIPV2_DENSE_ACT_NONE: return launch<128, 3, RLIPV2_DENSE_ACT_NONE>(ta, tb, bias, rowmask, y, M, N, K, s);
+        case RLIPV2_DENSE_ACT_RELU: return launch<128, 3, RLIPV2_DENSE_ACT_RELU>(ta, tb, bias, rowmask, y, M, N, K, s);
+        case RLIPV2_DENSE_ACT_GELU: return launch<128, 3, RLIPV2_DENSE_ACT_GELU>(ta, tb, bias, rowmask, y, M, N, K, s);
         default: return RLIPV2_DENSE_EINVAL;
     }
+}
+
+int rlipv2_dense_linear_tf32(const float *x, const float *w, const float *bias, float *y, int M, int N, int K,
+                             int act, void *stream)
+{
+    return rlipv2_dense_linear_tf32_rowmask(x, w, bias, nullptr, y, M, N, K, act, stream);
 }
 
 const char *rlipv2_dense_error_string(int code)

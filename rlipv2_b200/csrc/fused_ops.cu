@@ -135,7 +135,9 @@ layernorm_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ z, 
 }
 
 // ---- (ReLU mask +) column sum: CTA = 32 columns x 8 row-lanes, grid.y row chunks --------------------------------
-template <bool MASK>
+// MASK: 0 = plain column sum, 1 = ReLU mask from the forward output y, 2 = row mask (bytes, y reinterpreted):
+// rows with a non-zero byte are zeroed (the backward of masked_fill(mask[..., None], 0))
+template <int MASK>
 __global__ void __launch_bounds__(256)
 relu_bwd_colsum_kernel(const float *__restrict__ g, const float *__restrict__ y, float *__restrict__ gm,
                        float *__restrict__ colsum, int M, int N)
@@ -149,10 +151,13 @@ relu_bwd_colsum_kernel(const float *__restrict__ g, const float *__restrict__ y,
     for (int row = blockIdx.y * 32 + rl; row < M; row += gridDim.y * 32) {
         const size_t off = (size_t)row * N + col;
         float4 v = *reinterpret_cast<const float4 *>(g + off);
-        if (MASK) {
+        if (MASK == 1) {
             const float4 t = *reinterpret_cast<const float4 *>(y + off);
             v.x = t.x > 0.f ? v.x : 0.f; v.y = t.y > 0.f ? v.y : 0.f;
             v.z = t.z > 0.f ? v.z : 0.f; v.w = t.w > 0.f ? v.w : 0.f;
+            *reinterpret_cast<float4 *>(gm + off) = v;
+        } else if (MASK == 2) {
+            if (reinterpret_cast<const unsigned char *>(y)[row]) v = make_float4(0.f, 0.f, 0.f, 0.f);
             *reinterpret_cast<float4 *>(gm + off) = v;
         }
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
@@ -276,8 +281,26 @@ int rlipv2_relu_bwd_colsum_f32(const float *g, const float *y, float *gmasked, f
     const int max_gy = (M + 31) / 32;
     if (gy > max_gy) gy = max_gy;
     if (gy < 1) gy = 1;
-    if (y) relu_bwd_colsum_kernel<true><<<dim3(gx, gy), 256, 0, s>>>(g, y, gmasked, colsum, M, N);
-    else relu_bwd_colsum_kernel<false><<<dim3(gx, gy), 256, 0, s>>>(g, nullptr, nullptr, colsum, M, N);
+    if (y) relu_bwd_colsum_kernel<1><<<dim3(gx, gy), 256, 0, s>>>(g, y, gmasked, colsum, M, N);
+    else relu_bwd_colsum_kernel<0><<<dim3(gx, gy), 256, 0, s>>>(g, nullptr, nullptr, colsum, M, N);
+    return done();
+}
+
+int rlipv2_rowmask_bwd_colsum_f32(const float *g, const unsigned char *rowmask, float *gmasked, float *colsum, int M,
+                                  int N, void *stream)
+{
+    if (!colsum || M < 0 || N <= 0 || N % 32 != 0) return N % 32 != 0 ? RLIPV2_FUSED_ESHAPE : RLIPV2_FUSED_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(colsum, 0, sizeof(float) * N, s);
+    if (e != cudaSuccess) return (int)e;
+    if (M == 0) return 0;
+    if (!g || !rowmask || !gmasked) return RLIPV2_FUSED_EINVAL;
+    const int gx = N / 32;
+    int gy = (kSMs * 8 + gx - 1) / gx;
+    const int max_gy = (M + 31) / 32;
+    if (gy > max_gy) gy = max_gy;
+    if (gy < 1) gy = 1;
+    relu_bwd_colsum_kernel<2><<<dim3(gx, gy), 256, 0, s>>>(g, reinterpret_cast<const float *>(rowmask), gmasked, colsum, M, N);
     return done();
 }
 

@@ -23,6 +23,7 @@ _USE_FUSED = True        # fused LayerNorm / bias-gradient kernels (exact fp32 a
 # backward GEMMs (weight / input gradients) on the tcgen05 kernels instead of cuBLAS, for calls with at least
 # _OWN_BWD_MIN_ROWS rows (the split-K weight gradient pays off on the encoder's 44k-token activations)
 _OWN_BWD = os.environ.get("RLIPV2_OWN_BWD", "0") == "1"
+_OWN_WGRAD = os.environ.get("RLIPV2_OWN_WGRAD", "1") != "0"
 _OWN_BWD_MIN_ROWS = int(os.environ.get("RLIPV2_OWN_BWD_MIN_ROWS", "4096"))
 
 
@@ -49,26 +50,33 @@ class _LinearTF32(torch.autograd.Function):
     """y = act(x W^T + b) on the tcgen05 kernel; backward = cuBLAS TF32 GEMMs + fused mask."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act):
+    def forward(ctx, x, weight, bias, act, row_mask=None):
         abi = _abi()
         x2 = x.reshape(-1, x.shape[-1])
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         w = weight if weight.is_contiguous() else weight.contiguous()
-        y = abi.linear_tf32(x2, w, bias, act)
+        rm = None
+        if row_mask is not None:
+            rm = row_mask.reshape(-1)
+            rm = rm if rm.is_contiguous() else rm.contiguous()
+        y = abi.linear_tf32(x2, w, bias, act, rm)
         ctx.act = act
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(x2, w, y if act == abi.ACT_RELU else None)
+        ctx.save_for_backward(x2, w, y if act == abi.ACT_RELU else None, rm)
         return y.view(*x.shape[:-1], weight.shape[0])
 
     @staticmethod
     def backward(ctx, grad_out):
-        x2, w, y = ctx.saved_tensors
+        x2, w, y, rm = ctx.saved_tensors
         g = grad_out.reshape(-1, grad_out.shape[-1])
         if not g.is_contiguous():
             g = g.contiguous()
         gb = None
-        if g.shape[1] % 32 == 0:
+        if rm is not None:
+            # rows zeroed in the forward carry no gradient (N % 128 == 0 on this path, so the kernel applies)
+            g, gb = _fused().rowmask_bwd_colsum(g, rm)
+        elif g.shape[1] % 32 == 0:
             # one pass: ReLU mask (when fused in the forward) + bias-gradient column sum
             g, gb = _fused().relu_bwd_colsum(g, y)
         else:
@@ -76,15 +84,20 @@ class _LinearTF32(torch.autograd.Function):
                 g = g * (y > 0)
             gb = g.sum(0)
         gx = gw = None
-        own = _OWN_BWD and _abi().grads_supported(g.shape[0], g.shape[1], w.shape[1])
+        T, N, K = g.shape[0], g.shape[1], w.shape[1]
+        big = T >= _OWN_BWD_MIN_ROWS and _abi().grads_supported(T, N, K)
         if ctx.needs_input_grad[0]:
-            gx = (_abi().dgrad_tf32(g, w)[0] if own and g.shape[0] >= _OWN_BWD_MIN_ROWS else g @ w)
-            gx = gx.view(*grad_out.shape[:-1], w.shape[1])
+            gx = (_abi().dgrad_tf32(g, w)[0] if _OWN_BWD and big else g @ w).view(*grad_out.shape[:-1], K)
         if ctx.needs_input_grad[1]:
-            gw = _abi().wgrad_tf32(g, x2) if own and g.shape[0] >= _OWN_BWD_MIN_ROWS else g.t() @ x2
+            # tall-skinny weight gradients (44k tokens -> a 256x256 .. 384x256 weight): cuBLAS falls back to an
+            # sm_80 64x64 kernel at 65-72 us; the split-K tcgen05 kernel takes 28-40 us (measured, B200)
+            if big and _OWN_WGRAD and (_OWN_BWD or N * K <= 384 * 256):
+                gw = _abi().wgrad_tf32(g, x2)
+            else:
+                gw = g.t() @ x2
         if not (ctx.has_bias and ctx.needs_input_grad[2]):
             gb = None
-        return gx, gw, gb, None
+        return gx, gw, gb, None, None
 
 
 class _FFNReLU(torch.autograd.Function):
@@ -174,10 +187,12 @@ def _tcgen05_ok(x, weight):
     return M > 0 and _abi().supported(M, weight.shape[0], weight.shape[1])
 
 
-def linear(x, weight, bias=None):
+def linear(x, weight, bias=None, row_mask=None):
+    """x W^T + b; `row_mask` (bool, x.shape[:-1]): those rows of the result are zero (masked_fill folded in)"""
     if _tcgen05_ok(x, weight):
-        return _LinearTF32.apply(x, weight, bias, 0)
-    return F.linear(x, weight, bias)
+        return _LinearTF32.apply(x, weight, bias, 0, row_mask)
+    y = F.linear(x, weight, bias)
+    return y if row_mask is None else y.masked_fill(row_mask[..., None], float(0))
 
 
 def linear_relu(x, weight, bias=None):

@@ -13,6 +13,8 @@ _lib = ctypes.CDLL(_path)
 _i, _p = ctypes.c_int, ctypes.c_void_p
 _lib.rlipv2_dense_linear_tf32.argtypes = [_p, _p, _p, _p, _i, _i, _i, _i, _p]
 _lib.rlipv2_dense_linear_tf32.restype = _i
+_lib.rlipv2_dense_linear_tf32_rowmask.argtypes = [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]
+_lib.rlipv2_dense_linear_tf32_rowmask.restype = _i
 _lib.rlipv2_dense_linear_tf32_supported.argtypes = [_i, _i, _i]
 _lib.rlipv2_dense_linear_tf32_supported.restype = _i
 _lib.rlipv2_dense_wgrad_tf32.argtypes = [_p, _p, _p, _i, _i, _i, _i, _p]
@@ -24,7 +26,7 @@ _lib.rlipv2_dense_error_string.restype = ctypes.c_char_p
 _lib.rlipv2_dense_launch_count.restype = ctypes.c_ulonglong
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
-EXPORTS = ("rlipv2_dense_linear_tf32", "rlipv2_dense_linear_tf32_supported", "rlipv2_dense_wgrad_tf32",
+EXPORTS = ("rlipv2_dense_linear_tf32", "rlipv2_dense_linear_tf32_rowmask", "rlipv2_dense_linear_tf32_supported", "rlipv2_dense_wgrad_tf32",
            "rlipv2_dense_dgrad_tf32", "rlipv2_dense_error_string", "rlipv2_dense_launch_count")
 
 
@@ -40,15 +42,17 @@ def supported(M, N, K):
     return bool(_lib.rlipv2_dense_linear_tf32_supported(M, N, K))
 
 
-def linear_tf32(x2d, weight, bias, act=ACT_NONE):
-    """x2d [M,K], weight [N,K], bias [N]|None - contiguous fp32 CUDA tensors -> y [M,N]"""
+def linear_tf32(x2d, weight, bias, act=ACT_NONE, rowmask=None):
+    """x2d [M,K], weight [N,K], bias [N]|None - contiguous fp32 CUDA tensors -> y [M,N]; rows r with rowmask[r]
+    (bool [M], contiguous) come out as zeros"""
     M, K = x2d.shape
     N = weight.shape[0]
     y = torch.empty((M, N), dtype=torch.float32, device=x2d.device)
     with torch.cuda.device(x2d.device):
-        rc = _lib.rlipv2_dense_linear_tf32(x2d.data_ptr(), weight.data_ptr(), bias.data_ptr() if bias is not None else None,
-                                           y.data_ptr(), M, N, K, act,
-                                           ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        rc = _lib.rlipv2_dense_linear_tf32_rowmask(
+            x2d.data_ptr(), weight.data_ptr(), bias.data_ptr() if bias is not None else None,
+            rowmask.data_ptr() if rowmask is not None else None, y.data_ptr(), M, N, K, act,
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     if rc != 0:
         raise RuntimeError(f"rlipv2_dense_linear_tf32: {_lib.rlipv2_dense_error_string(rc).decode()} (code {rc})")
     return y
@@ -68,7 +72,9 @@ def wgrad_splits(T, N, K):
     bn = 256 if K % 256 == 0 else 128
     tiles = ((N + 127) // 128) * ((K + bn - 1) // bn)
     kb = (T + 31) // 32
-    return max(1, min((296 + tiles - 1) // tiles, kb // 8 if kb >= 8 else 1))
+    # measured on the encoder's 44k-token shapes (profiles/dense_bwd_microbench_r01.jsonl): one wave of CTAs is best
+    # for small outputs, ~8 splits for the 2048x256 FFN weights (more splits = more reduction traffic)
+    return max(1, min((148 + tiles - 1) // tiles, kb // 8 if kb >= 8 else 1))
 
 
 def wgrad_tf32(g2d, x2d, splits=None):
@@ -90,11 +96,17 @@ def dgrad_tf32(g2d, weight, relu_out=None):
     T, N = g2d.shape
     K = weight.shape[1]
     dx = torch.empty((T, K), dtype=torch.float32, device=g2d.device)
-    colsum = torch.zeros(K, dtype=torch.float32, device=g2d.device) if relu_out is not None else None
+    colsum = torch.empty(((T + 127) // 128, K), dtype=torch.float32, device=g2d.device) if relu_out is not None else None
     with torch.cuda.device(g2d.device):
         rc = _lib.rlipv2_dense_dgrad_tf32(g2d.data_ptr(), weight.data_ptr(), dx.data_ptr(),
                                           relu_out.data_ptr() if relu_out is not None else None,
                                           colsum.data_ptr() if colsum is not None else None, T, N, K, _stream())
     if rc != 0:
         raise RuntimeError(f"rlipv2_dense_dgrad_tf32: {_lib.rlipv2_dense_error_string(rc).decode()} (code {rc})")
+    if colsum is not None:                       # add the row-tile partials up
+        if K % 32 == 0:
+            from . import fused_abi
+            colsum = fused_abi.relu_bwd_colsum(colsum, None)[1]
+        else:
+            colsum = colsum.sum(0)
     return dx, colsum

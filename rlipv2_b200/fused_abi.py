@@ -17,14 +17,15 @@ _lib.rlipv2_relu_bwd_colsum_f32.argtypes = [_p, _p, _p, _p, _i, _i, _p]
 _d = ctypes.c_double
 _lib.rlipv2_adamw_f32.argtypes = [_p, _p, _p, _p, _ll, _d, _d, _d, _d, _d, _p, _p]
 _lib.rlipv2_gather_chunks_f32.argtypes = [_p, _i, _p, _p]
-for _n in ("add_layernorm_fwd_f32", "layernorm_bwd_f32", "relu_bwd_colsum_f32", "adamw_f32", "gather_chunks_f32"):
+_lib.rlipv2_rowmask_bwd_colsum_f32.argtypes = [_p, _p, _p, _p, _i, _i, _p]
+for _n in ("add_layernorm_fwd_f32", "layernorm_bwd_f32", "relu_bwd_colsum_f32", "adamw_f32", "gather_chunks_f32", "rowmask_bwd_colsum_f32"):
     getattr(_lib, "rlipv2_" + _n).restype = _i
 _lib.rlipv2_fused_error_string.argtypes = [_i]
 _lib.rlipv2_fused_error_string.restype = ctypes.c_char_p
 _lib.rlipv2_fused_launch_count.restype = ctypes.c_ulonglong
 
 EXPORTS = ("rlipv2_add_layernorm_fwd_f32", "rlipv2_layernorm_bwd_f32", "rlipv2_relu_bwd_colsum_f32",
-           "rlipv2_adamw_f32", "rlipv2_gather_chunks_f32", "rlipv2_fused_error_string", "rlipv2_fused_launch_count")
+           "rlipv2_adamw_f32", "rlipv2_gather_chunks_f32", "rlipv2_rowmask_bwd_colsum_f32", "rlipv2_fused_error_string", "rlipv2_fused_launch_count")
 
 
 def library_path():
@@ -119,3 +120,14 @@ def gather_chunks(table_dev, n_chunks, flat):
     with torch.cuda.device(flat.device):
         rc = _lib.rlipv2_gather_chunks_f32(table_dev.data_ptr(), n_chunks, flat.data_ptr(), _stream())
     _check(rc, "rlipv2_gather_chunks_f32")
+
+
+def rowmask_bwd_colsum(g2, rowmask):
+    """g2 [M,N] contiguous fp32, rowmask [M] bool (True = row zeroed in the forward) -> (masked g, column sums)"""
+    M, N = g2.shape
+    colsum = torch.empty(N, dtype=torch.float32, device=g2.device)
+    gm = torch.empty_like(g2)
+    with torch.cuda.device(g2.device):
+        rc = _lib.rlipv2_rowmask_bwd_colsum_f32(g2.data_ptr(), rowmask.data_ptr(), gm.data_ptr(), colsum.data_ptr(), M, N, _stream())
+    _check(rc, "rlipv2_rowmask_bwd_colsum_f32")
+    return gm, colsum

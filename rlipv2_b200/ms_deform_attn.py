@@ -140,9 +140,8 @@ class MSDeformAttn(nn.Module):
         else:
             assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
 
-        value = dense.linear(input_flatten, self.value_proj.weight, self.value_proj.bias)
-        if input_padding_mask is not None:
-            value = value.masked_fill(input_padding_mask[..., None], float(0))
+        # value_proj + `masked_fill(padding_mask, 0)` (:98-100): the mask rides in the GEMM epilogue
+        value = dense.linear(input_flatten, self.value_proj.weight, self.value_proj.bias, row_mask=input_padding_mask)
         value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
         if (_FUSED_PROLOGUE and not reference_points.requires_grad and value.is_cuda
                 and input_flatten.dtype == torch.float32 and self.d_model // self.n_heads == 32

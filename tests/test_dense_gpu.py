@@ -129,3 +129,58 @@ def test_dgrad_tf32(T, N, K, mask):
     else:
         assert colsum is None
     assert float(((dx.double() - ref).abs() / bound).max()) <= 1.0
+
+
+def test_linear_rowmask_and_small_wgrad_through_the_seam():
+    """dense.linear(..., row_mask) in tf32 mode: masked_fill folded into the GEMM epilogue, its backward (row mask +
+    bias gradient in one pass), and the split-K tcgen05 weight gradient (T >= 4096 rows)"""
+    from rlipv2_b200 import dense
+    try:
+        dense.set_matmul_precision("tf32")
+        g = torch.Generator(device="cuda").manual_seed(5)
+        T = 5000
+        x = torch.randn(2, T // 2, 256, device="cuda", generator=g, requires_grad=True)
+        w = (torch.randn(256, 256, device="cuda", generator=g) / 16).requires_grad_(True)
+        b = torch.randn(256, device="cuda", generator=g).requires_grad_(True)
+        mask = torch.rand(2, T // 2, device="cuda", generator=g) < 0.2
+        go = torch.randn(2, T // 2, 256, device="cuda", generator=g)
+        y = dense.linear(x, w, b, row_mask=mask)
+        y.backward(go)
+        xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+        yr = torch.nn.functional.linear(xd, wd, bd).masked_fill(mask[..., None], 0.0)
+        yr.backward(go.double())
+        assert bool((y[mask] == 0).all())
+        rel = lambda a, r: float((a.double() - r).abs().max() / r.abs().max())
+        assert rel(y, yr) < 2e-3 and rel(x.grad, xd.grad) < 2e-3 and rel(w.grad, wd.grad) < 2e-3
+        assert rel(b.grad, bd.grad) < 1e-5
+        assert bool((x.grad[mask] == 0).all())
+    finally:
+        dense.set_matmul_precision("fp32")
+
+
+def test_ffn_relu_fused_backward(monkeypatch):
+    """dense.ffn_relu with the tcgen05 backward (dgrad with fused ReLU mask + bias gradient, split-K wgrad)"""
+    from rlipv2_b200 import dense
+    try:
+        dense.set_matmul_precision("tf32")
+        monkeypatch.setattr(dense, "_OWN_BWD", True)
+        g = torch.Generator(device="cuda").manual_seed(6)
+        T = 4500
+        x = torch.randn(T, 256, device="cuda", generator=g, requires_grad=True)
+        w1 = (torch.randn(2048, 256, device="cuda", generator=g) / 16).requires_grad_(True)
+        b1 = torch.randn(2048, device="cuda", generator=g).requires_grad_(True)
+        w2 = (torch.randn(256, 2048, device="cuda", generator=g) / 45).requires_grad_(True)
+        b2 = torch.randn(256, device="cuda", generator=g).requires_grad_(True)
+        go = torch.randn(T, 256, device="cuda", generator=g)
+        y = dense.ffn_relu(x, w1, b1, w2, b2)
+        assert y.grad_fn.__class__.__name__ == "_FFNReLUBackward"
+        y.backward(go)
+        ps = [t.detach().double().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+        yr = torch.nn.functional.linear(torch.relu(torch.nn.functional.linear(ps[0], ps[1], ps[2])), ps[3], ps[4])
+        yr.backward(go.double())
+        rel = lambda a, r: float((a.double() - r).abs().max() / r.abs().max())
+        assert rel(y, yr) < 3e-3
+        for a, r in zip((x, w1, b1, w2, b2), ps):
+            assert rel(a.grad, r.grad) < 4e-3
+    finally:
+        dense.set_matmul_precision("fp32")

@@ -17,7 +17,7 @@ for _ in range(3):
     ts.step_device(samples, targets, text)
 torch.cuda.synchronize()
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
-with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
     ts.step_device(samples, targets, text)
     torch.cuda.synchronize()
 agg = defaultdict(lambda: [0, 0.0])
@@ -38,3 +38,10 @@ if len(sys.argv) > 2 and sys.argv[2] == "big":
         t = e.device_time if hasattr(e, "device_time") else e.cuda_time
         if t >= 40:
             print(f"{t:8.1f} us  {e.name[:140]}")
+
+# which aten ops (with which operand shapes) own the device time: attribution of the copies / elementwise kernels
+print("---- aten ops by (name, input shapes), self device time")
+ka = prof.key_averages(group_by_input_shape=True)
+rows = sorted(ka, key=lambda e: -e.self_device_time_total)[:int(os.environ.get("TOPOPS", "120"))]
+for e in rows:
+    print(f"{e.self_device_time_total / 1e3:8.3f} ms  n={e.count:4d}  {e.key[:40]:40s} {str(e.input_shapes)[:150]}")

@@ -72,9 +72,9 @@ def wgrad_splits(T, N, K):
     bn = 256 if K % 256 == 0 else 128
     tiles = ((N + 127) // 128) * ((K + bn - 1) // bn)
     kb = (T + 31) // 32
-    # measured on the encoder's 44k-token shapes (profiles/dense_bwd_microbench_r01.jsonl): one wave of CTAs is best
-    # for small outputs, ~8 splits for the 2048x256 FFN weights (more splits = more reduction traffic)
-    return max(1, min((148 + tiles - 1) // tiles, kb // 8 if kb >= 8 else 1))
+    # measured on the encoder's 44k-token shapes (profiles/dense_bwd_microbench_r01.jsonl): one wave of CTAs, never
+    # more (a 2048x256 weight at 10 splits = 160 CTAs runs 45 % slower than at 8 = 128 CTAs on 148 SMs)
+    return max(1, min(148 // tiles if tiles <= 148 else 1, kb // 8 if kb >= 8 else 1))
 
 
 def wgrad_tf32(g2d, x2d, splits=None):

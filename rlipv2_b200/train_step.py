@@ -169,13 +169,8 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         else:
             self.flat_grad.zero_()
             total.backward()
-        if self.world > 1:
-            dist.all_reduce(self.flat_grad)
-            self.flat_grad.div_(self.world)
-        if self.clip_max_norm > 0:
-            # clip_grad_norm_ over the used parameters == one norm + one scale of the flat buffer
-            coef = torch.clamp(self.clip_max_norm / (self.flat_grad.norm() + 1e-6), max=1.0)
-            self.flat_grad.mul_(coef)
+        self.flat.allreduce_mean_()                  # one NCCL all-reduce of the flat buffer (world > 1)
+        self.flat.clip_(self.clip_max_norm)          # clip_grad_norm_: one norm + one scale
         self._adamw_step()
         return total.detach()
 
@@ -249,29 +244,14 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         # 2. flat parameter / gradient / Adam-moment buffers, one contiguous 16-byte aligned range per
         #    group: parameters and their .grad become views, so the step needs one all-reduce, one
         #    norm and three AdamW launches regardless of the number of tensors
-        ranges, off = [], 0
-        for plist, lr in groups:
-            start = off
-            off += sum(p.numel() for p in plist)
-            ranges.append((start, off, lr))
-            off = (off + 3) // 4 * 4
-        self.flat_param = torch.zeros(off, device=dev)
-        self.flat_grad = torch.zeros(off, device=dev)
-        self.exp_avg = torch.zeros(off, device=dev)
-        self.exp_avg_sq = torch.zeros(off, device=dev)
+        from .flat_dp import FlatParams
+        self.flat = FlatParams(groups, dev, grad_views=not self.gather_grads)
+        self.flat_param, self.flat_grad = self.flat.flat_param, self.flat.flat_grad
+        self.exp_avg, self.exp_avg_sq = self.flat.exp_avg, self.flat.exp_avg_sq
         self.step_t = torch.zeros((), device=dev)
-        self.param_offsets = []
-        for (plist, _), (start, _, _) in zip(groups, ranges):
-            o = start
-            for p in plist:
-                n = p.numel()
-                self.flat_param[o:o + n].copy_(p.data.reshape(-1))
-                p.data = self.flat_param[o:o + n].view_as(p)
-                p.grad = None if self.gather_grads else self.flat_grad[o:o + n].view_as(p)
-                self.param_offsets.append(o)
-                o += n
-        self.group_ranges = ranges
-        self.params = [p for plist, _ in groups for p in plist]
+        self.param_offsets = self.flat.param_offsets
+        self.group_ranges = self.flat.group_ranges
+        self.params = self.flat.params
         if self.gather_grads:
             from . import fused_abi
             rows = sum((p.numel() + fused_abi.GATHER_CHUNK - 1) // fused_abi.GATHER_CHUNK for p in self.params)

@@ -1,0 +1,121 @@
+"""N > 1 host logic on CPU: two `gloo` ranks.
+
+* `FlatParams` (the flat-gradient data-parallel scheme of the graphed step): after the single all-reduce the flat
+  gradient equals the gradient of the global-batch loss, `clip_` equals `clip_grad_norm_`, and the replicas stay
+  bit-identical after an optimizer step on the views.
+* `SetCriterionHOI`: `num_interactions` is all-reduced over ranks (/root/reference/models/hoi.py:4737-4740), so the
+  rank-mean of the box losses equals the single-process loss over the union of the ranks' images.
+"""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests.test_criterion_stacked import _setup
+
+WORLD = 2
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _model(seed=0):
+    torch.manual_seed(seed)
+    return torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+
+
+def _groups(model, lrs=(1e-2, 1e-3)):
+    ps = list(model.parameters())
+    return [(ps[:2], lrs[0]), (ps[2:], lrs[1])]        # group sizes 35 and 18: exercises the 4-element alignment
+
+
+def _worker(rank, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        from rlipv2_b200.flat_dp import FlatParams
+        torch.manual_seed(1)
+        x, y = torch.randn(8, 6) * 3, torch.randn(8, 3)
+        # ---- flat-gradient data parallelism
+        model = _model(seed=rank)                     # replicas start different on purpose
+        flat = FlatParams(_groups(model), "cpu")
+        flat.broadcast_params(0)
+        lo = rank * 4
+        flat.zero_grad()
+        torch.nn.functional.mse_loss(model(x[lo:lo + 4]), y[lo:lo + 4]).backward()
+        flat.allreduce_mean_()
+        g_after_reduce = flat.flat_grad.clone()
+        flat.clip_(0.1)
+        g_after_clip = flat.flat_grad.clone()
+        opt = torch.optim.AdamW([{"params": pl, "lr": lr} for pl, lr in _groups(model)], weight_decay=1e-4)
+        opt.step()                                     # updates the views == the flat buffer
+        # ---- criterion normalisation over ranks
+        criterion, outputs, targets = _setup(bs=2, sizes=(3, 1), giou_verb_label=False)
+        mine = {k: v[rank:rank + 1] for k, v in outputs.items() if k != "aux_outputs"}
+        mine["aux_outputs"] = [{k: v[rank:rank + 1] for k, v in a.items()} for a in outputs["aux_outputs"]]
+        losses = criterion(mine, targets[rank:rank + 1])
+        keys = ["loss_sub_bbox", "loss_sub_giou", "loss_sub_bbox_0", "loss_sub_giou_1"]
+        vec = torch.stack([losses[k].detach().reshape(()) for k in keys])
+        dist.all_reduce(vec)
+        q.put((rank, g_after_reduce, g_after_clip, flat.flat_param.clone(), flat.group_ranges, vec / WORLD))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_gloo_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, port, q)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in range(WORLD)], key=lambda r: r[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    # single-process reference: the global batch through one replica
+    torch.manual_seed(1)
+    x, y = torch.randn(8, 6) * 3, torch.randn(8, 3)
+    ref = _model(seed=0)
+    torch.nn.functional.mse_loss(ref(x), y).backward()
+
+    def flatten(tensors, ranges):
+        out = torch.zeros(res[0][1].numel())
+        groups = _groups(ref)
+        for (plist, _), (start, _, _) in zip(groups, ranges):
+            o = start
+            for p, t in zip(plist, tensors[:len(plist)]):
+                out[o:o + p.numel()] = t.reshape(-1)
+                o += p.numel()
+            tensors = tensors[len(plist):]
+        return out
+
+    ranges = res[0][4]
+    assert ranges[0][0] == 0 and ranges[1][0] % 4 == 0 and ranges[1][0] >= ranges[0][1]
+    g_ref = flatten([p.grad for p in ref.parameters()], ranges)
+    for r in res:
+        torch.testing.assert_close(r[1], g_ref, rtol=1e-5, atol=1e-6)
+    total = torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.1)
+    assert total > 0.1                               # the clip is active in this test
+    g_clip = flatten([p.grad for p in ref.parameters()], ranges)
+    for r in res:
+        torch.testing.assert_close(r[2], g_clip, rtol=1e-5, atol=1e-7)
+    opt = torch.optim.AdamW([{"params": pl, "lr": lr} for pl, lr in _groups(ref)], weight_decay=1e-4)
+    opt.step()
+    p_ref = flatten([p.data for p in ref.parameters()], ranges)
+    assert torch.equal(res[0][3], res[1][3])         # replicas stay bit-identical
+    torch.testing.assert_close(res[0][3], p_ref, rtol=1e-5, atol=1e-6)
+    # criterion: rank-mean of the num_interactions-normalised losses == single process over both images
+    criterion, outputs, targets = _setup(bs=2, sizes=(3, 1), giou_verb_label=False)
+    full = criterion(outputs, targets)
+    keys = ["loss_sub_bbox", "loss_sub_giou", "loss_sub_bbox_0", "loss_sub_giou_1"]
+    want = torch.stack([full[k].detach().reshape(()) for k in keys])
+    torch.testing.assert_close(res[0][5], want, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(res[1][5], want, rtol=1e-5, atol=1e-6)

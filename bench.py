@@ -250,6 +250,8 @@ def run_train_step(args, rank, world, device):
     e2e(0)
     n_e2e = max(2, min(args.steps, 5))
     ms_e2e = timed(e2e, n_e2e, world)
+    if args.graphs:
+        ts.check()                                   # no replay's host-flag wait timed out
     ms, ms_e2e = max_over_ranks([ms, ms_e2e], device, world)
     nparams = sum(p.numel() for p in ts.params)
     line = {

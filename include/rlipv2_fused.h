@@ -62,6 +62,22 @@ int rlipv2_adamw_f32(float *param, const float *grad, float *exp_avg, float *exp
  * buckets / engine.py:166-172 in the reference). */
 int rlipv2_gather_chunks_f32(const long long *table, int n_chunks, float *dst, void *stream);
 
+/* Head of the backward graph: a one-thread kernel that holds `stream` until the 32-bit word at `flag` (pinned host
+ * memory, device-visible) reaches *seq + 1, then stores that value to *seq.  The host publishes the replay's
+ * sequence number after it has written the matched indices (models/matcher.py:193 runs scipy on the host) into the
+ * pinned buffers that the following copy nodes read; the graph launch itself no longer waits for the host.  After
+ * `timeout_ns` without the flag the kernel stores the awaited value to *err and lets the stream continue. */
+int rlipv2_wait_host_flag(const unsigned *flag, unsigned *seq, unsigned long long timeout_ns, unsigned *err,
+                          void *stream);
+
+/* y[i] = sigmoid(delta[i] + inverse_sigmoid(ref[i])): the DAB decoder's box refinement
+ * (/root/reference/models/dab_deformable/deformable_transformer.py:1511-1541, util/misc.py:460-464) in one pass. */
+int rlipv2_box_refine_f32(const float *delta, const float *ref, float eps, long long n, float *y, void *stream);
+
+/* gen_sineembed_for_position (deformable_transformer.py:1777-1802): pos [rows, n] (n = 2 or 4; x, y[, w, h]) ->
+ * out [rows, n*128], coordinate order (y, x[, w, h]), temperature 10000. */
+int rlipv2_sine_embed_f32(const float *pos, int rows, int n, float *out, void *stream);
+
 const char *rlipv2_fused_error_string(int code);
 unsigned long long rlipv2_fused_launch_count(void);
 

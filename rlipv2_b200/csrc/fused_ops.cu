@@ -227,6 +227,62 @@ gather_chunks_kernel(const long long *__restrict__ table, float *__restrict__ ds
     }
 }
 
+// ---- host-flag wait: the head of the backward graph ------------------------------------------------------------
+// The step's only host work is the assignment solve between the forward graph and the backward graph.  The
+// backward graph is launched right behind the forward graph (its multi-millisecond launch cost overlaps the
+// forward's execution) and starts with this one-thread kernel, which holds the stream until the host publishes
+// the sequence number of this replay in a pinned, device-visible word - after it has written the matched indices
+// into the pinned buffers the following memcpy nodes read.  A timeout (reported through *err) bounds the wait, so a
+// host that died cannot hang the GPU.
+__global__ void wait_host_flag_kernel(const unsigned *flag, unsigned *seq, unsigned long long timeout_ns, unsigned *err)
+{
+    const unsigned want = *seq + 1u;
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - want) >= 0) break;
+        __nanosleep(200);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeout_ns) { *err = want; break; }
+    }
+    *seq = want;
+}
+
+// ---- DAB decoder small-op chains -------------------------------------------------------------------------------
+// y = sigmoid(delta + inverse_sigmoid(ref)), inverse_sigmoid(x) = log(max(clamp(x,0,1), eps) / max(1 - clamp(x,0,1), eps))
+// (util/misc.py:460-464 + the box refinement of dab_deformable/deformable_transformer.py:1511-1541): 9 torch
+// kernels over a [bs, nq, 4] tensor, one here.  Same operation order and IEEE division / accurate logf, expf.
+__global__ void __launch_bounds__(256)
+box_refine_kernel(const float *__restrict__ delta, const float *__restrict__ ref, float eps, long long n,
+                  float *__restrict__ y)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float x = fminf(fmaxf(ref[i], 0.f), 1.f);
+        const float inv = logf(__fdiv_rn(fmaxf(x, eps), fmaxf(1.f - x, eps)));
+        const float z = delta[i] + inv;
+        y[i] = __fdiv_rn(1.f, 1.f + expf(-z));
+    }
+}
+
+// Sine embedding of anchor coordinates (gen_sineembed_for_position, deformable_transformer.py:1777-1802):
+// pos [R, n] (x, y[, w, h]) -> out [R, n*128] in the order (y, x[, w, h]); feature k of a coordinate p is
+// sin(2 pi p / T_k) for even k, cos(2 pi p / T_k) for odd k, T_k = 10000^(2 floor(k/2) / 128).
+__global__ void __launch_bounds__(128)
+sine_embed_kernel(const float *__restrict__ pos, int R, int n, float *__restrict__ out)
+{
+    const int k = threadIdx.x;                       // feature 0..127
+    const float dim_t = powf(10000.f, (float)(2 * (k >> 1)) / 128.f);
+    const float scale = 6.283185307179586f;
+    for (int rc = blockIdx.x; rc < R * n; rc += gridDim.x) {
+        const int r = rc / n, c = rc - r * n;
+        const int src = c == 0 ? 1 : (c == 1 ? 0 : c);           // (y, x, w, h) <- columns (1, 0, 2, 3)
+        const float p = __fdiv_rn(pos[(size_t)r * n + src] * scale, dim_t);
+        out[(size_t)rc * 128 + k] = (k & 1) ? cosf(p) : sinf(p);
+    }
+}
+
 inline int done() {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
@@ -325,6 +381,34 @@ int rlipv2_gather_chunks_f32(const long long *table, int n_chunks, float *dst, v
     if (n_chunks == 0) return 0;
     if (!table || !dst || n_chunks < 0) return RLIPV2_FUSED_EINVAL;
     gather_chunks_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(table, dst);
+    return done();
+}
+
+int rlipv2_wait_host_flag(const unsigned *flag, unsigned *seq, unsigned long long timeout_ns, unsigned *err, void *stream)
+{
+    if (!flag || !seq || !err) return RLIPV2_FUSED_EINVAL;
+    wait_host_flag_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag, seq, timeout_ns, err);
+    return done();
+}
+
+int rlipv2_box_refine_f32(const float *delta, const float *ref, float eps, long long n, float *y, void *stream)
+{
+    if (n == 0) return 0;
+    if (!delta || !ref || !y || n < 0) return RLIPV2_FUSED_EINVAL;
+    long long blocks = (n + 255) / 256;
+    if (blocks > kSMs * 8) blocks = kSMs * 8;
+    box_refine_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(delta, ref, eps, n, y);
+    return done();
+}
+
+int rlipv2_sine_embed_f32(const float *pos, int rows, int n, float *out, void *stream)
+{
+    if (rows == 0) return 0;
+    if (!pos || !out || rows < 0) return RLIPV2_FUSED_EINVAL;
+    if (n != 2 && n != 4) return RLIPV2_FUSED_ESHAPE;
+    long long blocks = (long long)rows * n;
+    if (blocks > kSMs * 16) blocks = kSMs * 16;
+    sine_embed_kernel<<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(pos, rows, n, out);
     return done();
 }
 

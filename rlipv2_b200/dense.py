@@ -12,6 +12,7 @@ Two execution modes (`set_matmul_precision`):
           TF32 (round-1 state).
 There is no CPU implementation behind the tcgen05 path; CPU tensors only ever reach the torch ops.
 """
+import math
 import os
 
 import torch
@@ -220,3 +221,86 @@ def add_layer_norm(x, residual, weight, bias, eps):
     if _fused_ln_ok(x) and residual.shape == x.shape:
         return _AddLayerNorm.apply(x, residual, weight, bias, eps)
     return F.layer_norm(x + residual, (x.shape[-1],), weight, bias, eps)
+
+
+# ---- DAB decoder small-op chains (csrc/fused_ops.cu: box_refine_kernel, sine_embed_kernel) ---------------------
+_SMALL_OPS = os.environ.get("RLIPV2_SMALL_OPS", "1") != "0"
+
+
+def _inverse_sigmoid_torch(x, eps=1e-5):
+    x = x.clamp(min=0, max=1)
+    return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
+
+
+class _BoxRefine(torch.autograd.Function):
+    """sigmoid(delta + inverse_sigmoid(ref)) in one kernel; the gradient of `ref` (needed for the first decoder
+    layer only, whose anchors are the learned `refpoint_embed`) is formed by torch from the same formula."""
+
+    @staticmethod
+    def forward(ctx, delta, ref, eps):
+        d = delta if delta.is_contiguous() else delta.contiguous()
+        r = ref if ref.is_contiguous() else ref.contiguous()
+        y = _fused().box_refine(d, r, eps)
+        ctx.eps = eps
+        ctx.save_for_backward(y, r)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        y, r = ctx.saved_tensors
+        gz = torch.ops.aten.sigmoid_backward(g.contiguous(), y)
+        gref = None
+        if ctx.needs_input_grad[1]:
+            with torch.enable_grad():
+                rr = r.detach().requires_grad_(True)
+                (gref,) = torch.autograd.grad(_inverse_sigmoid_torch(rr, ctx.eps), rr, gz)
+        return gz, gref, None
+
+
+def box_refine(delta, ref, eps=1e-5):
+    """(delta + inverse_sigmoid(ref)).sigmoid() - the iterative box refinement of the DAB decoder
+    (dab_deformable/deformable_transformer.py:1511-1541; inverse_sigmoid: util/misc.py:460-464)"""
+    if _SMALL_OPS and _USE_FUSED and delta.is_cuda and delta.dtype == torch.float32 and delta.shape == ref.shape \
+            and delta.numel() > 0:
+        return _BoxRefine.apply(delta, ref, eps)
+    return (delta + _inverse_sigmoid_torch(ref, eps)).sigmoid()
+
+
+def _sine_embed_torch(pos_tensor):
+    n = pos_tensor.size(-1)
+    dim_t = torch.arange(128, dtype=torch.float32, device=pos_tensor.device)
+    dim_t = 10000 ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / 128)
+    # (x, y, ...) -> (y, x, ...) with slices only: an index list would become a host tensor + H2D copy, which a
+    # CUDA-graph capture rejects
+    yx = torch.cat((pos_tensor[..., 1:2], pos_tensor[..., 0:1], pos_tensor[..., 2:]), dim=-1)
+    p = (yx * (2 * math.pi))[..., None] / dim_t                                   # [.., n, 128]
+    emb = torch.stack((p[..., 0::2].sin(), p[..., 1::2].cos()), dim=-1)          # [.., n, 64, 2]
+    return emb.flatten(-3)
+
+
+class _SineEmbed(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos):
+        n = pos.shape[-1]
+        p2 = pos.reshape(-1, n)
+        p2 = p2 if p2.is_contiguous() else p2.contiguous()
+        ctx.save_for_backward(pos)
+        return _fused().sine_embed(p2).view(*pos.shape[:-1], n * 128)
+
+    @staticmethod
+    def backward(ctx, g):
+        (pos,) = ctx.saved_tensors
+        with torch.enable_grad():
+            pp = pos.detach().requires_grad_(True)
+            (gp,) = torch.autograd.grad(_sine_embed_torch(pp), pp, g)
+        return gp
+
+
+def sine_embed(pos_tensor):
+    """[..., 2|4] normalised (x, y[, w, h]) -> [..., 256|512] sine embedding in the order (y, x[, w, h]); 128
+    features each, temperature 10000 (gen_sineembed_for_position, deformable_transformer.py:1777-1802)."""
+    if pos_tensor.size(-1) not in (2, 4):
+        raise ValueError("Unknown pos_tensor shape(-1):{}".format(pos_tensor.size(-1)))
+    if _SMALL_OPS and _USE_FUSED and pos_tensor.is_cuda and pos_tensor.dtype == torch.float32 and pos_tensor.numel() > 0:
+        return _SineEmbed.apply(pos_tensor)
+    return _sine_embed_torch(pos_tensor)

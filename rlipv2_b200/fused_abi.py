@@ -18,6 +18,12 @@ _d = ctypes.c_double
 _lib.rlipv2_adamw_f32.argtypes = [_p, _p, _p, _p, _ll, _d, _d, _d, _d, _d, _p, _p]
 _lib.rlipv2_gather_chunks_f32.argtypes = [_p, _i, _p, _p]
 _lib.rlipv2_rowmask_bwd_colsum_f32.argtypes = [_p, _p, _p, _p, _i, _i, _p]
+_ull, _u64p = ctypes.c_ulonglong, ctypes.c_void_p
+_lib.rlipv2_wait_host_flag.argtypes = [_p, _p, _ull, _p, _p]
+_lib.rlipv2_box_refine_f32.argtypes = [_p, _p, _f, _ll, _p, _p]
+_lib.rlipv2_sine_embed_f32.argtypes = [_p, _i, _i, _p, _p]
+for _n in ("wait_host_flag", "box_refine_f32", "sine_embed_f32"):
+    getattr(_lib, "rlipv2_" + _n).restype = _i
 for _n in ("add_layernorm_fwd_f32", "layernorm_bwd_f32", "relu_bwd_colsum_f32", "adamw_f32", "gather_chunks_f32", "rowmask_bwd_colsum_f32"):
     getattr(_lib, "rlipv2_" + _n).restype = _i
 _lib.rlipv2_fused_error_string.argtypes = [_i]
@@ -25,7 +31,8 @@ _lib.rlipv2_fused_error_string.restype = ctypes.c_char_p
 _lib.rlipv2_fused_launch_count.restype = ctypes.c_ulonglong
 
 EXPORTS = ("rlipv2_add_layernorm_fwd_f32", "rlipv2_layernorm_bwd_f32", "rlipv2_relu_bwd_colsum_f32",
-           "rlipv2_adamw_f32", "rlipv2_gather_chunks_f32", "rlipv2_rowmask_bwd_colsum_f32", "rlipv2_fused_error_string", "rlipv2_fused_launch_count")
+           "rlipv2_adamw_f32", "rlipv2_gather_chunks_f32", "rlipv2_rowmask_bwd_colsum_f32", "rlipv2_wait_host_flag",
+           "rlipv2_box_refine_f32", "rlipv2_sine_embed_f32", "rlipv2_fused_error_string", "rlipv2_fused_launch_count")
 
 
 def library_path():
@@ -131,3 +138,34 @@ def rowmask_bwd_colsum(g2, rowmask):
         rc = _lib.rlipv2_rowmask_bwd_colsum_f32(g2.data_ptr(), rowmask.data_ptr(), gm.data_ptr(), colsum.data_ptr(), M, N, _stream())
     _check(rc, "rlipv2_rowmask_bwd_colsum_f32")
     return gm, colsum
+
+
+def wait_host_flag(flag_pinned, seq_dev, err_dev, timeout_s=10.0):
+    """Enqueue the backward graph's head: hold the current stream until the pinned int32 word `flag_pinned[0]`
+    reaches seq_dev[0] + 1 (see include/rlipv2_fused.h).  flag_pinned: pinned CPU int32 tensor (UVA: its host
+    address is its device address); seq_dev, err_dev: CUDA int32 tensors."""
+    assert flag_pinned.is_pinned() and flag_pinned.dtype == torch.int32
+    assert seq_dev.is_cuda and err_dev.is_cuda and seq_dev.dtype == torch.int32 and err_dev.dtype == torch.int32
+    with torch.cuda.device(seq_dev.device):
+        rc = _lib.rlipv2_wait_host_flag(flag_pinned.data_ptr(), seq_dev.data_ptr(), int(timeout_s * 1e9),
+                                        err_dev.data_ptr(), _stream())
+    _check(rc, "rlipv2_wait_host_flag")
+
+
+def box_refine(delta, ref, eps=1e-5):
+    """sigmoid(delta + inverse_sigmoid(ref)); contiguous fp32 CUDA tensors of equal shape."""
+    y = torch.empty_like(delta)
+    with torch.cuda.device(delta.device):
+        rc = _lib.rlipv2_box_refine_f32(delta.data_ptr(), ref.data_ptr(), eps, delta.numel(), y.data_ptr(), _stream())
+    _check(rc, "rlipv2_box_refine_f32")
+    return y
+
+
+def sine_embed(pos2d):
+    """pos2d [R, n] contiguous fp32 CUDA, n in (2, 4) -> [R, n*128]"""
+    R, n = pos2d.shape
+    out = torch.empty((R, n * 128), dtype=torch.float32, device=pos2d.device)
+    with torch.cuda.device(pos2d.device):
+        rc = _lib.rlipv2_sine_embed_f32(pos2d.data_ptr(), R, n, out.data_ptr(), _stream())
+    _check(rc, "rlipv2_sine_embed_f32")
+    return out

@@ -81,18 +81,7 @@ def gen_sineembed_for_position(pos_tensor):
     (y, x[, w, h]); 128 features each, temperature 10000 (deformable_transformer.py:1777-1802).
     The reference embeds one coordinate at a time (6 kernels each); here all coordinates go through the
     same elementwise ops at once - the values are identical, the launch count drops from ~28 to 7."""
-    n = pos_tensor.size(-1)
-    if n not in (2, 4):
-        raise ValueError("Unknown pos_tensor shape(-1):{}".format(n))
-    scale = 2 * math.pi
-    dim_t = torch.arange(128, dtype=torch.float32, device=pos_tensor.device)
-    dim_t = 10000 ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / 128)
-    # (x, y, ...) -> (y, x, ...) with slices only: an index list would become a host tensor + H2D copy, which a
-    # CUDA-graph capture rejects
-    yx = torch.cat((pos_tensor[..., 1:2], pos_tensor[..., 0:1], pos_tensor[..., 2:]), dim=-1)
-    p = (yx * scale)[..., None] / dim_t                                          # [bs, nq, n, 128]
-    emb = torch.stack((p[..., 0::2].sin(), p[..., 1::2].cos()), dim=4)          # [bs, nq, n, 64, 2]
-    return emb.flatten(2)
+    return dense.sine_embed(pos_tensor)
 
 
 class MultiBranchFusion(nn.Module):
@@ -359,11 +348,11 @@ class DABDeformableTransformerDecoderHOI(nn.Module):
             # iterative box refinement; the refined anchors are detached (:1511-1541)
             if self.sub_bbox_embed is not None:
                 sub_in = output[:, :pair_num] if self.ParSe else output
-                sub_box = (self.sub_bbox_embed[lid](sub_in) + inverse_sigmoid(sub_ref)).sigmoid()
+                sub_box = dense.box_refine(self.sub_bbox_embed[lid](sub_in), sub_ref)
                 sub_ref = sub_box.detach()
             if self.obj_bbox_embed is not None:
                 obj_in = output[:, pair_num:] if self.ParSe else output
-                obj_box = (self.obj_bbox_embed[lid](obj_in) + inverse_sigmoid(obj_ref)).sigmoid()
+                obj_box = dense.box_refine(self.obj_bbox_embed[lid](obj_in), obj_ref)
                 obj_ref = obj_box.detach()
             if self.sub_bbox_embed is not None and self.obj_bbox_embed is not None:
                 refined.append((sub_box, obj_box))

@@ -143,6 +143,9 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         # measured neutral on 1xB200 (37.2 vs 37.0 ms/step): inside a graph the ~600 accumulation kernels cost about what
         # the gather + the copies of non-stealable gradients cost.  Kept behind the switch.
         self.gather_grads = os.environ.get("RLIPV2_GATHER_GRADS", "0") == "1"
+        # backward graph launched behind the forward graph, parked on a host flag until the assignment is solved
+        # (hides the multi-millisecond launch of the ~3000-node graph; RLIPV2_FLAG_WAIT=0: launch it after the solve)
+        self.flag_wait = os.environ.get("RLIPV2_FLAG_WAIT", "1") != "0"
 
     # the piece of work each graph records -------------------------------------------------------------
     def _forward_and_costs(self):
@@ -155,8 +158,15 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         giou = -torch.stack([cl[0] for cl in cost_lists]) if self.criterion.giou_verb_label else None
         return outputs, giou
 
-    def _loss_backward_step(self, outputs, giou):
+    def _loss_backward_step(self, outputs, giou, graph_head=False):
         from .criterion import StackedMatches
+        if graph_head:
+            # captured as the first nodes of graph B: wait for the host's publication of this replay, then fetch
+            # the matched indices from the pinned buffers (memcpy nodes with fixed addresses)
+            from . import fused_abi
+            fused_abi.wait_host_flag(self.h_flag, self.d_seq, self.d_err, timeout_s=self.flag_timeout_s)
+            self.s_I.copy_(self.h_I, non_blocking=True)
+            self.s_J.copy_(self.h_J, non_blocking=True)
         matches = StackedMatches(self.s_I, self.s_J, giou, self.ks)
         total = self._weighted_total(self.criterion(outputs, self.s_targets, matches=matches))
         if self.gather_grads:
@@ -208,6 +218,27 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         self.s_I.copy_(self.h_I, non_blocking=True)
         self.s_J.copy_(self.h_J, non_blocking=True)
 
+    def _solve_assignment_host(self):
+        """the same solve, written straight into the pinned index buffers through numpy views (no torch ops, no
+        H2D: graph B copies them after its flag wait)"""
+        from scipy.optimize import linear_sum_assignment
+        cost, hi, hj = self.np_cost, self.np_I, self.np_J
+        o = 0
+        for li in range(cost.shape[0]):
+            t0 = 0
+            for b, n in enumerate(self.sizes):
+                i, j = linear_sum_assignment(cost[li, b, :, t0:t0 + n])      # models/matcher.py:193
+                k = i.shape[0]
+                hi[o:o + k] = i
+                hj[o:o + k] = j
+                o += k
+                t0 += n
+
+    def check(self):
+        """raise if a replay's flag wait timed out (the host never published its assignment)"""
+        if self.captured and self.flag_wait and int(self.d_err.item()) != 0:
+            raise RuntimeError(f"backward graph replay {int(self.d_err.item())} timed out waiting for the host assignment")
+
     def capture(self, images_host, targets_host, text, warmup=3):
         dev = self.device
         self.s_tok = self.module.transformer.tokenize(text, dev)
@@ -220,6 +251,13 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         K = n_layers * sum(self.ks)
         self.h_I, self.h_J = torch.zeros(K, dtype=torch.long).pin_memory(), torch.zeros(K, dtype=torch.long).pin_memory()
         self.s_I, self.s_J = torch.zeros(K, dtype=torch.long, device=dev), torch.zeros(K, dtype=torch.long, device=dev)
+        self.np_cost, self.np_I, self.np_J = self.h_cost.numpy(), self.h_I.numpy(), self.h_J.numpy()
+        self.h_flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.np_flag = self.h_flag.numpy()
+        self.d_seq = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.d_err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.flag_seq = 0
+        self.flag_timeout_s = float(os.environ.get("RLIPV2_FLAG_TIMEOUT_S", "10"))
 
         # One stream for the probe, the warm-up and both captures: autograd runs every backward node
         # (AccumulateGrad included) on the stream its forward op first ran on, so all of them must be
@@ -277,7 +315,7 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
             outputs, giou = self._forward_and_costs()
         self.graph_b = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool(), stream=self.cap_stream):
-            self.s_loss = self._loss_backward_step(outputs, giou)
+            self.s_loss = self._loss_backward_step(outputs, giou, graph_head=self.flag_wait)
         self._keep = (outputs, giou)      # the autograd graph's buffers belong to the captured pool
         self.done_a = torch.cuda.Event()
         self.captured = True
@@ -295,9 +333,18 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         """One step on the batch currently held by the static buffers."""
         self.graph_a.replay()
         self.done_a.record()
+        if not self.flag_wait:
+            self.done_a.synchronize()           # costs are in pinned memory now
+            self._solve_assignment()
+            self.graph_b.replay()
+            return self.s_loss
+        self.graph_b.replay()                   # enqueued behind A; its head waits for the flag below
         self.done_a.synchronize()               # costs are in pinned memory now
-        self._solve_assignment()
-        self.graph_b.replay()
+        try:
+            self._solve_assignment_host()
+        finally:
+            self.flag_seq += 1                  # always publish: a failed solve must not park the GPU
+            self.np_flag[0] = self.flag_seq
         return self.s_loss
 
     def step(self, images_host, targets_host, text=None):

@@ -41,5 +41,7 @@ def test_graphed_step_matches_eager_step():
         imgs2, tg2 = train_step.synthetic_batch(2, 160, 192, n_obj=6, n_verb=4, triplets=3, seed=2)
         l5 = float(graphed.step(imgs2, tg2))
         assert l5 == l5 and l5 > 0
+        graphed.check()                                         # no flag wait timed out
+        assert graphed.flag_wait and int(graphed.d_seq.item()) == 3 == graphed.flag_seq
     finally:
         dense.set_matmul_precision("fp32")

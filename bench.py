@@ -61,9 +61,11 @@ class ClockSampler:
         self.index, self.samples, self.proc = index, [], None
 
     def __enter__(self):
+        if os.environ.get("RLIPV2_BENCH_NO_CLOCKS") == "1":      # diagnostic only: how much the polling costs
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", os.environ.get("RLIPV2_BENCH_CLOCKS_MS", "200")], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
             time.sleep(0.25)

@@ -70,6 +70,9 @@ int rlipv2_gather_chunks_f32(const long long *table, int n_chunks, float *dst, v
 int rlipv2_wait_host_flag(const unsigned *flag, unsigned *seq, unsigned long long timeout_ns, unsigned *err,
                           void *stream);
 
+/* Diagnostic: a one-thread kernel that stores the GPU's %globaltimer (ns) to *dst when the stream reaches it. */
+int rlipv2_stamp_globaltimer(unsigned long long *dst, void *stream);
+
 /* y[i] = sigmoid(delta[i] + inverse_sigmoid(ref[i])): the DAB decoder's box refinement
  * (/root/reference/models/dab_deformable/deformable_transformer.py:1511-1541, util/misc.py:460-464) in one pass. */
 int rlipv2_box_refine_f32(const float *delta, const float *ref, float eps, long long n, float *y, void *stream);

@@ -250,6 +250,14 @@ __global__ void wait_host_flag_kernel(const unsigned *flag, unsigned *seq, unsig
     *seq = want;
 }
 
+// one-thread timestamp: *dst = %globaltimer (ns).  Diagnostic node for the graphed step's anatomy (tools/step_anatomy.py).
+__global__ void stamp_kernel(unsigned long long *dst)
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *dst = t;
+}
+
 // ---- DAB decoder small-op chains -------------------------------------------------------------------------------
 // y = sigmoid(delta + inverse_sigmoid(ref)), inverse_sigmoid(x) = log(max(clamp(x,0,1), eps) / max(1 - clamp(x,0,1), eps))
 // (util/misc.py:460-464 + the box refinement of dab_deformable/deformable_transformer.py:1511-1541): 9 torch
@@ -388,6 +396,13 @@ int rlipv2_wait_host_flag(const unsigned *flag, unsigned *seq, unsigned long lon
 {
     if (!flag || !seq || !err) return RLIPV2_FUSED_EINVAL;
     wait_host_flag_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag, seq, timeout_ns, err);
+    return done();
+}
+
+int rlipv2_stamp_globaltimer(unsigned long long *dst, void *stream)
+{
+    if (!dst) return RLIPV2_FUSED_EINVAL;
+    stamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dst);
     return done();
 }
 

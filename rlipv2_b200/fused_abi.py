@@ -20,6 +20,8 @@ _lib.rlipv2_gather_chunks_f32.argtypes = [_p, _i, _p, _p]
 _lib.rlipv2_rowmask_bwd_colsum_f32.argtypes = [_p, _p, _p, _p, _i, _i, _p]
 _ull, _u64p = ctypes.c_ulonglong, ctypes.c_void_p
 _lib.rlipv2_wait_host_flag.argtypes = [_p, _p, _ull, _p, _p]
+_lib.rlipv2_stamp_globaltimer.argtypes = [_p, _p]
+_lib.rlipv2_stamp_globaltimer.restype = _i
 _lib.rlipv2_box_refine_f32.argtypes = [_p, _p, _f, _ll, _p, _p]
 _lib.rlipv2_sine_embed_f32.argtypes = [_p, _i, _i, _p, _p]
 for _n in ("wait_host_flag", "box_refine_f32", "sine_embed_f32"):
@@ -32,7 +34,7 @@ _lib.rlipv2_fused_launch_count.restype = ctypes.c_ulonglong
 
 EXPORTS = ("rlipv2_add_layernorm_fwd_f32", "rlipv2_layernorm_bwd_f32", "rlipv2_relu_bwd_colsum_f32",
            "rlipv2_adamw_f32", "rlipv2_gather_chunks_f32", "rlipv2_rowmask_bwd_colsum_f32", "rlipv2_wait_host_flag",
-           "rlipv2_box_refine_f32", "rlipv2_sine_embed_f32", "rlipv2_fused_error_string", "rlipv2_fused_launch_count")
+           "rlipv2_box_refine_f32", "rlipv2_sine_embed_f32", "rlipv2_stamp_globaltimer", "rlipv2_fused_error_string", "rlipv2_fused_launch_count")
 
 
 def library_path():
@@ -169,3 +171,11 @@ def sine_embed(pos2d):
         rc = _lib.rlipv2_sine_embed_f32(pos2d.data_ptr(), R, n, out.data_ptr(), _stream())
     _check(rc, "rlipv2_sine_embed_f32")
     return out
+
+
+def stamp(dst_int64, index):
+    """diagnostic: dst_int64[index] = GPU globaltimer (ns) when the current stream gets here"""
+    assert dst_int64.is_cuda and dst_int64.dtype == torch.int64
+    with torch.cuda.device(dst_int64.device):
+        rc = _lib.rlipv2_stamp_globaltimer(dst_int64.data_ptr() + 8 * index, _stream())
+    _check(rc, "rlipv2_stamp_globaltimer")

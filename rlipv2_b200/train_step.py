@@ -146,20 +146,29 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         # backward graph launched behind the forward graph, parked on a host flag until the assignment is solved
         # (hides the multi-millisecond launch of the ~3000-node graph; RLIPV2_FLAG_WAIT=0: launch it after the solve)
         self.flag_wait = os.environ.get("RLIPV2_FLAG_WAIT", "1") != "0"
+        self.stamps = None                      # diagnostic globaltimer stamps (RLIPV2_STAMPS=1, tools/step_anatomy.py)
 
     # the piece of work each graph records -------------------------------------------------------------
+    def _stamp(self, i):
+        if self.stamps is not None:
+            from . import fused_abi
+            fused_abi.stamp(self.stamps, i)
+
     def _forward_and_costs(self):
+        self._stamp(0)
         cache = self.module(self.s_samples, encode_and_save=True, text=self.s_tok, targets=self.s_targets)
         outputs = self.module(self.s_samples, encode_and_save=False, memory_cache=cache, text=self.s_tok,
                               targets=self.s_targets)
         layers = self.criterion.layers_of(outputs)
         C, cost_lists = self.criterion.matcher.compute_costs_layers(layers, self.s_targets)   # all layers, one pass
         self.h_cost.copy_(C, non_blocking=True)
+        self._stamp(1)
         giou = -torch.stack([cl[0] for cl in cost_lists]) if self.criterion.giou_verb_label else None
         return outputs, giou
 
     def _loss_backward_step(self, outputs, giou, graph_head=False):
         from .criterion import StackedMatches
+        self._stamp(2)
         if graph_head:
             # captured as the first nodes of graph B: wait for the host's publication of this replay, then fetch
             # the matched indices from the pinned buffers (memcpy nodes with fixed addresses)
@@ -167,6 +176,7 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
             fused_abi.wait_host_flag(self.h_flag, self.d_seq, self.d_err, timeout_s=self.flag_timeout_s)
             self.s_I.copy_(self.h_I, non_blocking=True)
             self.s_J.copy_(self.h_J, non_blocking=True)
+        self._stamp(3)
         matches = StackedMatches(self.s_I, self.s_J, giou, self.ks)
         total = self._weighted_total(self.criterion(outputs, self.s_targets, matches=matches))
         if self.gather_grads:
@@ -182,6 +192,7 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         self.flat.allreduce_mean_()                  # one NCCL all-reduce of the flat buffer (world > 1)
         self.flat.clip_(self.clip_max_norm)          # clip_grad_norm_: one norm + one scale
         self._adamw_step()
+        self._stamp(4)
         return total.detach()
 
     def _gather_grads(self):
@@ -257,6 +268,8 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         self.d_seq = torch.zeros(1, dtype=torch.int32, device=dev)
         self.d_err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.flag_seq = 0
+        if os.environ.get("RLIPV2_STAMPS", "0") == "1":
+            self.stamps = torch.zeros(8, dtype=torch.int64, device=dev)
         self.flag_timeout_s = float(os.environ.get("RLIPV2_FLAG_TIMEOUT_S", "10"))
 
         # One stream for the probe, the warm-up and both captures: autograd runs every backward node

@@ -219,9 +219,8 @@ def run_train_step(args, rank, world, device):
     loss = None
     if args.graphs:
         ts = train_step.GraphedParSeDATrainStep(device=str(device), precision=args.precision, seed=0)
-        l0 = own()
         ts.capture(images_h, targets_h, text, warmup=max(1, args.warmup - 1))
-        per_step = (own() - l0) // (max(1, args.warmup - 1) + 3)     # probe + warm-ups + 2 captures record one step each
+        per_step = ts.own_launches_per_step            # this repo's kernel nodes in the two captured graphs
 
         def step(i):
             nonlocal loss

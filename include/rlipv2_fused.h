@@ -48,6 +48,18 @@ int rlipv2_relu_bwd_colsum_f32(const float *g, const float *y, float *gmasked, f
 int rlipv2_rowmask_bwd_colsum_f32(const float *g, const unsigned char *rowmask, float *gmasked, float *colsum, int M,
                                   int N, void *stream);
 
+/* `_acc` variants: with accumulate != 0 the reduced outputs (dgamma/dbeta, colsum) are ADDED to what the arrays hold
+ * instead of overwriting them - the parameter-gradient accumulation (`param.grad += ...`, autograd's AccumulateGrad
+ * in the reference's loss.backward(), engine.py:163) folded into the producing kernel, writing straight into the
+ * flat gradient buffer. */
+int rlipv2_layernorm_bwd_acc_f32(const float *dy, const float *z, const float *mean, const float *rstd,
+                                 const float *gamma, int M, int C, float *dz, float *dgamma, float *dbeta,
+                                 int accumulate, void *stream);
+int rlipv2_relu_bwd_colsum_acc_f32(const float *g, const float *y, float *gmasked, float *colsum, int M, int N,
+                                   int accumulate, void *stream);
+int rlipv2_rowmask_bwd_colsum_acc_f32(const float *g, const unsigned char *rowmask, float *gmasked, float *colsum,
+                                      int M, int N, int accumulate, void *stream);
+
 /* One AdamW step over n contiguous elements (decoupled weight decay, torch.optim.AdamW semantics).
  * `step` is a device float holding the 1-based step count of THIS update (bias correction). */
 int rlipv2_adamw_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n,

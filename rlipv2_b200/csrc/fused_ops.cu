@@ -314,15 +314,17 @@ int rlipv2_add_layernorm_fwd_f32(const float *x, const float *r, const float *ga
     return done();
 }
 
-int rlipv2_layernorm_bwd_f32(const float *dy, const float *z, const float *mean, const float *rstd, const float *gamma,
-                             int M, int C, float *dz, float *dgamma, float *dbeta, void *stream)
+int rlipv2_layernorm_bwd_acc_f32(const float *dy, const float *z, const float *mean, const float *rstd, const float *gamma,
+                                 int M, int C, float *dz, float *dgamma, float *dbeta, int accumulate, void *stream)
 {
     if (!dgamma || !dbeta || M < 0) return RLIPV2_FUSED_EINVAL;
     if (C % 128 != 0 || C > 1024 || C <= 0) return RLIPV2_FUSED_ESHAPE;
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(dgamma, 0, sizeof(float) * C, s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(dbeta, 0, sizeof(float) * C, s);
-    if (e != cudaSuccess) return (int)e;
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(dgamma, 0, sizeof(float) * C, s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(dbeta, 0, sizeof(float) * C, s);
+        if (e != cudaSuccess) return (int)e;
+    }
     if (M == 0) return 0;
     if (!dy || !z || !mean || !rstd || !gamma || !dz) return RLIPV2_FUSED_EINVAL;
     const int grid = (int)(((long long)M + 7) / 8 < kSMs * 4 ? ((long long)M + 7) / 8 : kSMs * 4);
@@ -332,12 +334,21 @@ int rlipv2_layernorm_bwd_f32(const float *dy, const float *z, const float *mean,
     return done();
 }
 
-int rlipv2_relu_bwd_colsum_f32(const float *g, const float *y, float *gmasked, float *colsum, int M, int N, void *stream)
+int rlipv2_layernorm_bwd_f32(const float *dy, const float *z, const float *mean, const float *rstd, const float *gamma,
+                             int M, int C, float *dz, float *dgamma, float *dbeta, void *stream)
+{
+    return rlipv2_layernorm_bwd_acc_f32(dy, z, mean, rstd, gamma, M, C, dz, dgamma, dbeta, 0, stream);
+}
+
+int rlipv2_relu_bwd_colsum_acc_f32(const float *g, const float *y, float *gmasked, float *colsum, int M, int N, int accumulate,
+                                   void *stream)
 {
     if (!colsum || M < 0 || N <= 0 || N % 32 != 0) return N % 32 != 0 ? RLIPV2_FUSED_ESHAPE : RLIPV2_FUSED_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(colsum, 0, sizeof(float) * N, s);
-    if (e != cudaSuccess) return (int)e;
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(colsum, 0, sizeof(float) * N, s);
+        if (e != cudaSuccess) return (int)e;
+    }
     if (M == 0) return 0;
     if (!g || (y && !gmasked)) return RLIPV2_FUSED_EINVAL;
     const int gx = N / 32;
@@ -350,13 +361,20 @@ int rlipv2_relu_bwd_colsum_f32(const float *g, const float *y, float *gmasked, f
     return done();
 }
 
-int rlipv2_rowmask_bwd_colsum_f32(const float *g, const unsigned char *rowmask, float *gmasked, float *colsum, int M,
-                                  int N, void *stream)
+int rlipv2_relu_bwd_colsum_f32(const float *g, const float *y, float *gmasked, float *colsum, int M, int N, void *stream)
+{
+    return rlipv2_relu_bwd_colsum_acc_f32(g, y, gmasked, colsum, M, N, 0, stream);
+}
+
+int rlipv2_rowmask_bwd_colsum_acc_f32(const float *g, const unsigned char *rowmask, float *gmasked, float *colsum, int M,
+                                      int N, int accumulate, void *stream)
 {
     if (!colsum || M < 0 || N <= 0 || N % 32 != 0) return N % 32 != 0 ? RLIPV2_FUSED_ESHAPE : RLIPV2_FUSED_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(colsum, 0, sizeof(float) * N, s);
-    if (e != cudaSuccess) return (int)e;
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(colsum, 0, sizeof(float) * N, s);
+        if (e != cudaSuccess) return (int)e;
+    }
     if (M == 0) return 0;
     if (!g || !rowmask || !gmasked) return RLIPV2_FUSED_EINVAL;
     const int gx = N / 32;
@@ -366,6 +384,12 @@ int rlipv2_rowmask_bwd_colsum_f32(const float *g, const unsigned char *rowmask, 
     if (gy < 1) gy = 1;
     relu_bwd_colsum_kernel<2><<<dim3(gx, gy), 256, 0, s>>>(g, reinterpret_cast<const float *>(rowmask), gmasked, colsum, M, N);
     return done();
+}
+
+int rlipv2_rowmask_bwd_colsum_f32(const float *g, const unsigned char *rowmask, float *gmasked, float *colsum, int M,
+                                  int N, void *stream)
+{
+    return rlipv2_rowmask_bwd_colsum_acc_f32(g, rowmask, gmasked, colsum, M, N, 0, stream);
 }
 
 int rlipv2_adamw_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, double lr,

@@ -64,6 +64,10 @@ class _LinearTF32(torch.autograd.Function):
         y = abi.linear_tf32(x2, w, bias, act, rm)
         ctx.act = act
         ctx.has_bias = bias is not None
+        # parameters whose .grad is a view of the step's flat gradient buffer (train_step marks them `_fuse_grad`):
+        # the backward adds their gradients straight into that view instead of returning them to AccumulateGrad
+        ctx.w_acc = weight if getattr(weight, "_fuse_grad", False) and weight.is_contiguous() else None
+        ctx.b_acc = bias if bias is not None and getattr(bias, "_fuse_grad", False) else None
         ctx.save_for_backward(x2, w, y if act == abi.ACT_RELU else None, rm)
         return y.view(*x.shape[:-1], weight.shape[0])
 
@@ -74,12 +78,14 @@ class _LinearTF32(torch.autograd.Function):
         if not g.is_contiguous():
             g = g.contiguous()
         gb = None
+        b_acc = ctx.b_acc.grad if ctx.b_acc is not None and ctx.needs_input_grad[2] else None
+        w_acc = ctx.w_acc.grad if ctx.w_acc is not None and ctx.needs_input_grad[1] else None
         if rm is not None:
             # rows zeroed in the forward carry no gradient (N % 128 == 0 on this path, so the kernel applies)
-            g, gb = _fused().rowmask_bwd_colsum(g, rm)
+            g, gb = _fused().rowmask_bwd_colsum(g, rm, acc=b_acc)
         elif g.shape[1] % 32 == 0:
             # one pass: ReLU mask (when fused in the forward) + bias-gradient column sum
-            g, gb = _fused().relu_bwd_colsum(g, y)
+            g, gb = _fused().relu_bwd_colsum(g, y, acc=b_acc)
         else:
             if y is not None:
                 g = g * (y > 0)
@@ -93,7 +99,11 @@ class _LinearTF32(torch.autograd.Function):
             # tall-skinny weight gradients (44k tokens -> a 256x256 .. 384x256 weight): cuBLAS falls back to an
             # sm_80 64x64 kernel at 65-72 us; the split-K tcgen05 kernel takes 28-40 us (measured, B200)
             if big and _OWN_WGRAD and (_OWN_BWD or N * K <= 384 * 256):
-                gw = _abi().wgrad_tf32(g, x2)
+                gw = _abi().wgrad_tf32(g, x2, acc=w_acc)
+                gw = None if w_acc is not None else gw
+            elif w_acc is not None:
+                w_acc.addmm_(g.t(), x2)                  # cuBLAS with beta = 1: grad view += g^T x
+                gw = None
             else:
                 gw = g.t() @ x2
         if not (ctx.has_bias and ctx.needs_input_grad[2]):
@@ -165,6 +175,8 @@ class _AddLayerNorm(torch.autograd.Function):
         y, z, mean, rstd = f.add_layernorm_fwd(x2, r2, weight, bias, eps)
         ctx.save_for_backward(z, mean, rstd, weight)
         ctx.has_r = r is not None
+        fuse = getattr(weight, "_fuse_grad", False) and getattr(bias, "_fuse_grad", False)
+        ctx.acc = (weight, bias) if fuse else None
         return y.view(x.shape)
 
     @staticmethod
@@ -172,7 +184,11 @@ class _AddLayerNorm(torch.autograd.Function):
         z, mean, rstd, weight = ctx.saved_tensors
         g = grad_out.reshape(-1, grad_out.shape[-1])
         g = g if g.is_contiguous() else g.contiguous()
-        dz, dgamma, dbeta = _fused().layernorm_bwd(g, z, mean, rstd, weight)
+        acc = ctx.acc if ctx.acc is not None and ctx.needs_input_grad[2] and ctx.needs_input_grad[3] else None
+        if acc is not None and acc[0].grad is not None and acc[1].grad is not None:
+            dz, dgamma, dbeta = _fused().layernorm_bwd(g, z, mean, rstd, weight, acc[0].grad, acc[1].grad)
+        else:
+            dz, dgamma, dbeta = _fused().layernorm_bwd(g, z, mean, rstd, weight)
         dz = dz.view(grad_out.shape)
         return dz, (dz if ctx.has_r else None), dgamma, dbeta, None
 

@@ -77,11 +77,17 @@ def wgrad_splits(T, N, K):
     return max(1, min(148 // tiles if tiles <= 148 else 1, kb // 8 if kb >= 8 else 1))
 
 
-def wgrad_tf32(g2d, x2d, splits=None):
-    """dw [N,K] = g2d[T,N]^T @ x2d[T,K] (contiguous fp32 CUDA), split over the T axis and reduced with fp32 reductions"""
+def wgrad_tf32(g2d, x2d, splits=None, acc=None):
+    """dw [N,K] = g2d[T,N]^T @ x2d[T,K] (contiguous fp32 CUDA), split over the T axis and reduced with fp32 reductions.
+    `acc` (contiguous fp32 [N,K], e.g. the weight's view of the flat gradient buffer): the product is ADDED into it (the
+    kernel reduces with red.global.add anyway) instead of into a fresh zero-filled tensor."""
     T, N = g2d.shape
     K = x2d.shape[1]
-    dw = torch.zeros((N, K), dtype=torch.float32, device=g2d.device)
+    if acc is not None:
+        assert acc.shape == (N, K) and acc.is_contiguous() and acc.dtype == torch.float32 and acc.is_cuda
+        dw = acc
+    else:
+        dw = torch.zeros((N, K), dtype=torch.float32, device=g2d.device)
     with torch.cuda.device(g2d.device):
         rc = _lib.rlipv2_dense_wgrad_tf32(g2d.data_ptr(), x2d.data_ptr(), dw.data_ptr(), T, N, K,
                                           splits if splits is not None else wgrad_splits(T, N, K), _stream())

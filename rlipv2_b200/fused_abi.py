@@ -20,6 +20,11 @@ _lib.rlipv2_gather_chunks_f32.argtypes = [_p, _i, _p, _p]
 _lib.rlipv2_rowmask_bwd_colsum_f32.argtypes = [_p, _p, _p, _p, _i, _i, _p]
 _ull, _u64p = ctypes.c_ulonglong, ctypes.c_void_p
 _lib.rlipv2_wait_host_flag.argtypes = [_p, _p, _ull, _p, _p]
+_lib.rlipv2_layernorm_bwd_acc_f32.argtypes = [_p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _i, _p]
+_lib.rlipv2_relu_bwd_colsum_acc_f32.argtypes = [_p, _p, _p, _p, _i, _i, _i, _p]
+_lib.rlipv2_rowmask_bwd_colsum_acc_f32.argtypes = [_p, _p, _p, _p, _i, _i, _i, _p]
+for _n in ("layernorm_bwd_acc_f32", "relu_bwd_colsum_acc_f32", "rowmask_bwd_colsum_acc_f32"):
+    getattr(_lib, "rlipv2_" + _n).restype = _i
 _lib.rlipv2_stamp_globaltimer.argtypes = [_p, _p]
 _lib.rlipv2_stamp_globaltimer.restype = _i
 _lib.rlipv2_box_refine_f32.argtypes = [_p, _p, _f, _ll, _p, _p]
@@ -34,7 +39,8 @@ _lib.rlipv2_fused_launch_count.restype = ctypes.c_ulonglong
 
 EXPORTS = ("rlipv2_add_layernorm_fwd_f32", "rlipv2_layernorm_bwd_f32", "rlipv2_relu_bwd_colsum_f32",
            "rlipv2_adamw_f32", "rlipv2_gather_chunks_f32", "rlipv2_rowmask_bwd_colsum_f32", "rlipv2_wait_host_flag",
-           "rlipv2_box_refine_f32", "rlipv2_sine_embed_f32", "rlipv2_stamp_globaltimer", "rlipv2_fused_error_string", "rlipv2_fused_launch_count")
+           "rlipv2_box_refine_f32", "rlipv2_sine_embed_f32", "rlipv2_stamp_globaltimer", "rlipv2_layernorm_bwd_acc_f32",
+           "rlipv2_relu_bwd_colsum_acc_f32", "rlipv2_rowmask_bwd_colsum_acc_f32", "rlipv2_fused_error_string", "rlipv2_fused_launch_count")
 
 
 def library_path():
@@ -73,28 +79,40 @@ def add_layernorm_fwd(x2, r2, gamma, beta, eps):
     return y, z, mean, rstd
 
 
-def layernorm_bwd(dy2, z, mean, rstd, gamma):
+def _acc_ok(t, n):
+    return t is not None and t.is_cuda and t.dtype == torch.float32 and t.numel() == n and t.is_contiguous()
+
+
+def layernorm_bwd(dy2, z, mean, rstd, gamma, acc_gamma=None, acc_beta=None):
+    """-> (dz, dgamma, dbeta).  With `acc_gamma` / `acc_beta` (contiguous fp32 [C] views of the flat gradient buffer)
+    the parameter gradients are ADDED into them and (dz, None, None) is returned."""
     M, C = dy2.shape
     dz = torch.empty_like(dy2)
-    dgamma = torch.empty(C, dtype=torch.float32, device=dy2.device)
-    dbeta = torch.empty(C, dtype=torch.float32, device=dy2.device)
+    acc = _acc_ok(acc_gamma, C) and _acc_ok(acc_beta, C)
+    dgamma = acc_gamma if acc else torch.empty(C, dtype=torch.float32, device=dy2.device)
+    dbeta = acc_beta if acc else torch.empty(C, dtype=torch.float32, device=dy2.device)
     with torch.cuda.device(dy2.device):
-        rc = _lib.rlipv2_layernorm_bwd_f32(dy2.data_ptr(), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
-                                           M, C, dz.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _stream())
-    _check(rc, "rlipv2_layernorm_bwd_f32")
-    return dz, dgamma, dbeta
+        rc = _lib.rlipv2_layernorm_bwd_acc_f32(dy2.data_ptr(), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                               gamma.data_ptr(), M, C, dz.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                                               1 if acc else 0, _stream())
+    _check(rc, "rlipv2_layernorm_bwd_acc_f32")
+    return (dz, None, None) if acc else (dz, dgamma, dbeta)
 
 
-def relu_bwd_colsum(g2, y2=None):
-    """g2 [M,N] contiguous; y2 = forward output of the ReLU (or None) -> (masked g [M,N], column sums [N])"""
+def relu_bwd_colsum(g2, y2=None, acc=None):
+    """g2 [M,N] contiguous; y2 = forward output of the ReLU (or None) -> (masked g [M,N], column sums [N]).
+    With `acc` (contiguous fp32 [N] view of the flat gradient buffer) the column sums are ADDED into it and
+    (masked g, None) is returned."""
     M, N = g2.shape
-    colsum = torch.empty(N, dtype=torch.float32, device=g2.device)
+    into = _acc_ok(acc, N)
+    colsum = acc if into else torch.empty(N, dtype=torch.float32, device=g2.device)
     gm = torch.empty_like(g2) if y2 is not None else g2
     with torch.cuda.device(g2.device):
-        rc = _lib.rlipv2_relu_bwd_colsum_f32(g2.data_ptr(), y2.data_ptr() if y2 is not None else None,
-                                             gm.data_ptr() if y2 is not None else None, colsum.data_ptr(), M, N, _stream())
-    _check(rc, "rlipv2_relu_bwd_colsum_f32")
-    return gm, colsum
+        rc = _lib.rlipv2_relu_bwd_colsum_acc_f32(g2.data_ptr(), y2.data_ptr() if y2 is not None else None,
+                                                 gm.data_ptr() if y2 is not None else None, colsum.data_ptr(), M, N,
+                                                 1 if into else 0, _stream())
+    _check(rc, "rlipv2_relu_bwd_colsum_acc_f32")
+    return gm, (None if into else colsum)
 
 
 def adamw(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step):
@@ -131,15 +149,18 @@ def gather_chunks(table_dev, n_chunks, flat):
     _check(rc, "rlipv2_gather_chunks_f32")
 
 
-def rowmask_bwd_colsum(g2, rowmask):
-    """g2 [M,N] contiguous fp32, rowmask [M] bool (True = row zeroed in the forward) -> (masked g, column sums)"""
+def rowmask_bwd_colsum(g2, rowmask, acc=None):
+    """g2 [M,N] contiguous fp32, rowmask [M] bool (True = row zeroed in the forward) -> (masked g, column sums);
+    `acc`: as in relu_bwd_colsum"""
     M, N = g2.shape
-    colsum = torch.empty(N, dtype=torch.float32, device=g2.device)
+    into = _acc_ok(acc, N)
+    colsum = acc if into else torch.empty(N, dtype=torch.float32, device=g2.device)
     gm = torch.empty_like(g2)
     with torch.cuda.device(g2.device):
-        rc = _lib.rlipv2_rowmask_bwd_colsum_f32(g2.data_ptr(), rowmask.data_ptr(), gm.data_ptr(), colsum.data_ptr(), M, N, _stream())
-    _check(rc, "rlipv2_rowmask_bwd_colsum_f32")
-    return gm, colsum
+        rc = _lib.rlipv2_rowmask_bwd_colsum_acc_f32(g2.data_ptr(), rowmask.data_ptr(), gm.data_ptr(), colsum.data_ptr(), M, N,
+                                                    1 if into else 0, _stream())
+    _check(rc, "rlipv2_rowmask_bwd_colsum_acc_f32")
+    return gm, (None if into else colsum)
 
 
 def wait_host_flag(flag_pinned, seq_dev, err_dev, timeout_s=10.0):

@@ -303,6 +303,11 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         self.param_offsets = self.flat.param_offsets
         self.group_ranges = self.flat.group_ranges
         self.params = self.flat.params
+        if not self.gather_grads and os.environ.get("RLIPV2_FUSE_GRAD_ACC", "1") != "0":
+            # dense.py's backward functions add weight / bias / LayerNorm gradients straight into these views
+            # (GEMM with beta = 1, reductions without the zero-fill) instead of handing them to AccumulateGrad
+            for p in self.params:
+                p._fuse_grad = True
         if self.gather_grads:
             from . import fused_abi
             rows = sum((p.numel() + fused_abi.GATHER_CHUNK - 1) // fused_abi.GATHER_CHUNK for p in self.params)
@@ -315,23 +320,43 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
                 if id(p) not in used_ids:
                     dist.broadcast(p.data, 0)
         # 3. warm-up on a side stream (cuBLAS/cuDNN workspaces, lazy inits), then capture
+        # (with the flag wait, the last warm-up step is the priming replay below: `warmup` optimizer steps either way)
+        n_eager = max(1, warmup - 1) if self.flag_wait else warmup
         with torch.cuda.stream(side):
-            for _ in range(warmup):
+            for _ in range(n_eager):
                 outputs, giou = self._forward_and_costs()
                 side.synchronize()
                 self._solve_assignment()
                 self._loss_backward_step(outputs, giou)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        from . import dense_abi, fused_abi, msda_abi
+        own = lambda: msda_abi.launch_count() + dense_abi.launch_count() + fused_abi.launch_count()
+        l0 = own()
         self.graph_a = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_a, stream=self.cap_stream):
             outputs, giou = self._forward_and_costs()
         self.graph_b = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool(), stream=self.cap_stream):
             self.s_loss = self._loss_backward_step(outputs, giou, graph_head=self.flag_wait)
+        self.own_launches_per_step = own() - l0   # kernel nodes of this repo's libraries in the two graphs
         self._keep = (outputs, giou)      # the autograd graph's buffers belong to the captured pool
         self.done_a = torch.cuda.Event()
         self.captured = True
+        if self.flag_wait:
+            # Priming replay.  The first launch of a graph can block the host until the launch has been processed
+            # (measured on B200: the whole flag timeout, once) - with the backward graph parked on a flag only the
+            # host can publish, that is a deadlock bounded by the timeout.  So the first launch of graph B happens
+            # here with the flag already published; every later launch is asynchronous.
+            self.graph_a.replay()
+            self.done_a.record()
+            self.done_a.synchronize()
+            self._solve_assignment_host()
+            self.flag_seq += 1
+            self.np_flag[0] = self.flag_seq
+            self.graph_b.replay()
+            torch.cuda.synchronize()
+            self.check()
 
     def _forward_and_costs_eager_probe(self):
         outputs, giou = self._forward_and_costs()

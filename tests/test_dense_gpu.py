@@ -189,3 +189,56 @@ def test_ffn_relu_fused_backward(monkeypatch):
             assert rel(a.grad, r.grad) < 4e-3
     finally:
         dense.set_matmul_precision("fp32")
+
+
+@pytest.mark.parametrize("T,mode", [(300, "plain"), (300, "relu"), (5000, "plain"), (5000, "rowmask")])
+def test_fused_gradient_accumulation_into_flat_views(T, mode):
+    """Parameters marked `_fuse_grad` (the graphed step does that): weight / bias / LayerNorm gradients are ADDED
+    straight into the pre-assigned `.grad` views (cuBLAS beta = 1 or the split-K kernel without its zero-fill,
+    column sums without the memset) and autograd receives None for them - same values as AccumulateGrad."""
+    from rlipv2_b200 import dense
+    try:
+        dense.set_matmul_precision("tf32")
+        g = torch.Generator(device="cuda").manual_seed(7)
+        x = torch.randn(T, 256, device="cuda", generator=g, requires_grad=True)
+        go = torch.randn(T, 256, device="cuda", generator=g)
+        mask = (torch.rand(T, device="cuda", generator=g) < 0.2) if mode == "rowmask" else None
+
+        def params(fuse):
+            gg = torch.Generator(device="cuda").manual_seed(8)
+            flat = torch.ones(256 * 256 + 256 + 512, device="cuda")          # non-zero start: checks the "+="
+            w = torch.nn.Parameter(torch.randn(256, 256, device="cuda", generator=gg) / 16)
+            b = torch.nn.Parameter(torch.randn(256, device="cuda", generator=gg))
+            lw = torch.nn.Parameter(torch.rand(256, device="cuda", generator=gg) + 0.5)
+            lb = torch.nn.Parameter(torch.randn(256, device="cuda", generator=gg))
+            o = 0
+            for p in (w, b, lw, lb):
+                p.grad = flat[o:o + p.numel()].view_as(p)
+                o += p.numel()
+                if fuse:
+                    p._fuse_grad = True
+            return flat, w, b, lw, lb
+
+        def run(fuse):
+            flat, w, b, lw, lb = params(fuse)
+            xx = x.detach().clone().requires_grad_(True)
+            if mode == "relu":
+                h = dense.linear_relu(xx, w, b)
+            else:
+                h = dense.linear(xx, w, b, row_mask=mask)
+            y = dense.add_layer_norm(h, xx, lw, lb, 1e-5)
+            # the weight is used twice: both uses must land in the same view
+            y = y + dense.linear(xx, w, b, row_mask=mask) if mode != "relu" else y + dense.linear_relu(xx, w, b)
+            y.backward(go)
+            return flat, xx.grad
+
+        flat_f, gx_f = run(True)
+        flat_r, gx_r = run(False)
+        rel = lambda a, r: float((a - r).abs().max() / r.abs().max())
+        assert rel(gx_f, gx_r) < 1e-6
+        nw = 256 * 256
+        assert rel(flat_f[:nw], flat_r[:nw]) < 2e-3                         # weight: different GEMM kernels (TF32)
+        assert rel(flat_f[nw:], flat_r[nw:]) < 1e-5                         # bias, LayerNorm gamma / beta
+        assert float((flat_r - 1).abs().max()) > 1                          # the gradients are not trivially zero
+    finally:
+        dense.set_matmul_precision("fp32")

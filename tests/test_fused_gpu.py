@@ -45,6 +45,7 @@ def test_relu_bwd_colsum(M, N, mask):
 def test_flat_adamw_matches_torch():
     from rlipv2_b200 import fused_abi
     n = 1_000_003
+    torch.manual_seed(0)
     p0 = torch.randn(n + 1, device="cuda")[:n]                 # odd length exercises the scalar tail
     p0 = p0.clone()
     ref_p = torch.nn.Parameter(p0.clone())
@@ -59,5 +60,6 @@ def test_flat_adamw_matches_torch():
         fused_abi.adamw(p, grad, m, v, 1.41e-4, 0.9, 0.999, 1e-8, 1e-4, step)
     torch.testing.assert_close(p, ref_p.detach(), rtol=1e-5, atol=1e-6)
     st = opt.state[ref_p]
-    torch.testing.assert_close(m, st["exp_avg"], rtol=1e-5, atol=1e-7)
+    # moments are O(1) sums of O(1) terms that can cancel: a few ulps of 1.0 (1.2e-7) absolute, fma vs mul+add
+    torch.testing.assert_close(m, st["exp_avg"], rtol=1e-5, atol=5e-7)
     torch.testing.assert_close(v, st["exp_avg_sq"], rtol=1e-5, atol=1e-9)

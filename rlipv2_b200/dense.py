@@ -24,6 +24,9 @@ _USE_FUSED = True        # fused LayerNorm / bias-gradient kernels (exact fp32 a
 # backward GEMMs (weight / input gradients) on the tcgen05 kernels instead of cuBLAS, for calls with at least
 # _OWN_BWD_MIN_ROWS rows (the split-K weight gradient pays off on the encoder's 44k-token activations)
 _OWN_BWD = os.environ.get("RLIPV2_OWN_BWD", "0") == "1"
+# 'hybrid' FFN backward: only the down-projection's input gradient (ReLU gate + bias gradient fused in its epilogue) and
+# the two split-K weight gradients run on the tcgen05 kernels; the plain input gradient stays on cuBLAS' 256x256 2-SM kernel
+_FFN_BWD = os.environ.get("RLIPV2_FFN_BWD", "cublas")
 _OWN_WGRAD = os.environ.get("RLIPV2_OWN_WGRAD", "1") != "0"
 _OWN_BWD_MIN_ROWS = int(os.environ.get("RLIPV2_OWN_BWD_MIN_ROWS", "4096"))
 
@@ -129,6 +132,7 @@ class _FFNReLU(torch.autograd.Function):
         h = abi.linear_tf32(x2, w1.contiguous(), b1, abi.ACT_RELU)
         y = abi.linear_tf32(h, w2.contiguous(), b2, abi.ACT_NONE)
         ctx.save_for_backward(x2, w1, w2, h)
+        ctx.params = (w1, b1, w2, b2)
         return y.view(*x.shape[:-1], w2.shape[0])
 
     @staticmethod
@@ -137,18 +141,27 @@ class _FFNReLU(torch.autograd.Function):
         x2, w1, w2, h = ctx.saved_tensors
         g = grad_out.reshape(-1, grad_out.shape[-1])
         g = g if g.is_contiguous() else g.contiguous()
-        _, gb2 = _fused().relu_bwd_colsum(g, None)
-        gw2 = abi.wgrad_tf32(g, h)
+        acc = lambda p: p.grad if (p is not None and getattr(p, "_fuse_grad", False) and p.grad is not None) else None
+        w1p, b1p, w2p, b2p = ctx.params
+        _, gb2 = _fused().relu_bwd_colsum(g, None, acc=acc(b2p))
+        gw2 = abi.wgrad_tf32(g, h, acc=acc(w2p))
         gh, gb1 = abi.dgrad_tf32(g, w2, relu_out=h)
-        gw1 = abi.wgrad_tf32(gh, x2)
-        gx = abi.dgrad_tf32(gh, w1)[0].view(*grad_out.shape[:-1], w1.shape[1]) if ctx.needs_input_grad[0] else None
+        gw1 = abi.wgrad_tf32(gh, x2, acc=acc(w1p))
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = (gh @ w1 if _FFN_BWD == "hybrid" else abi.dgrad_tf32(gh, w1)[0]).view(*grad_out.shape[:-1], w1.shape[1])
+        if acc(b1p) is not None:
+            b1p.grad.add_(gb1)
+            gb1 = None
+        gw1 = None if acc(w1p) is not None else gw1
+        gw2 = None if acc(w2p) is not None else gw2
         return gx, gw1, gb1, gw2, gb2
 
 
 def ffn_relu(x, w1, b1, w2, b2):
     """relu(x W1^T + b1) W2^T + b2"""
     M = x.numel() // x.shape[-1]
-    if (_OWN_BWD and _tcgen05_ok(x, w1) and _abi().supported(M, w2.shape[0], w2.shape[1]) and M >= _OWN_BWD_MIN_ROWS
+    if ((_OWN_BWD or _FFN_BWD == "hybrid") and _tcgen05_ok(x, w1) and _abi().supported(M, w2.shape[0], w2.shape[1]) and M >= _OWN_BWD_MIN_ROWS
             and b1 is not None and b2 is not None and w2.shape[0] % 32 == 0):
         return _FFNReLU.apply(x, w1, b1, w2, b2)
     return linear(linear_relu(x, w1, b1), w2, b2)

@@ -8,9 +8,12 @@ Offline (no weights on disk) the synthetic path below is used: a random-init RoB
 same shape and a deterministic hash tokenizer, so that benchmarks and parity fixtures do the same
 arithmetic as a real run.
 """
+import os
+import types
 import zlib
 
 import torch
+from torch import nn
 
 
 def roberta_base_config():
@@ -82,3 +85,29 @@ def pooled_text(text_encoder, input_ids, attention_mask):
         ext = (1.0 - attention_mask[:, None, None, :].to(emb.dtype)) * torch.finfo(emb.dtype).min
         return te.pooler(te.encoder(emb, attention_mask=ext).last_hidden_state)
     return te(input_ids=input_ids, attention_mask=attention_mask).pooler_output
+
+
+def route_through_dense_seam(text_encoder):
+    """Send the text tower's `nn.Linear` / `nn.LayerNorm` calls through dense.py ("the
+    same tcgen05 RobertaLayer kernels" for the 12 RoBERTa layers that run every step).  Module structure, parameter
+    names and the arithmetic class stay HF's (x W^T + b, LayerNorm in fp32); what changes on a GPU in 'tf32' mode is
+    the execution: tcgen05 forward GEMMs with the bias in the epilogue, one-pass bias-gradient column sums, fused
+    LayerNorm backward, and - in the graphed step - weight / bias / LayerNorm gradients added straight into the
+    flat gradient buffer instead of ~200 AccumulateGrad kernels.  On CPU tensors and in 'fp32' mode dense.py calls
+    F.linear / F.layer_norm exactly as the modules did.  `RLIPV2_TEXT_DENSE=0` leaves the tower untouched."""
+    if os.environ.get("RLIPV2_TEXT_DENSE", "1") == "0":
+        return text_encoder
+    from . import dense
+
+    def linear_forward(self, x):
+        return dense.linear(x, self.weight, self.bias)
+
+    def ln_forward(self, x):
+        return dense.layer_norm(x, self.weight, self.bias, self.eps)
+
+    for m in text_encoder.modules():
+        if type(m) is nn.Linear:
+            m.forward = types.MethodType(linear_forward, m)
+        elif type(m) is nn.LayerNorm and len(m.normalized_shape) == 1 and m.elementwise_affine:
+            m.forward = types.MethodType(ln_forward, m)
+    return text_encoder

@@ -158,12 +158,15 @@ def test_linear_rowmask_and_small_wgrad_through_the_seam():
         dense.set_matmul_precision("fp32")
 
 
-def test_ffn_relu_fused_backward(monkeypatch):
-    """dense.ffn_relu with the tcgen05 backward (dgrad with fused ReLU mask + bias gradient, split-K wgrad)"""
+@pytest.mark.parametrize("mode,fuse", [("own", False), ("hybrid", False), ("hybrid", True)])
+def test_ffn_relu_fused_backward(monkeypatch, mode, fuse):
+    """dense.ffn_relu with the tcgen05 backward (dgrad with fused ReLU mask + bias gradient, split-K wgrad); 'hybrid'
+    keeps the plain input gradient on cuBLAS; `fuse`: parameter gradients added into pre-assigned .grad views"""
     from rlipv2_b200 import dense
     try:
         dense.set_matmul_precision("tf32")
-        monkeypatch.setattr(dense, "_OWN_BWD", True)
+        monkeypatch.setattr(dense, "_OWN_BWD", mode == "own")
+        monkeypatch.setattr(dense, "_FFN_BWD", "hybrid" if mode == "hybrid" else "cublas")
         g = torch.Generator(device="cuda").manual_seed(6)
         T = 4500
         x = torch.randn(T, 256, device="cuda", generator=g, requires_grad=True)
@@ -172,9 +175,16 @@ def test_ffn_relu_fused_backward(monkeypatch):
         w2 = (torch.randn(256, 2048, device="cuda", generator=g) / 45).requires_grad_(True)
         b2 = torch.randn(256, device="cuda", generator=g).requires_grad_(True)
         go = torch.randn(T, 256, device="cuda", generator=g)
+        if fuse:
+            for t in (w1, b1, w2, b2):
+                t.grad = torch.full_like(t, 0.5)                 # "+=": starts non-zero
+                t._fuse_grad = True
         y = dense.ffn_relu(x, w1, b1, w2, b2)
         assert y.grad_fn.__class__.__name__ == "_FFNReLUBackward"
         y.backward(go)
+        if fuse:
+            for t in (w1, b1, w2, b2):
+                t.grad = t.grad - 0.5
         ps = [t.detach().double().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
         # the ReLU gate is discontinuous: a hidden unit whose pre-activation is within TF32 rounding of zero may be
         # gated differently in fp64, which moves a gradient entry by a whole term - so the fp64 reference uses the

@@ -22,6 +22,7 @@ ts.capture(images_h, targets_h, text, warmup=2)
 for _ in range(3):
     ts.replay()
 torch.cuda.synchronize()
+ts.check()
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
@@ -34,6 +35,11 @@ for e in prof.events():
         dur = e.device_time if hasattr(e, "device_time") else e.cuda_time
         evs.append((e.time_range.start, e.time_range.start + dur, e.name, getattr(e, "device_resource_id", 0)))
 evs.sort()
+if os.environ.get("TIMELINE_DUMP"):
+    with open(os.environ["TIMELINE_DUMP"], "w") as f:
+        f.write("start_us,dur_us,stream,kernel\n")
+        for s_, e_, n_, st_ in evs:
+            f.write(f"{s_ - evs[0][0]:.1f},{e_ - s_:.1f},{st_},\"{n_[:110]}\"\n")
 t0, t1 = evs[0][0], max(e[1] for e in evs)
 span = t1 - t0
 print(f"kernels {len(evs)}  span {span / 1e3:.2f} ms  kernel-time sum {sum(e[1] - e[0] for e in evs) / 1e3:.2f} ms")

@@ -104,6 +104,21 @@ int rlipv2_msda_proj_backward_f32(const float *value, const int64_t *spatial_sha
                                   int num_heads, int channels, int num_levels, int num_query, int num_point,
                                   float *grad_value, float *grad_proj, void *stream);
 
+/* The same fused prologue for 4-d reference points (the decoders' cross-attention, anchors (cx, cy, w, h) per level,
+ * ms_deform_attn.py:110-112): reference_boxes [batch, num_query, num_levels, 4], not differentiated;
+ *     loc = box[:2] + offset / num_point * box[2:] * 0.5
+ * and in the backward d offset = d loc * 0.5 * box[2:] / num_point. */
+int rlipv2_msda_proj_ref4_forward_f32(const float *value, const int64_t *spatial_shapes,
+                                      const int64_t *level_start_index, const float *reference_boxes,
+                                      const float *proj, int batch, int spatial_size, int num_heads, int channels,
+                                      int num_levels, int num_query, int num_point, float *out, void *stream);
+
+int rlipv2_msda_proj_ref4_backward_f32(const float *value, const int64_t *spatial_shapes,
+                                       const int64_t *level_start_index, const float *reference_boxes,
+                                       const float *proj, const float *grad_out, int batch, int spatial_size,
+                                       int num_heads, int channels, int num_levels, int num_query, int num_point,
+                                       float *grad_value, float *grad_proj, void *stream);
+
 /* Human-readable text for a return code of the functions above (static storage). */
 const char *rlipv2_msda_error_string(int code);
 

@@ -145,7 +145,7 @@ __device__ __forceinline__ float group_sum8(float x) {
 
 // This lane's two points (2*sub, 2*sub+1 - both on level sub/2) of pair (Q, m): locations l4 =
 // (x0, y0, x1, y1) and attention weights a2.  Must be called by all 32 lanes (group shuffles).
-template <bool PROJ>
+template <int PROJ>
 __device__ __forceinline__ void lane_points(const PairSrc &src, const WarpCtx &c, const LevelRow &my,
                                             int Q, int M, int m, bool live, float4 &l4, float2 &a2)
 {
@@ -160,26 +160,39 @@ __device__ __forceinline__ void lane_points(const PairSrc &src, const WarpCtx &c
         return;
     }
     float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float2 lg = make_float2(0.f, 0.f), r = make_float2(0.f, 0.f);
+    float2 lg = make_float2(0.f, 0.f);
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);          // (x, y[, w, h]) of this lane's level
     if (live) {
         const float *row = src.proj + (size_t)Q * (size_t)(M * kFastLP * 3);
         o4 = ldg_f4(row + m * (kFastLP * 2) + c.sub * 4);
         lg = __ldg(reinterpret_cast<const float2 *>(row + M * (kFastLP * 2) + m * kFastLP + c.sub * 2));
-        r = __ldg(reinterpret_cast<const float2 *>(src.ref + ((size_t)Q * kFastL + (c.sub >> 1)) * 2));
+        if (PROJ == 2) {
+            r = ldg_f4(src.ref + ((size_t)Q * kFastL + (c.sub >> 1)) * 4);
+        } else {
+            const float2 r2 = __ldg(reinterpret_cast<const float2 *>(src.ref + ((size_t)Q * kFastL + (c.sub >> 1)) * 2));
+            r.x = r2.x; r.y = r2.y;
+        }
     }
     // softmax over the 16 logits of the pair (F.softmax(.., -1), ms_deform_attn.py:104)
     const float mx = group_max8(fmaxf(lg.x, lg.y));
     const float e0 = expf(lg.x - mx), e1 = expf(lg.y - mx);
     const float sum = group_sum8(e0 + e1);
     a2 = make_float2(__fdiv_rn(e0, sum), __fdiv_rn(e1, sum));
-    // ms_deform_attn.py:106-109: loc = ref[:, :, None, :, None, :] + offsets / (W_l, H_l)
-    const float Wf = (float)my.W, Hf = (float)my.H;
-    l4 = make_float4(r.x + __fdiv_rn(o4.x, Wf), r.y + __fdiv_rn(o4.y, Hf),
-                     r.x + __fdiv_rn(o4.z, Wf), r.y + __fdiv_rn(o4.w, Hf));
+    if (PROJ == 2) {
+        // ms_deform_attn.py:110-112: loc = ref[..., :2] + offsets / n_points * ref[..., 2:] * 0.5
+        // (/4 and *0.5 are exact; the one rounding of the product and the one of the sum are torch's)
+        l4 = make_float4(r.x + __fmul_rn(o4.x * 0.25f, r.z) * 0.5f, r.y + __fmul_rn(o4.y * 0.25f, r.w) * 0.5f,
+                         r.x + __fmul_rn(o4.z * 0.25f, r.z) * 0.5f, r.y + __fmul_rn(o4.w * 0.25f, r.w) * 0.5f);
+    } else {
+        // ms_deform_attn.py:106-109: loc = ref[:, :, None, :, None, :] + offsets / (W_l, H_l)
+        const float Wf = (float)my.W, Hf = (float)my.H;
+        l4 = make_float4(r.x + __fdiv_rn(o4.x, Wf), r.y + __fdiv_rn(o4.y, Hf),
+                         r.x + __fdiv_rn(o4.z, Wf), r.y + __fdiv_rn(o4.w, Hf));
+    }
 }
 
 // forward for the 4 pairs (same head m, queries Q of the 4 lane groups) owned by this warp
-template <int UNROLL, bool PROJ>
+template <int UNROLL, int PROJ>
 __device__ __forceinline__ void fwd_warp_pairs(const float *__restrict__ value, const PairSrc &src,
                                                float *__restrict__ out, const WarpCtx &c,
                                                const LevelRow &my, uint4 *mine, int Q, bool live,
@@ -253,7 +266,7 @@ __device__ __forceinline__ float group_reduce_scatter8(const float (&x)[8], int 
 // backward for the 4 pairs owned by this warp.  The 16 points are walked in two halves of 8 so
 // that the per-point partials (3 x 8 registers) stay small; scaleW/scaleH = (W, H) of the level
 // of point `sub` in each half (cuh:156-158).
-template <bool PROJ>
+template <int PROJ>
 __device__ __forceinline__ void bwd_warp_pairs(const float *__restrict__ value, const PairSrc &src,
                                                const float *__restrict__ grad_out,
                                                float *__restrict__ grad_value,
@@ -323,9 +336,21 @@ __device__ __forceinline__ void bwd_warp_pairs(const float *__restrict__ value, 
         const float gw = group_reduce_scatter8(pw, c.sub);
         const float gh = group_reduce_scatter8(ph, c.sub);
         if (PROJ) {
-            // d loc / d offset = 1 / (W, H): torch forms grad_loc (cuh:156-158) and divides it again
-            const float gx = __fdiv_rn(gw * scaleW[half], scaleW[half]);
-            const float gy = __fdiv_rn(gh * scaleH[half], scaleH[half]);
+            float gx, gy;
+            if (PROJ == 2) {
+                // 4-d reference points: d loc / d offset = (w, h) * 0.5 / n_points; this lane's point half*8 + sub
+                // lies on level half*2 + sub/4 (torch: grad_loc * 0.5, * ref_wh, / 4 - one rounding each side)
+                float2 wh = make_float2(0.f, 0.f);
+                if (live)
+                    wh = __ldg(reinterpret_cast<const float2 *>(
+                        src.ref + ((size_t)Q * kFastL + (half * 2 + (c.sub >> 2))) * 4 + 2));
+                gx = __fmul_rn((gw * scaleW[half]) * 0.5f, wh.x) * 0.25f;
+                gy = __fmul_rn((gh * scaleH[half]) * 0.5f, wh.y) * 0.25f;
+            } else {
+                // d loc / d offset = 1 / (W, H): torch forms grad_loc (cuh:156-158) and divides it again
+                gx = __fdiv_rn(gw * scaleW[half], scaleW[half]);
+                gy = __fdiv_rn(gh * scaleH[half], scaleH[half]);
+            }
             if (half == 0) { ka0 = ga; kx0 = gx; ky0 = gy; } else { ka1 = ga; kx1 = gx; ky1 = gy; }
         } else if (live) {
             const int pt_idx = half * 8 + c.sub;
@@ -365,14 +390,14 @@ __device__ __forceinline__ WarpCtx make_ctx(const LevelRow *lvl_tab, int M) {
 }
 
 // ---- linear schedule --------------------------------------------------------------------------
-template <int UNROLL, int MINB, bool PROJ = false>
+template <int UNROLL, int MINB, int PROJ = 0>
 __global__ void __launch_bounds__(kThreads, MINB)
 msda_fwd_d32_l4p4(const float *__restrict__ value, const int64_t *__restrict__ shapes,
                   const int64_t *__restrict__ lsi, const float *__restrict__ loc,
                   const float *__restrict__ attn, int NQ, int Lq, int S, int M,
                   float *__restrict__ out)
 {
-    // PROJ: `loc` carries proj [NQ, M*48] and `attn` carries ref [NQ, 4, 2]
+    // PROJ: `loc` carries proj [NQ, M*48] and `attn` carries ref [NQ, 4, 2] (PROJ == 1) or [NQ, 4, 4] (PROJ == 2)
     const PairSrc src = PROJ ? PairSrc{nullptr, nullptr, loc, attn} : PairSrc{loc, attn, nullptr, nullptr};
     __shared__ __align__(16) uint4 prep[kWarpsPerCta][4 * kFastLP];
     __shared__ LevelRow lvl_tab[kFastL];
@@ -390,7 +415,7 @@ msda_fwd_d32_l4p4(const float *__restrict__ value, const int64_t *__restrict__ s
         fwd_warp_pairs<UNROLL, PROJ>(value, src, out, c, my, prep[warp], Q, live, n, S, M, m);
 }
 
-template <int MINB, bool PROJ = false>
+template <int MINB, int PROJ = 0>
 __global__ void __launch_bounds__(kThreads, MINB)
 msda_bwd_d32_l4p4(const float *__restrict__ value, const int64_t *__restrict__ shapes,
                   const int64_t *__restrict__ lsi, const float *__restrict__ loc,
@@ -650,8 +675,9 @@ int backward_impl(const T *value, const int64_t *shapes, const int64_t *lsi, con
 // fused-prologue variant: fast path only (fp32, D=32, L=4, P=4, 2-d reference points)
 int proj_forward_impl(const float *value, const int64_t *shapes, const int64_t *lsi, const float *ref,
                       const float *proj, int batch, int spatial_size, int num_heads, int channels,
-                      int num_levels, int num_query, int num_point, float *out, cudaStream_t stream)
+                      int num_levels, int num_query, int num_point, float *out, cudaStream_t stream, int ref_dim = 2)
 {
+    if (ref_dim != 2 && ref_dim != 4) return RLIPV2_MSDA_EINVAL;
     if (bad_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point))
         return RLIPV2_MSDA_EINVAL;
     if (!fast_ok(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point))
@@ -660,12 +686,19 @@ int proj_forward_impl(const float *value, const int64_t *shapes, const int64_t *
     if (NQ == 0) return 0;
     if (!value || !shapes || !lsi || !ref || !proj || !out) return RLIPV2_MSDA_EINVAL;
     const dim3 grid = fast_grid(NQ, num_heads);
-    if (NQ >= 8192)
-        msda_fwd_d32_l4p4<8, 5, true><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, NQ, num_query,
-                                                                    spatial_size, num_heads, out);
-    else
-        msda_fwd_d32_l4p4<16, 3, true><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, NQ, num_query,
+    if (ref_dim == 4) {
+        if (NQ >= 8192)
+            msda_fwd_d32_l4p4<8, 5, 2><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, NQ, num_query,
                                                                      spatial_size, num_heads, out);
+        else
+            msda_fwd_d32_l4p4<16, 3, 2><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, NQ, num_query,
+                                                                      spatial_size, num_heads, out);
+    } else if (NQ >= 8192)
+        msda_fwd_d32_l4p4<8, 5, 1><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, NQ, num_query,
+                                                                 spatial_size, num_heads, out);
+    else
+        msda_fwd_d32_l4p4<16, 3, 1><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, NQ, num_query,
+                                                                  spatial_size, num_heads, out);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
 }
@@ -673,8 +706,9 @@ int proj_forward_impl(const float *value, const int64_t *shapes, const int64_t *
 int proj_backward_impl(const float *value, const int64_t *shapes, const int64_t *lsi, const float *ref,
                        const float *proj, const float *grad_out, int batch, int spatial_size, int num_heads,
                        int channels, int num_levels, int num_query, int num_point, float *grad_value,
-                       float *grad_proj, cudaStream_t stream)
+                       float *grad_proj, cudaStream_t stream, int ref_dim = 2)
 {
+    if (ref_dim != 2 && ref_dim != 4) return RLIPV2_MSDA_EINVAL;
     if (bad_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point))
         return RLIPV2_MSDA_EINVAL;
     if (!fast_ok(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point))
@@ -689,8 +723,12 @@ int proj_backward_impl(const float *value, const int64_t *shapes, const int64_t 
     if (NQ == 0) return 0;
     if (!value || !shapes || !lsi || !ref || !proj || !grad_out || !grad_proj) return RLIPV2_MSDA_EINVAL;
     const dim3 grid = fast_grid(NQ, num_heads);
-    msda_bwd_d32_l4p4<2, true><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, grad_out, NQ, num_query,
-                                                               spatial_size, num_heads, grad_value, grad_proj, nullptr);
+    if (ref_dim == 4)
+        msda_bwd_d32_l4p4<2, 2><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, grad_out, NQ, num_query,
+                                                                spatial_size, num_heads, grad_value, grad_proj, nullptr);
+    else
+        msda_bwd_d32_l4p4<2, 1><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, grad_out, NQ, num_query,
+                                                                spatial_size, num_heads, grad_value, grad_proj, nullptr);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
 }
@@ -718,6 +756,27 @@ int rlipv2_msda_proj_backward_f32(const float *value, const int64_t *spatial_sha
     return proj_backward_impl(value, spatial_shapes, level_start_index, reference_points, proj, grad_out,
                               batch, spatial_size, num_heads, channels, num_levels, num_query, num_point,
                               grad_value, grad_proj, (cudaStream_t)stream);
+}
+
+int rlipv2_msda_proj_ref4_forward_f32(const float *value, const int64_t *spatial_shapes,
+                                      const int64_t *level_start_index, const float *reference_boxes,
+                                      const float *proj, int batch, int spatial_size, int num_heads, int channels,
+                                      int num_levels, int num_query, int num_point, float *out, void *stream)
+{
+    return proj_forward_impl(value, spatial_shapes, level_start_index, reference_boxes, proj, batch,
+                             spatial_size, num_heads, channels, num_levels, num_query, num_point, out,
+                             (cudaStream_t)stream, 4);
+}
+
+int rlipv2_msda_proj_ref4_backward_f32(const float *value, const int64_t *spatial_shapes,
+                                       const int64_t *level_start_index, const float *reference_boxes,
+                                       const float *proj, const float *grad_out, int batch, int spatial_size,
+                                       int num_heads, int channels, int num_levels, int num_query, int num_point,
+                                       float *grad_value, float *grad_proj, void *stream)
+{
+    return proj_backward_impl(value, spatial_shapes, level_start_index, reference_boxes, proj, grad_out,
+                              batch, spatial_size, num_heads, channels, num_levels, num_query, num_point,
+                              grad_value, grad_proj, (cudaStream_t)stream, 4);
 }
 
 int rlipv2_msda_forward_f32(const float *value, const int64_t *spatial_shapes,

@@ -75,6 +75,7 @@ class MSDeformAttnProjFunction(Function):
 
 
 _FUSED_PROLOGUE = os.environ.get("RLIPV2_MSDA_FUSED_PROLOGUE", "1") != "0"     # A/B switch for measurements
+_FUSED_PROLOGUE_REF4 = os.environ.get("RLIPV2_MSDA_FUSED_PROLOGUE_REF4", "1") != "0"   # decoder cross-attention (4-d anchors)
 
 
 def _is_power_of_2(n):
@@ -145,9 +146,11 @@ class MSDeformAttn(nn.Module):
         value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
         if (_FUSED_PROLOGUE and not reference_points.requires_grad and value.is_cuda
                 and input_flatten.dtype == torch.float32 and self.d_model // self.n_heads == 32
-                and reference_points.shape[-1] == 2 and self.n_levels == 4 and self.n_points == 4
+                and reference_points.shape[-1] in ((2, 4) if _FUSED_PROLOGUE_REF4 else (2,))
+                and self.n_levels == 4 and self.n_points == 4
                 and value.numel() < 2 ** 32):
-            # one GEMM for offsets | logits, then the fused-prologue kernels (encoder self-attention)
+            # one GEMM for offsets | logits, then the fused-prologue kernels (encoder self-attention: 2-d reference
+            # points; decoder cross-attention from the second layer on: detached 4-d anchors)
             w = torch.cat((self.sampling_offsets.weight, self.attention_weights.weight), 0)
             b = torch.cat((self.sampling_offsets.bias, self.attention_weights.bias), 0)
             proj = dense.linear(query, w, b)

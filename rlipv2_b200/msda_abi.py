@@ -30,7 +30,10 @@ _lib.rlipv2_msda_backward_f32.argtypes = [_p] * 6 + _DIMS + [_p] * 4
 _lib.rlipv2_msda_backward_f64.argtypes = [_p] * 6 + _DIMS + [_p] * 4
 _lib.rlipv2_msda_proj_forward_f32.argtypes = [_p] * 5 + _DIMS + [_p, _p]
 _lib.rlipv2_msda_proj_backward_f32.argtypes = [_p] * 6 + _DIMS + [_p] * 3
-for _f in ("forward_f32", "forward_f64", "backward_f32", "backward_f64", "proj_forward_f32", "proj_backward_f32"):
+_lib.rlipv2_msda_proj_ref4_forward_f32.argtypes = [_p] * 5 + _DIMS + [_p, _p]
+_lib.rlipv2_msda_proj_ref4_backward_f32.argtypes = [_p] * 6 + _DIMS + [_p] * 3
+for _f in ("forward_f32", "forward_f64", "backward_f32", "backward_f64", "proj_forward_f32", "proj_backward_f32",
+           "proj_ref4_forward_f32", "proj_ref4_backward_f32"):
     getattr(_lib, "rlipv2_msda_" + _f).restype = _i
 _lib.rlipv2_msda_error_string.argtypes = [_i]
 _lib.rlipv2_msda_error_string.restype = ctypes.c_char_p
@@ -42,6 +45,7 @@ if _lib.rlipv2_msda_abi_version() != ABI_VERSION:
 
 EXPORTS = ("rlipv2_msda_forward_f32", "rlipv2_msda_forward_f64", "rlipv2_msda_backward_f32",
            "rlipv2_msda_backward_f64", "rlipv2_msda_proj_forward_f32", "rlipv2_msda_proj_backward_f32",
+           "rlipv2_msda_proj_ref4_forward_f32", "rlipv2_msda_proj_ref4_backward_f32",
            "rlipv2_msda_error_string", "rlipv2_msda_abi_version", "rlipv2_msda_launch_count")
 
 
@@ -88,17 +92,18 @@ def backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight
 
 
 def proj_supported(value, reference_points, n_levels, n_points):
-    """shapes the fused-prologue entry points accept (fp32, D=32, L=4, P=4, 2-d reference points)"""
+    """shapes the fused-prologue entry points accept (fp32, D=32, L=4, P=4, 2-d or 4-d reference points)"""
     return (value.is_cuda and value.dtype == torch.float32 and value.shape[-1] == 32 and n_levels == 4
-            and n_points == 4 and reference_points.shape[-1] == 2 and value.numel() < 2 ** 32)
+            and n_points == 4 and reference_points.shape[-1] in (2, 4) and value.numel() < 2 ** 32)
 
 
 def proj_forward(value, spatial_shapes, level_start_index, reference_points, proj, out):
-    """value [N,S,M,32], reference_points [N,Lq,4,2], proj [N,Lq,M*48] (offsets | logits) -> out [N,Lq,M*32]"""
+    """value [N,S,M,32], reference_points [N,Lq,4,2|4], proj [N,Lq,M*48] (offsets | logits) -> out [N,Lq,M*32]"""
     N, S, M, D = value.shape
     Lq = proj.shape[1]
+    fn = _lib.rlipv2_msda_proj_ref4_forward_f32 if reference_points.shape[-1] == 4 else _lib.rlipv2_msda_proj_forward_f32
     with torch.cuda.device(value.device):
-        code = _lib.rlipv2_msda_proj_forward_f32(
+        code = fn(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), reference_points.data_ptr(),
             proj.data_ptr(), N, S, M, D, 4, Lq, 4, out.data_ptr(), _stream())
     _check(code, "msda_proj_forward")
@@ -107,8 +112,9 @@ def proj_forward(value, spatial_shapes, level_start_index, reference_points, pro
 def proj_backward(value, spatial_shapes, level_start_index, reference_points, proj, grad_output, grad_value, grad_proj):
     N, S, M, D = value.shape
     Lq = proj.shape[1]
+    fn = _lib.rlipv2_msda_proj_ref4_backward_f32 if reference_points.shape[-1] == 4 else _lib.rlipv2_msda_proj_backward_f32
     with torch.cuda.device(value.device):
-        code = _lib.rlipv2_msda_proj_backward_f32(
+        code = fn(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), reference_points.data_ptr(),
             proj.data_ptr(), grad_output.data_ptr(), N, S, M, D, 4, Lq, 4, grad_value.data_ptr(),
             grad_proj.data_ptr(), _stream())

@@ -17,11 +17,14 @@ pytestmark = pytest.mark.gpu
 SHAPES = [(20, 27), (10, 14), (5, 7), (3, 4)]
 
 
-def _inputs(N, Lq, M, shapes, seed, spread=3.0):
+def _inputs(N, Lq, M, shapes, seed, spread=3.0, ref_dim=2):
     g = torch.Generator().manual_seed(seed)
     S = sum(h * w for h, w in shapes)
     value = torch.randn(N, S, M, 32, generator=g)
     ref = torch.rand(N, Lq, 4, 2, generator=g) * 1.2 - 0.1                 # some points fall outside the map
+    if ref_dim == 4:                                                       # anchors (cx, cy, w, h) per level
+        ref = torch.cat((ref, torch.rand(N, Lq, 4, 2, generator=g) * 0.6 + 0.02), -1)
+        spread = 1.5
     proj = torch.cat((torch.randn(N, Lq, M * 32, generator=g) * spread,    # raw offsets, in cells
                       torch.randn(N, Lq, M * 16, generator=g) * 2.0), -1)  # raw logits
     gout = torch.randn(N, Lq, M * 32, generator=g)
@@ -35,20 +38,24 @@ def _module_arithmetic(ref, proj, sh, M):
     N, Lq = proj.shape[:2]
     off = proj[..., :M * 32].reshape(N, Lq, M, 4, 4, 2)
     attn = F.softmax(proj[..., M * 32:].reshape(N, Lq, M, 16), -1).view(N, Lq, M, 4, 4)
+    if ref.shape[-1] == 4:                                                 # ms_deform_attn.py:110-112
+        loc = ref[:, :, None, :, None, :2] + off / 4 * ref[:, :, None, :, None, 2:] * 0.5
+        return loc.contiguous(), attn.contiguous()
     normalizer = torch.stack([sh[..., 1], sh[..., 0]], -1).to(proj.dtype)
     loc = ref[:, :, None, :, None, :] + off / normalizer[None, None, None, :, None, :]
     return loc.contiguous(), attn.contiguous()
 
 
+@pytest.mark.parametrize("ref_dim", [2, 4])
 @pytest.mark.parametrize("N,Lq,M,shapes,seed", [
     (2, 50, 8, SHAPES, 1), (1, 1, 8, SHAPES, 2), (3, 37, 2, SHAPES, 3),
     (2, sum(h * w for h, w in SHAPES), 8, SHAPES, 4),                       # encoder-shaped: Lq == S
     (1, 9000, 8, [(64, 80), (32, 40), (16, 20), (8, 10)], 5),              # NQ >= 8192 kernel variant
 ])
-def test_proj_matches_oracle_and_plain_op(N, Lq, M, shapes, seed):
+def test_proj_matches_oracle_and_plain_op(N, Lq, M, shapes, seed, ref_dim):
     from rlipv2_b200 import msda_abi
     from rlipv2_b200.dropin import MultiScaleDeformableAttention as MSDA
-    value, sh, lsi, ref, proj, gout = _inputs(N, Lq, M, shapes, seed)
+    value, sh, lsi, ref, proj, gout = _inputs(N, Lq, M, shapes, seed, ref_dim=ref_dim)
     dv = lambda t: t.cuda().contiguous()
     value_d, sh_d, lsi_d, ref_d, proj_d, gout_d = map(dv, (value, sh, lsi, ref, proj, gout))
     out = torch.empty(N, Lq, M * 32, device="cuda")
@@ -83,8 +90,10 @@ def test_proj_matches_oracle_and_plain_op(N, Lq, M, shapes, seed):
         np.testing.assert_allclose(gp.cpu().numpy(), c(proj_c.grad), rtol=1e-3, atol=2e-4 * scale(proj_r.grad))
 
 
-def test_module_fused_prologue_equals_unfused(monkeypatch):
-    """MSDeformAttn.forward with 2-d reference points: fused-prologue path == reference arithmetic path"""
+@pytest.mark.parametrize("ref_dim", [2, 4])
+def test_module_fused_prologue_equals_unfused(monkeypatch, ref_dim):
+    """MSDeformAttn.forward with 2-d reference points (encoder) and detached 4-d anchors (decoder layers >= 1):
+    fused-prologue path == reference arithmetic path"""
     import rlipv2_b200.ms_deform_attn as mod
     from rlipv2_b200 import dense
     dense.set_matmul_precision("fp32")
@@ -96,6 +105,8 @@ def test_module_fused_prologue_equals_unfused(monkeypatch):
         m.attention_weights.weight.normal_(0, 0.05)
     src = torch.randn(2, S, 256, device="cuda")
     refp = torch.rand(2, S, 4, 2, device="cuda")
+    if ref_dim == 4:
+        refp = torch.cat((refp, torch.rand(2, S, 4, 2, device="cuda") * 0.5 + 0.02), -1)
     sh = torch.as_tensor(SHAPES, dtype=torch.long, device="cuda")
     lsi = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
     mask = torch.zeros(2, S, dtype=torch.bool, device="cuda")

@@ -31,6 +31,11 @@
 namespace {
 
 std::atomic<unsigned long long> g_launches{0};
+// small-grid tuning of the forward linear (rlipv2_dense_set_small_mode): 0 = always 128x128 tiles, 3 stages, 2 CTAs/SM;
+// 1 = grids of at most one CTA per SM run a 6-stage ring (1 CTA/SM); 2 = additionally 128x64 tiles with an 8-stage ring
+// while that keeps the grid within one CTA per SM
+std::atomic<int> g_small_mode{1};
+constexpr int kNumSMs = 148;
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 32;                 // 32 fp32 = 128 bytes = one swizzle-128B row
@@ -597,19 +602,37 @@ int rlipv2_dense_linear_tf32_rowmask(const float *x, const float *w, const float
     if (!rlipv2_dense_linear_tf32_supported(M, N, K)) return RLIPV2_DENSE_ESHAPE;
     if (!x || !w || !y) return RLIPV2_DENSE_EINVAL;
     if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y | (uintptr_t)bias) & 15) return RLIPV2_DENSE_EALIGN;
+    if (act != RLIPV2_DENSE_ACT_NONE && act != RLIPV2_DENSE_ACT_RELU && act != RLIPV2_DENSE_ACT_GELU) return RLIPV2_DENSE_EINVAL;
+    // Tile / pipeline choice.  A CTA that has its SM to itself is bound by the latency of its own TMA loads: a 3-stage
+    // ring keeps 96 KB in flight (~1 us of L2 latency per 96 KB, i.e. ~8 us for the 768 KB a K = 768 tile streams).
+    // Grids of at most one CTA per SM (the ALIF / RobertaLayer / decoder linears: 300-1300 rows) therefore run a
+    // 6-stage ring, and - while the grid still fits one CTA per SM - 128x64 tiles, which put twice as many SMs to work.
+    const long long ctas128 = (long long)(N / 128) * ((M + kBlockM - 1) / kBlockM);
+    const int mode = g_small_mode.load(std::memory_order_relaxed);
+    int cfg = 0;
+    if (mode >= 1 && ctas128 <= kNumSMs) cfg = 1;
+    if (mode >= 2 && 2 * ctas128 <= kNumSMs) cfg = 2;
     CUtensorMap ta, tb;
     int rc = make_map(&ta, x, (uint64_t)M, (uint64_t)K, kBlockM);
     if (rc) return rc;
-    rc = make_map(&tb, w, (uint64_t)N, (uint64_t)K, 128);
+    rc = make_map(&tb, w, (uint64_t)N, (uint64_t)K, cfg == 2 ? 64 : 128);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    switch (act) {
-        case RLIPV2_DENSE_ACT_NONE: return launch<128, 3, RLIPV2_DENSE_ACT_NONE>(ta, tb, bias, rowmask, y, M, N, K, s);
-        case RLIPV2_DENSE_ACT_RELU: return launch<128, 3, RLIPV2_DENSE_ACT_RELU>(ta, tb, bias, rowmask, y, M, N, K, s);
-        case RLIPV2_DENSE_ACT_GELU: return launch<128, 3, RLIPV2_DENSE_ACT_GELU>(ta, tb, bias, rowmask, y, M, N, K, s);
-        default: return RLIPV2_DENSE_EINVAL;
+#define RLIPV2_DISPATCH_ACT(BN, ST)                                                                              \
+    switch (act) {                                                                                               \
+        case RLIPV2_DENSE_ACT_NONE: return launch<BN, ST, RLIPV2_DENSE_ACT_NONE>(ta, tb, bias, rowmask, y, M, N, K, s); \
+        case RLIPV2_DENSE_ACT_RELU: return launch<BN, ST, RLIPV2_DENSE_ACT_RELU>(ta, tb, bias, rowmask, y, M, N, K, s); \
+        default: return launch<BN, ST, RLIPV2_DENSE_ACT_GELU>(ta, tb, bias, rowmask, y, M, N, K, s);               \
     }
+    if (cfg == 2) { RLIPV2_DISPATCH_ACT(64, 8) }
+    if (cfg == 1) { RLIPV2_DISPATCH_ACT(128, 6) }
+    RLIPV2_DISPATCH_ACT(128, 3)
+#undef RLIPV2_DISPATCH_ACT
 }
+
+void rlipv2_dense_set_small_mode(int mode) { g_small_mode.store(mode < 0 ? 0 : (mode > 2 ? 2 : mode), std::memory_order_relaxed); }
+
+int rlipv2_dense_get_small_mode(void) { return g_small_mode.load(std::memory_order_relaxed); }
 
 int rlipv2_dense_linear_tf32(const float *x, const float *w, const float *bias, float *y, int M, int N, int K,
                              int act, void *stream)

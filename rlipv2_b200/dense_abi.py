@@ -24,10 +24,25 @@ _lib.rlipv2_dense_dgrad_tf32.restype = _i
 _lib.rlipv2_dense_error_string.argtypes = [_i]
 _lib.rlipv2_dense_error_string.restype = ctypes.c_char_p
 _lib.rlipv2_dense_launch_count.restype = ctypes.c_ulonglong
+_lib.rlipv2_dense_set_small_mode.argtypes = [_i]
+_lib.rlipv2_dense_set_small_mode.restype = None
+_lib.rlipv2_dense_get_small_mode.restype = _i
+if os.environ.get("RLIPV2_DENSE_SMALL_MODE"):                      # A/B switch for measurements
+    _lib.rlipv2_dense_set_small_mode(int(os.environ["RLIPV2_DENSE_SMALL_MODE"]))
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 EXPORTS = ("rlipv2_dense_linear_tf32", "rlipv2_dense_linear_tf32_rowmask", "rlipv2_dense_linear_tf32_supported", "rlipv2_dense_wgrad_tf32",
-           "rlipv2_dense_dgrad_tf32", "rlipv2_dense_error_string", "rlipv2_dense_launch_count")
+           "rlipv2_dense_dgrad_tf32", "rlipv2_dense_error_string", "rlipv2_dense_launch_count",
+           "rlipv2_dense_set_small_mode", "rlipv2_dense_get_small_mode")
+
+
+def set_small_mode(mode):
+    """tile / pipeline choice of the forward linear for grids of at most one CTA per SM (include/rlipv2_dense.h)"""
+    _lib.rlipv2_dense_set_small_mode(int(mode))
+
+
+def small_mode():
+    return int(_lib.rlipv2_dense_get_small_mode())
 
 
 def library_path():

@@ -41,6 +41,31 @@ def test_linear_tf32_matches_fp64(M, N, K, act):
     assert bool(((y2.double() - ref2).abs() <= 1.5e-3 * bound2 + 1e-5).all())
 
 
+@pytest.mark.parametrize("M,N,K", [(546, 2048, 256), (512, 768, 3072), (300, 256, 512), (37, 128, 256), (1280, 768, 768),
+                                   (600, 256, 2048)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_linear_small_grid_modes_are_bit_identical(M, N, K, act):
+    """the small-grid tile / pipeline choices (rlipv2_dense_set_small_mode: 3-stage 128x128, 6-stage 128x128, 8-stage
+    128x64) issue the same MMAs in the same K order for every output element: results must be bit-identical"""
+    from rlipv2_b200 import dense_abi
+    g = torch.Generator(device="cuda").manual_seed(7 * M + N + K + act)
+    x = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) * K ** -0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    keep = dense_abi.small_mode()
+    try:
+        ys = []
+        for mode in (0, 1, 2):
+            dense_abi.set_small_mode(mode)
+            assert dense_abi.small_mode() == mode
+            ys.append(dense_abi.linear_tf32(x, w, b, act))
+    finally:
+        dense_abi.set_small_mode(keep)
+    ref, bound = _ref(x, w, b, act)
+    assert bool(((ys[0].double() - ref).abs() <= 1.5e-3 * bound + 1e-5).all())
+    assert torch.equal(ys[0], ys[1]) and torch.equal(ys[0], ys[2])
+
+
 def test_unsupported_shapes_are_reported_not_silently_rerouted():
     from rlipv2_b200 import dense_abi
     assert not dense_abi.supported(64, 100, 256)

@@ -15,13 +15,34 @@ SHAPES = [  # (name, M, N, K, act)
     ("enc value_proj", 44446, 256, 256, 0), ("enc attn_weights", 44446, 128, 256, 0),
     ("ALIF v_proj", 546, 2048, 256, 0), ("ALIF l_proj", 512, 2048, 768, 0), ("ALIF out_l", 512, 768, 2048, 0),
     ("Roberta qkv", 512, 768, 768, 0), ("Roberta FFN up", 512, 3072, 768, 2), ("Roberta FFN down", 512, 768, 3072, 0),
+    ("text tower qkv (256 labels x 5 tok)", 1280, 768, 768, 0), ("text tower FFN up", 1280, 3072, 768, 2),
+    ("text tower FFN down", 1280, 768, 3072, 0), ("decoder linear (2 x 300 q)", 600, 256, 256, 0),
+    ("decoder FFN up", 600, 2048, 256, 1), ("decoder FFN down", 600, 256, 2048, 0),
 ]
 
 
 def timeit(fns, iters):
+    """small kernels (a few us) are shorter than the python/ctypes launch path: time them as a CUDA-graph replay of
+    `iters` back-to-back launches (what the train step does), big ones eagerly"""
     for f in fns[:3]:
         f()
     torch.cuda.synchronize()
+    if GRAPH:
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=st):
+                for i in range(iters):
+                    fns[i % len(fns)]()
+        gr.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            gr.replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / (3 * iters) * 1e-3
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for i in range(iters):
@@ -31,6 +52,7 @@ def timeit(fns, iters):
     return a.elapsed_time(b) / iters * 1e-3
 
 
+GRAPH = False
 only = sys.argv[1] if len(sys.argv) > 1 else None
 for name, M, N, K, act in SHAPES:
     if only and only not in name:
@@ -48,7 +70,15 @@ for name, M, N, K, act in SHAPES:
     else:
         ref = [lambda x=x: F.linear(x, w, b) for x in xs]
     iters = 50 if M > 10000 else 200
-    t_o, t_r = timeit(ours, iters), timeit(ref, iters)
+    GRAPH = M <= 10000
     fl = 2.0 * M * N * K
-    print(json.dumps({"shape": name, "M": M, "N": N, "K": K, "act": act, "ours_us": t_o * 1e6, "cublas_us": t_r * 1e6,
-                      "ours_TFLOPs": fl / t_o / 1e12, "cublas_TFLOPs": fl / t_r / 1e12, "ours_GBs": bytes_ / t_o / 1e9}))
+    rec = {"shape": name, "M": M, "N": N, "K": K, "act": act}
+    keep = dense_abi.small_mode()
+    for mode in ((0, 1, 2) if (N // 128) * ((M + 127) // 128) <= 148 else (keep,)):      # small grids: all tile / ring choices
+        dense_abi.set_small_mode(mode)
+        rec[f"ours_mode{mode}_us"] = timeit(ours, iters) * 1e6
+    dense_abi.set_small_mode(keep)
+    t_o, t_r = timeit(ours, iters), timeit(ref, iters)
+    rec.update({"ours_us": t_o * 1e6, "cublas_us": t_r * 1e6, "ours_TFLOPs": fl / t_o / 1e12,
+                "cublas_TFLOPs": fl / t_r / 1e12, "ours_GBs": bytes_ / t_o / 1e9, "default_mode": keep})
+    print(json.dumps(rec), flush=True)

@@ -60,9 +60,9 @@ int rlipv2_dense_linear_tf32_rowmask(const float *x, const float *w, const float
                                      float *y, int M, int N, int K, int act, void *stream);
 
 /* Tuning knob of rlipv2_dense_linear_tf32* for grids that leave SMs idle (M of a few hundred rows: the ALIF,
- * RobertaLayer and decoder linears).  0: always 128x128 tiles with a 3-stage TMA ring (2 CTAs/SM); 1 (default): grids of
- * at most one CTA per SM use a 6-stage ring; 2: additionally 128x64 tiles with an 8-stage ring while the grid still fits
- * one CTA per SM.  Results are identical in every mode (same products, same fp32 accumulation order per output). */
+ * RobertaLayer and decoder linears).  0: always 128x128 tiles with a 3-stage TMA ring (2 CTAs/SM); 1: grids of
+ * at most one CTA per SM use a 6-stage ring; 2 (default): additionally 128x64 tiles with an 8-stage ring while the grid
+ * still fits one CTA per SM.  Results are identical in every mode (same products, same fp32 accumulation order per output). */
 void rlipv2_dense_set_small_mode(int mode);
 int rlipv2_dense_get_small_mode(void);
 

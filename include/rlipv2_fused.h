@@ -66,6 +66,13 @@ int rlipv2_adamw_f32(float *param, const float *grad, float *exp_avg, float *exp
                      double lr, double beta1, double beta2, double eps, double weight_decay, const float *step,
                      void *stream);
 
+/* The same step on grad * (*grad_scale): `grad_scale` is a device float (or NULL = 1) holding the coefficient of
+ * torch.nn.utils.clip_grad_norm_ (/root/reference/engine.py:165-166), times 1 / world_size when `grad` holds the
+ * rank SUM of an all-reduce - the scaling pass over the gradient buffer is folded into the optimizer's read. */
+int rlipv2_adamw_scaled_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n,
+                            double lr, double beta1, double beta2, double eps, double weight_decay,
+                            const float *step, const float *grad_scale, void *stream);
+
 /* Gather scattered fp32 arrays into one flat buffer: for chunk c, copy table[3c+2] elements from the device
  * address table[3c] to dst + table[3c+1] (`table` is a device array of n_chunks x 3 int64; one CTA per chunk,
  * keep chunks <= 64K elements).  Used once per step to collect the gradient tensors autograd produced

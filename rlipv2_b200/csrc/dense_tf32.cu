@@ -34,7 +34,7 @@ std::atomic<unsigned long long> g_launches{0};
 // small-grid tuning of the forward linear (rlipv2_dense_set_small_mode): 0 = always 128x128 tiles, 3 stages, 2 CTAs/SM;
 // 1 = grids of at most one CTA per SM run a 6-stage ring (1 CTA/SM); 2 = additionally 128x64 tiles with an 8-stage ring
 // while that keeps the grid within one CTA per SM
-std::atomic<int> g_small_mode{1};
+std::atomic<int> g_small_mode{2};
 constexpr int kNumSMs = 148;
 
 constexpr int kBlockM = 128;

@@ -176,16 +176,20 @@ relu_bwd_colsum_kernel(const float *__restrict__ g, const float *__restrict__ y,
 __global__ void __launch_bounds__(256)
 adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
              long long n4, long long n, float lr, float b1, float b2, float omb1, float omb2, float eps, float wd,
-             const float *__restrict__ step)
+             const float *__restrict__ step, const float *__restrict__ grad_scale)
 {
     // omb1 / omb2 = 1 - beta computed in double on the host (1.f - 0.999f is 1.3e-5 off)
     const float t = *step;
+    // grad_scale: the clip_grad_norm_ coefficient (and 1 / world for the rank mean) applied to the gradient as it is
+    // read, instead of a separate pass over the gradient buffer
+    const float gs = grad_scale ? *grad_scale : 1.f;
     const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
     const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2), decay = 1.f - lr * wd;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 pp = reinterpret_cast<float4 *>(p)[i], mm = reinterpret_cast<float4 *>(m)[i], vv = reinterpret_cast<float4 *>(v)[i];
-        const float4 gg = reinterpret_cast<const float4 *>(g)[i];
+        float4 gg = reinterpret_cast<const float4 *>(g)[i];
+        gg.x *= gs; gg.y *= gs; gg.z *= gs; gg.w *= gs;
 #define RLIPV2_ADAMW_LANE(c)                                                         \
         pp.c *= decay;                                                               \
         mm.c = b1 * mm.c + omb1 * gg.c;                                              \
@@ -200,7 +204,7 @@ adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restri
     // tail (n not a multiple of 4)
     for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float pp = p[i] * decay;
-        const float gg = g[i];
+        const float gg = g[i] * gs;
         const float mm = b1 * m[i] + omb1 * gg, vv = b2 * v[i] + omb2 * gg * gg;
         pp -= step_size * mm / (sqrtf(vv) * inv_sqrt_bc2 + eps);
         p[i] = pp; m[i] = mm; v[i] = vv;
@@ -392,8 +396,9 @@ int rlipv2_rowmask_bwd_colsum_f32(const float *g, const unsigned char *rowmask, 
     return rlipv2_rowmask_bwd_colsum_acc_f32(g, rowmask, gmasked, colsum, M, N, 0, stream);
 }
 
-int rlipv2_adamw_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, double lr,
-                     double beta1, double beta2, double eps, double weight_decay, const float *step, void *stream)
+int rlipv2_adamw_scaled_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, double lr,
+                            double beta1, double beta2, double eps, double weight_decay, const float *step,
+                            const float *grad_scale, void *stream)
 {
     if (n == 0) return 0;
     if (!param || !grad || !exp_avg || !exp_avg_sq || !step || n < 0) return RLIPV2_FUSED_EINVAL;
@@ -404,8 +409,16 @@ int rlipv2_adamw_f32(float *param, const float *grad, float *exp_avg, float *exp
     if (blocks < 1) blocks = 1;
     adamw_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n4, n, (float)lr,
                                                                 (float)beta1, (float)beta2, (float)(1.0 - beta1),
-                                                                (float)(1.0 - beta2), (float)eps, (float)weight_decay, step);
+                                                                (float)(1.0 - beta2), (float)eps, (float)weight_decay, step,
+                                                                grad_scale);
     return done();
+}
+
+int rlipv2_adamw_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, double lr,
+                     double beta1, double beta2, double eps, double weight_decay, const float *step, void *stream)
+{
+    return rlipv2_adamw_scaled_f32(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, nullptr,
+                                   stream);
 }
 
 int rlipv2_gather_chunks_f32(const long long *table, int n_chunks, float *dst, void *stream)

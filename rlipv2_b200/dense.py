@@ -26,7 +26,8 @@ _USE_FUSED = True        # fused LayerNorm / bias-gradient kernels (exact fp32 a
 _OWN_BWD = os.environ.get("RLIPV2_OWN_BWD", "0") == "1"
 # 'hybrid' FFN backward: only the down-projection's input gradient (ReLU gate + bias gradient fused in its epilogue) and
 # the two split-K weight gradients run on the tcgen05 kernels; the plain input gradient stays on cuBLAS' 256x256 2-SM kernel
-_FFN_BWD = os.environ.get("RLIPV2_FFN_BWD", "cublas")
+# (measured on B200, r01s4a: 32.79 vs 33.40 ms/step -> the default; RLIPV2_FFN_BWD=cublas restores the torch backward)
+_FFN_BWD = os.environ.get("RLIPV2_FFN_BWD", "hybrid")
 _OWN_WGRAD = os.environ.get("RLIPV2_OWN_WGRAD", "1") != "0"
 _OWN_BWD_MIN_ROWS = int(os.environ.get("RLIPV2_OWN_BWD_MIN_ROWS", "4096"))
 

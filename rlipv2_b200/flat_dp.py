@@ -61,6 +61,21 @@ class FlatParams:
             dist.all_reduce(self.flat_grad)
             self.flat_grad.div_(w)
 
+    def allreduce_sum_(self):
+        """the rank SUM of the gradients; `clip_scale` folds the 1 / world of the mean into the optimizer's read"""
+        if world_size() > 1:
+            dist.all_reduce(self.flat_grad)
+
+    def clip_scale(self, max_norm):
+        """1-element tensor s such that `flat_grad * s` is what `allreduce_mean_()` + `clip_(max_norm)` would have left
+        in the buffer, given that `flat_grad` holds the rank SUM: s = clip coefficient of the mean gradient / world.
+        Nothing is written to the gradient buffer (the optimizer kernel applies s as it reads the gradient)."""
+        w = float(world_size())
+        if max_norm > 0:
+            coef = torch.clamp(max_norm / (self.flat_grad.norm() / w + 1e-6), max=1.0)
+            return (coef / w).reshape(1)
+        return torch.full((1,), 1.0 / w, device=self.flat_grad.device)
+
     def clip_(self, max_norm):
         """`clip_grad_norm_(parameters, max_norm)` over the used parameters == one norm + one scale of the flat
         buffer (padding elements are zero); no host sync."""

@@ -49,10 +49,16 @@ def _worker(rank, port, q):
         lo = rank * 4
         flat.zero_grad()
         torch.nn.functional.mse_loss(model(x[lo:lo + 4]), y[lo:lo + 4]).backward()
+        local = flat.flat_grad.clone()
         flat.allreduce_mean_()
         g_after_reduce = flat.flat_grad.clone()
         flat.clip_(0.1)
         g_after_clip = flat.flat_grad.clone()
+        # the fused variant of the graphed step: rank SUM in the buffer, clip coefficient / world applied by the optimizer
+        flat.flat_grad.copy_(local)
+        flat.allreduce_sum_()
+        g_scaled = flat.flat_grad * flat.clip_scale(0.1)
+        flat.flat_grad.copy_(g_after_clip)
         opt = torch.optim.AdamW([{"params": pl, "lr": lr} for pl, lr in _groups(model)], weight_decay=1e-4)
         opt.step()                                     # updates the views == the flat buffer
         # ---- criterion normalisation over ranks
@@ -63,7 +69,7 @@ def _worker(rank, port, q):
         keys = ["loss_sub_bbox", "loss_sub_giou", "loss_sub_bbox_0", "loss_sub_giou_1"]
         vec = torch.stack([losses[k].detach().reshape(()) for k in keys])
         dist.all_reduce(vec)
-        q.put((rank, g_after_reduce, g_after_clip, flat.flat_param.clone(), flat.group_ranges, vec / WORLD))
+        q.put((rank, g_after_reduce, g_after_clip, flat.flat_param.clone(), flat.group_ranges, vec / WORLD, g_scaled))
     finally:
         dist.destroy_process_group()
 
@@ -107,6 +113,7 @@ def test_two_gloo_ranks():
     g_clip = flatten([p.grad for p in ref.parameters()], ranges)
     for r in res:
         torch.testing.assert_close(r[2], g_clip, rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(r[6], g_clip, rtol=1e-5, atol=1e-7)      # sum + clip_scale == mean + clip_
     opt = torch.optim.AdamW([{"params": pl, "lr": lr} for pl, lr in _groups(ref)], weight_decay=1e-4)
     opt.step()
     p_ref = flatten([p.data for p in ref.parameters()], ranges)

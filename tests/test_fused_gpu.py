@@ -63,3 +63,24 @@ def test_flat_adamw_matches_torch():
     # moments are O(1) sums of O(1) terms that can cancel: a few ulps of 1.0 (1.2e-7) absolute, fma vs mul+add
     torch.testing.assert_close(m, st["exp_avg"], rtol=1e-5, atol=5e-7)
     torch.testing.assert_close(v, st["exp_avg_sq"], rtol=1e-5, atol=1e-9)
+
+
+def test_flat_adamw_grad_scale_equals_prescaled_gradient():
+    """rlipv2_adamw_scaled_f32: the clip coefficient / rank-mean factor applied inside the optimizer's gradient read"""
+    from rlipv2_b200 import fused_abi
+    n = 300_001
+    torch.manual_seed(1)
+    p0 = torch.randn(n, device="cuda")
+    grad = torch.randn(n, device="cuda") * 3
+    scale = torch.tensor([0.0371], device="cuda")
+    step = torch.ones((), device="cuda")
+    res = []
+    for fused in (True, False):
+        p, m, v = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+        if fused:
+            fused_abi.adamw(p, grad, m, v, 1e-3, 0.9, 0.999, 1e-8, 1e-4, step, grad_scale=scale)
+        else:
+            fused_abi.adamw(p, grad * scale, m, v, 1e-3, 0.9, 0.999, 1e-8, 1e-4, step)
+        res.append((p, m, v))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)          # the same fp32 product, formed in the kernel instead of by torch

@@ -75,6 +75,8 @@ class SetCriterionHOI(nn.Module):
         if giou_verb_label:
             assert verb_loss_type == "focal" and obj_loss_type == "cross_entropy"
         self.pseudo_verb = pseudo_verb
+        # independent loss terms on parallel streams (RLIPV2_PARALLEL_LOSSES=0: one chain, for A/B measurements)
+        self.parallel_losses = __import__("os").environ.get("RLIPV2_PARALLEL_LOSSES", "1") != "0"
 
     # ---- helpers ----------------------------------------------------------------------------------
     @staticmethod
@@ -312,25 +314,32 @@ class SetCriterionHOI(nn.Module):
             nll = F.cross_entropy(logits.reshape(-1, C), flat, w, reduction="none")      # = w[y] * nll
             return per_layer(nll) / per_layer(w[flat]), matched
 
-        if "obj_labels" in self.losses:
+        # The loss terms are independent chains of small kernels (a few hundred launches forward + backward, each a few
+        # microseconds): on the GPU every chain runs on its own stream (fork here, join below; autograd replays each
+        # chain's backward on the same stream), so the step pays for the longest chain instead of their sum.
+        br = _Branches(device, 5, self.parallel_losses)
+
+        def b_obj():
             loss_obj, matched_obj = ce(obj_logits, torch.cat([t["obj_labels"] for t in targets]))
             i0 = (c["batch"][:K], I_all[:K])                                            # layer 0 = final layer
             out["obj_class_error"] = [100 - accuracy(layers[0]["pred_obj_logits"][i0], matched_obj[:K])[0]]
-            if self.subject_class:
-                sub_logits = torch.cat([l["pred_sub_logits"] for l in layers], 0)
-                loss_sub, matched_sub = ce(sub_logits, torch.cat([t["sub_labels"] for t in targets]))
-                loss_obj = loss_obj + loss_sub
-                out["sub_class_error"] = [100 - accuracy(layers[0]["pred_sub_logits"][i0], matched_sub[:K])[0]]
-            out["loss_obj_ce"] = loss_obj
+            out["_loss_obj"] = loss_obj
+
+        def b_sub():
+            sub_logits = torch.cat([l["pred_sub_logits"] for l in layers], 0)
+            loss_sub, matched_sub = ce(sub_logits, torch.cat([t["sub_labels"] for t in targets]))
+            i0 = (c["batch"][:K], I_all[:K])
+            out["sub_class_error"] = [100 - accuracy(layers[0]["pred_sub_logits"][i0], matched_sub[:K])[0]]
+            out["_loss_sub"] = loss_sub
 
         # -- obj_cardinality (hoi.py:3909-3923)
-        if "obj_cardinality" in self.losses:
+        def b_card():
             with torch.no_grad():
                 card_pred = (obj_logits.argmax(-1) != obj_logits.shape[-1] - 1).sum(1)
                 out["obj_cardinality_error"] = (card_pred.float() - c["tgt_len"]).abs().view(n, bs).mean(1)
 
         # -- verb_labels (hoi.py:3925-4028, 4453-4495)
-        if "verb_labels" in self.losses:
+        def b_verb():
             src_logits = torch.cat([l["pred_verb_logits"] for l in layers], 0)
             labels = torch.cat([t["verb_labels"] for t in targets])[tcol]
             if self.giou_verb_label:
@@ -361,7 +370,7 @@ class SetCriterionHOI(nn.Module):
                     out["loss_verb_ce"] = torch.where(num_pos == 0, -neg, -(pos + neg) / num_pos.clamp(min=1))
 
         # -- sub_obj_boxes (hoi.py:4162-4193)
-        if "sub_obj_boxes" in self.losses:
+        def b_box():
             src_sub = torch.cat([l["pred_sub_boxes"] for l in layers], 0)[idx]           # [n*K, 4]
             src_obj = torch.cat([l["pred_obj_boxes"] for l in layers], 0)[idx]
             if K == 0:
@@ -378,6 +387,24 @@ class SetCriterionHOI(nn.Module):
                 out["loss_obj_bbox"] = per_layer((src_obj - tgt_obj).abs() * exist.unsqueeze(1)) / n_exist
                 out["loss_sub_giou"] = per_layer(giou_sub) / num_interactions
                 out["loss_obj_giou"] = per_layer(giou_obj * exist) / n_exist
+
+        if "verb_labels" in self.losses:
+            br.run(b_verb)
+        if "sub_obj_boxes" in self.losses:
+            br.run(b_box)
+        if "obj_labels" in self.losses:
+            br.run(b_obj)
+            if self.subject_class:
+                br.run(b_sub)
+        if "obj_cardinality" in self.losses:
+            br.run(b_card)
+        br.join()
+        for v in out.values():
+            for t in (v if isinstance(v, (list, tuple)) else (v,)):
+                br.hand_over(t)
+        if "_loss_obj" in out:                               # hoi.py:3696-3828: subject + object CE summed
+            loss_obj = out.pop("_loss_obj")
+            out["loss_obj_ce"] = loss_obj + out.pop("_loss_sub") if "_loss_sub" in out else loss_obj
 
         # reference key order: per layer, losses in self.losses order (hoi.py:4745-4764)
         order = {"obj_labels": ("loss_obj_ce", "obj_class_error", "sub_class_error"),
@@ -402,6 +429,42 @@ class SetCriterionHOI(nn.Module):
                                             for k in keys]).to(device)
             losses.weighted_total = (torch.stack([out[k] for k in keys]) * cache[wkey]).sum()
         return losses
+
+
+_BRANCH_STREAMS = {}
+
+
+class _Branches:
+    """fork / join of independent kernel chains over side streams (a no-op on CPU or when disabled)"""
+
+    def __init__(self, device, n, enabled):
+        self.on = bool(enabled) and device.type == "cuda"
+        self.used = 0
+        if self.on:
+            self.cur = torch.cuda.current_stream(device)
+            pool = _BRANCH_STREAMS.setdefault(str(device), [])
+            while len(pool) < n:
+                pool.append(torch.cuda.Stream(device))
+            self.streams = pool[:n]
+
+    def run(self, fn):
+        if not self.on:
+            return fn()
+        st = self.streams[self.used]
+        self.used += 1
+        st.wait_stream(self.cur)
+        with torch.cuda.stream(st):
+            return fn()
+
+    def join(self):
+        if self.on:
+            for st in self.streams[:self.used]:
+                self.cur.wait_stream(st)
+
+    def hand_over(self, t):
+        """a tensor produced on a side stream that the caller's stream will read (caching-allocator bookkeeping)"""
+        if self.on and torch.is_tensor(t) and t.is_cuda:
+            t.record_stream(self.cur)
 
 
 class LossDict(dict):

@@ -21,6 +21,7 @@ from .parseda_transformer import MLP
 
 
 _TEXT_STREAM = os.environ.get("RLIPV2_TEXT_STREAM", "1") != "0"      # A/B switch for measurements
+_STACKED_HEADS = os.environ.get("RLIPV2_STACKED_HEADS", "1") != "0"  # label-text heads of all decoder levels in one pass
 
 
 def _get_clones(module, n):
@@ -147,7 +148,8 @@ class RLIP_ParSeDA(nn.Module):
         self.transformer.ho_decoder.refined_boxes = None
         if not (self.with_box_refine and refined is not None and len(refined) == hs_h.shape[0]):
             refined = None
-        for lvl in range(hs_h.shape[0]):
+        n_lvl = hs_h.shape[0]
+        for lvl in range(n_lvl):
             if refined is not None:
                 sub_boxes.append(refined[lvl][0])
                 obj_boxes.append(refined[lvl][1])
@@ -155,15 +157,29 @@ class RLIP_ParSeDA(nn.Module):
                 sub_ref, obj_ref = init_reference if lvl == 0 else inter_references[lvl - 1]
                 sub_boxes.append((self.sub_bbox_embed[lvl](hs_h[lvl]) + inverse_sigmoid(sub_ref)).sigmoid())
                 obj_boxes.append((self.obj_bbox_embed[lvl](hs_o[lvl]) + inverse_sigmoid(obj_ref)).sigmoid())
-            text_memory = F.normalize(text_dec[lvl].transpose(0, 1), p=2, dim=-1)
+        if _STACKED_HEADS and torch.is_tensor(text_dec) and text_dec.dim() == 4 and text_dec.shape[0] == n_lvl:
+            # the label-text heads of all decoder levels in one pass (hoi.py:2145-2163 evaluates them level by level):
+            # one normalisation, one projection GEMM, one batched contraction per head instead of n_lvl of each
+            text_memory = F.normalize(text_dec.transpose(1, 2), p=2, dim=-1)             # [L, bs, Tl, C]
             proj_text = dense.linear(text_memory / 2.0, self.projection_text.weight, self.projection_text.bias)
-            assert max_obj + max_pred == proj_text.shape[1]
-            obj_text = proj_text[:, :max_obj].transpose(1, 2)                      # [bs, 256, n_obj]
-            pred_text = proj_text[:, max_obj:max_obj + max_pred].transpose(1, 2)
-            obj_cls.append(torch.matmul(hs_o[lvl] + self.bias_obj_a, obj_text) + self.bias_c)
-            verb_cls.append(torch.matmul(hs_verb[lvl] + self.bias_pred_a, pred_text) + self.bias_c)
+            assert max_obj + max_pred == proj_text.shape[2]
+            obj_text = proj_text[:, :, :max_obj].transpose(2, 3)                          # [L, bs, 256, n_obj]
+            pred_text = proj_text[:, :, max_obj:max_obj + max_pred].transpose(2, 3)
+            obj_cls = list((torch.matmul(hs_o + self.bias_obj_a, obj_text) + self.bias_c).unbind(0))
+            verb_cls = list((torch.matmul(hs_verb + self.bias_pred_a, pred_text) + self.bias_c).unbind(0))
             if self.subject_class:
-                sub_cls.append(torch.matmul(hs_h[lvl] + self.bias_obj_a, obj_text) + self.bias_c)
+                sub_cls = list((torch.matmul(hs_h + self.bias_obj_a, obj_text) + self.bias_c).unbind(0))
+        else:
+            for lvl in range(n_lvl):
+                text_memory = F.normalize(text_dec[lvl].transpose(0, 1), p=2, dim=-1)
+                proj_text = dense.linear(text_memory / 2.0, self.projection_text.weight, self.projection_text.bias)
+                assert max_obj + max_pred == proj_text.shape[1]
+                obj_text = proj_text[:, :max_obj].transpose(1, 2)                      # [bs, 256, n_obj]
+                pred_text = proj_text[:, max_obj:max_obj + max_pred].transpose(1, 2)
+                obj_cls.append(torch.matmul(hs_o[lvl] + self.bias_obj_a, obj_text) + self.bias_c)
+                verb_cls.append(torch.matmul(hs_verb[lvl] + self.bias_pred_a, pred_text) + self.bias_c)
+                if self.subject_class:
+                    sub_cls.append(torch.matmul(hs_h[lvl] + self.bias_obj_a, obj_text) + self.bias_c)
 
         out = {"pred_obj_logits": obj_cls[-1], "pred_verb_logits": verb_cls[-1],
                "pred_sub_boxes": sub_boxes[-1], "pred_obj_boxes": obj_boxes[-1]}

@@ -99,14 +99,67 @@ class MultiBranchFusion(nn.Module):
         self.fc_3 = nn.ModuleList([nn.Linear(sub, representation_size) for _ in range(cardinality)])
 
     def forward(self, appearance, spatial):
-        w1 = torch.cat([m.weight for m in self.fc_1], 0)
-        b1 = torch.cat([m.bias for m in self.fc_1], 0)
-        w2 = torch.cat([m.weight for m in self.fc_2], 0)
-        b2 = torch.cat([m.bias for m in self.fc_2], 0)
-        w3 = torch.cat([m.weight for m in self.fc_3], 1)          # [R, cardinality*sub]
-        b3 = torch.stack([m.bias for m in self.fc_3], 0).sum(0)
+        w1, b1 = _StackedBranchParams.apply(0, *[t for m in self.fc_1 for t in (m.weight, m.bias)])
+        w2, b2 = _StackedBranchParams.apply(0, *[t for m in self.fc_2 for t in (m.weight, m.bias)])
+        w3, b3 = _StackedBranchParams.apply(1, *[t for m in self.fc_3 for t in (m.weight, m.bias)])
         h = F.relu(dense.linear(appearance, w1, b1) * dense.linear(spatial, w2, b2))
         return dense.linear_relu(h, w3, b3)
+
+
+class _StackedBranchParams(torch.autograd.Function):
+    """(weight, bias) of `cardinality` per-branch nn.Linear modules -> the operands of one stacked GEMM.
+    mode 0: branches side by side along the output features: W [n*o, i] = cat(w_c, 0), b [n*o] = cat(b_c)
+    mode 1: branches summed: W [o, n*i] = cat(w_c, 1), b [o] = sum_c b_c
+    Backward: autograd would hand 2n slices to 2n AccumulateGrad nodes (96 tiny `+=` kernels for the verb-query
+    generator).  When the parameters' .grad are adjacent views of the step's flat gradient buffer (train_step marks
+    them `_fuse_grad`; layout w_0 | b_0 | w_1 | b_1 | ...), the same sums are two strided adds."""
+
+    @staticmethod
+    def forward(ctx, mode, *params):
+        ws, bs = params[0::2], params[1::2]
+        ctx.mode, ctx.n = mode, len(ws)
+        ctx.params = params
+        if mode == 0:
+            return torch.cat(ws, 0), torch.cat(bs, 0)
+        return torch.cat(ws, 1), torch.stack(bs, 0).sum(0)
+
+    @staticmethod
+    def _adjacent_grad_views(params):
+        """[n, numel(w) + numel(b)] strided view over the parameters' flat gradient range, or None"""
+        ws, bs = params[0::2], params[1::2]
+        if not all(getattr(p, "_fuse_grad", False) and p.grad is not None and p.grad.is_contiguous() for p in params):
+            return None
+        nw, nb = ws[0].numel(), bs[0].numel()
+        if any(w.numel() != nw for w in ws) or any(b.numel() != nb for b in bs):
+            return None
+        base = ws[0].grad
+        ptr = base.data_ptr()
+        for p in params:
+            if p.grad.data_ptr() != ptr or p.grad.dtype != base.dtype:
+                return None
+            ptr += p.numel() * base.element_size()
+        return base.as_strided((len(ws), nw + nb), (nw + nb, 1))
+
+    @staticmethod
+    def backward(ctx, gw, gb):
+        n, params = ctx.n, ctx.params
+        w0, b0 = params[0], params[1]
+        o, i = w0.shape
+        if ctx.mode == 0:
+            gws = gw.reshape(n, o * i)                              # branch c = rows c*o .. (c+1)*o
+            gbs = gb.reshape(n, o)
+        else:
+            gws = gw.reshape(o, n, i).transpose(0, 1).reshape(n, o * i)
+            gbs = gb.reshape(1, o).expand(n, o)
+        region = _StackedBranchParams._adjacent_grad_views(params)
+        if region is not None:
+            region[:, :o * i].add_(gws)
+            region[:, o * i:].add_(gbs)
+            return (None,) + (None,) * len(params)
+        grads = []
+        for c in range(n):
+            grads += [gws[c].reshape(o, i), gbs[c].reshape(o)]
+        return (None,) + tuple(grads)
 
 
 class DeformableTransformerEncoderLayer(nn.Module):

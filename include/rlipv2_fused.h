@@ -100,6 +100,13 @@ int rlipv2_box_refine_f32(const float *delta, const float *ref, float eps, long 
  * out [rows, n*128], coordinate order (y, x[, w, h]), temperature 10000. */
 int rlipv2_sine_embed_f32(const float *pos, int rows, int n, float *out, void *stream);
 
+/* Matched-pair box losses of SetCriterionHOI (/root/reference/models/hoi.py:4162-4193; util/box_ops.py:19-73): for
+ * `rows` pairs of (cx, cy, w, h) boxes, l1[r] = sum |src - tgt|, giou_loss[r] = 1 - GIoU(src, tgt), and their
+ * gradients w.r.t. src: dl1[rows, 4], dgiou[rows, 4] (the reverse-mode derivative torch's autograd forms for the
+ * same expression).  src, tgt, dl1, dgiou 16-byte aligned. */
+int rlipv2_box_pair_loss_f32(const float *src, const float *tgt, int rows, float *l1, float *giou_loss, float *dl1,
+                             float *dgiou, void *stream);
+
 const char *rlipv2_fused_error_string(int code);
 unsigned long long rlipv2_fused_launch_count(void);
 

@@ -77,6 +77,7 @@ class SetCriterionHOI(nn.Module):
         self.pseudo_verb = pseudo_verb
         # independent loss terms on parallel streams (RLIPV2_PARALLEL_LOSSES=0: one chain, for A/B measurements)
         self.parallel_losses = __import__("os").environ.get("RLIPV2_PARALLEL_LOSSES", "1") != "0"
+        self.fused_box_loss = __import__("os").environ.get("RLIPV2_FUSED_BOX_LOSS", "1") != "0"
 
     # ---- helpers ----------------------------------------------------------------------------------
     @staticmethod
@@ -381,6 +382,16 @@ class SetCriterionHOI(nn.Module):
                 tgt_obj = torch.cat([t["obj_boxes"] for t in targets])[tcol]
                 exist = (tgt_obj != 0).any(dim=1)
                 n_exist = per_layer(exist) + 1e-4
+                if self.fused_box_loss and src_sub.is_cuda and src_sub.dtype == torch.float32:
+                    # L1 row sums, 1 - GIoU and their gradients for all matched subject + object pairs in one kernel
+                    # (csrc/fused_ops.cu box_pair_loss_kernel) instead of ~250 slice / min / max / clamp launches
+                    nk = src_sub.shape[0]
+                    l1, gl = _BoxPairLoss.apply(torch.cat((src_sub, src_obj), 0), torch.cat((tgt_sub, tgt_obj), 0))
+                    out["loss_sub_bbox"] = per_layer(l1[:nk]) / num_interactions
+                    out["loss_obj_bbox"] = per_layer(l1[nk:] * exist) / n_exist
+                    out["loss_sub_giou"] = per_layer(gl[:nk]) / num_interactions
+                    out["loss_obj_giou"] = per_layer(gl[nk:] * exist) / n_exist
+                    return
                 giou_sub = 1 - self._paired_giou(box_cxcywh_to_xyxy(src_sub), box_cxcywh_to_xyxy(tgt_sub))
                 giou_obj = 1 - self._paired_giou(box_cxcywh_to_xyxy(src_obj), box_cxcywh_to_xyxy(tgt_obj))
                 out["loss_sub_bbox"] = per_layer((src_sub - tgt_sub).abs()) / num_interactions
@@ -429,6 +440,23 @@ class SetCriterionHOI(nn.Module):
                                             for k in keys]).to(device)
             losses.weighted_total = (torch.stack([out[k] for k in keys]) * cache[wkey]).sum()
         return losses
+
+
+class _BoxPairLoss(torch.autograd.Function):
+    """(sum_k |src_k - tgt_k|, 1 - GIoU(src, tgt)) per row of matched (cx, cy, w, h) boxes, hoi.py:4162-4193; forward
+    values and the gradients w.r.t. `src` come from one kernel (include/rlipv2_fused.h rlipv2_box_pair_loss_f32)."""
+
+    @staticmethod
+    def forward(ctx, src, tgt):
+        from . import fused_abi
+        l1, gl, dl1, dgl = fused_abi.box_pair_loss(src.contiguous(), tgt.contiguous())
+        ctx.save_for_backward(dl1, dgl)
+        return l1, gl
+
+    @staticmethod
+    def backward(ctx, g_l1, g_gl):
+        dl1, dgl = ctx.saved_tensors
+        return torch.addcmul(g_l1.unsqueeze(1) * dl1, g_gl.unsqueeze(1), dgl), None
 
 
 _BRANCH_STREAMS = {}

@@ -278,6 +278,59 @@ box_refine_kernel(const float *__restrict__ delta, const float *__restrict__ ref
     }
 }
 
+// Matched-pair box losses of SetCriterionHOI (/root/reference/models/hoi.py:4162-4193 with util/box_ops.py:19-73):
+// per row r, src/tgt boxes (cx, cy, w, h):
+//   l1[r]   = sum_k |src_k - tgt_k|                    gl[r] = 1 - GIoU(xyxy(src), xyxy(tgt))
+// and their gradients w.r.t. src, dl1[r, 4] = sign(src - tgt), dgl[r, 4] - the reverse-mode derivative of the same
+// expression graph torch differentiates (clamp(min=0) passes gradient where its argument is >= 0, min / max split
+// ties evenly).  The forward values use the operation order of the torch formulation with explicitly rounded
+// products / sums (no FMA contraction), so they equal torch's bit for bit.  One thread per row: the reference spends
+// ~250 kernel launches (forward + backward) on these ~30 rows.
+__device__ __forceinline__ float sel_w(float a, float b) { return a > b ? 1.f : (a == b ? 0.5f : 0.f); }
+
+__global__ void __launch_bounds__(128)
+box_pair_loss_kernel(const float *__restrict__ src, const float *__restrict__ tgt, int R, float *__restrict__ l1,
+                     float *__restrict__ gl, float *__restrict__ dl1, float *__restrict__ dgl)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const float4 s = reinterpret_cast<const float4 *>(src)[r], t = reinterpret_cast<const float4 *>(tgt)[r];
+    // box_cxcywh_to_xyxy
+    const float a0x = __fsub_rn(s.x, __fmul_rn(0.5f, s.z)), a0y = __fsub_rn(s.y, __fmul_rn(0.5f, s.w));
+    const float a1x = __fadd_rn(s.x, __fmul_rn(0.5f, s.z)), a1y = __fadd_rn(s.y, __fmul_rn(0.5f, s.w));
+    const float b0x = __fsub_rn(t.x, __fmul_rn(0.5f, t.z)), b0y = __fsub_rn(t.y, __fmul_rn(0.5f, t.w));
+    const float b1x = __fadd_rn(t.x, __fmul_rn(0.5f, t.z)), b1y = __fadd_rn(t.y, __fmul_rn(0.5f, t.w));
+    const float aw = __fsub_rn(a1x, a0x), ah = __fsub_rn(a1y, a0y);
+    const float area_a = __fmul_rn(aw, ah), area_b = __fmul_rn(__fsub_rn(b1x, b0x), __fsub_rn(b1y, b0y));
+    const float dix = __fsub_rn(fminf(a1x, b1x), fmaxf(a0x, b0x)), diy = __fsub_rn(fminf(a1y, b1y), fmaxf(a0y, b0y));
+    const float iw = fmaxf(dix, 0.f), ih = fmaxf(diy, 0.f);
+    const float inter = __fmul_rn(iw, ih);
+    const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    const float iou = __fdiv_rn(inter, uni);
+    const float dex = __fsub_rn(fmaxf(a1x, b1x), fminf(a0x, b0x)), dey = __fsub_rn(fmaxf(a1y, b1y), fminf(a0y, b0y));
+    const float ew = fmaxf(dex, 0.f), eh = fmaxf(dey, 0.f);
+    const float earea = __fmul_rn(ew, eh);
+    const float giou = __fsub_rn(iou, __fdiv_rn(__fsub_rn(earea, uni), earea));
+    gl[r] = __fsub_rn(1.f, giou);
+    const float e0 = __fsub_rn(s.x, t.x), e1 = __fsub_rn(s.y, t.y), e2 = __fsub_rn(s.z, t.z), e3 = __fsub_rn(s.w, t.w);
+    l1[r] = __fadd_rn(__fadd_rn(__fadd_rn(fabsf(e0), fabsf(e1)), fabsf(e2)), fabsf(e3));
+    auto sgn = [](float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); };
+    reinterpret_cast<float4 *>(dl1)[r] = make_float4(sgn(e0), sgn(e1), sgn(e2), sgn(e3));
+    // d giou / d (a0x, a0y, a1x, a1y)
+    const float G_union = -inter / (uni * uni) + 1.f / earea;
+    const float g_inter = 1.f / uni - G_union;
+    const float g_earea = -uni / (earea * earea);
+    const float g_iw = dix >= 0.f ? g_inter * ih : 0.f, g_ih = diy >= 0.f ? g_inter * iw : 0.f;
+    const float g_ew = dex >= 0.f ? g_earea * eh : 0.f, g_eh = dey >= 0.f ? g_earea * ew : 0.f;
+    const float g_a1x = g_iw * sel_w(b1x, a1x) + g_ew * sel_w(a1x, b1x) + G_union * ah;
+    const float g_a0x = -g_iw * sel_w(a0x, b0x) - g_ew * sel_w(b0x, a0x) - G_union * ah;
+    const float g_a1y = g_ih * sel_w(b1y, a1y) + g_eh * sel_w(a1y, b1y) + G_union * aw;
+    const float g_a0y = -g_ih * sel_w(a0y, b0y) - g_eh * sel_w(b0y, a0y) - G_union * aw;
+    // back through cxcywh -> xyxy, and the sign of (1 - giou)
+    reinterpret_cast<float4 *>(dgl)[r] = make_float4(-(g_a0x + g_a1x), -(g_a0y + g_a1y), -0.5f * (g_a1x - g_a0x),
+                                                     -0.5f * (g_a1y - g_a0y));
+}
+
 // Sine embedding of anchor coordinates (gen_sineembed_for_position, deformable_transformer.py:1777-1802):
 // pos [R, n] (x, y[, w, h]) -> out [R, n*128] in the order (y, x[, w, h]); feature k of a coordinate p is
 // sin(2 pi p / T_k) for even k, cos(2 pi p / T_k) for odd k, T_k = 10000^(2 floor(k/2) / 128).
@@ -450,6 +503,16 @@ int rlipv2_box_refine_f32(const float *delta, const float *ref, float eps, long 
     long long blocks = (n + 255) / 256;
     if (blocks > kSMs * 8) blocks = kSMs * 8;
     box_refine_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(delta, ref, eps, n, y);
+    return done();
+}
+
+int rlipv2_box_pair_loss_f32(const float *src, const float *tgt, int rows, float *l1, float *giou_loss, float *dl1,
+                             float *dgiou, void *stream)
+{
+    if (rows == 0) return 0;
+    if (!src || !tgt || !l1 || !giou_loss || !dl1 || !dgiou || rows < 0) return RLIPV2_FUSED_EINVAL;
+    if (((uintptr_t)src | (uintptr_t)tgt | (uintptr_t)dl1 | (uintptr_t)dgiou) & 15) return RLIPV2_FUSED_EINVAL;
+    box_pair_loss_kernel<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(src, tgt, rows, l1, giou_loss, dl1, dgiou);
     return done();
 }
 

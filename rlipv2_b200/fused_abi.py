@@ -31,6 +31,8 @@ _lib.rlipv2_stamp_globaltimer.argtypes = [_p, _p]
 _lib.rlipv2_stamp_globaltimer.restype = _i
 _lib.rlipv2_box_refine_f32.argtypes = [_p, _p, _f, _ll, _p, _p]
 _lib.rlipv2_sine_embed_f32.argtypes = [_p, _i, _i, _p, _p]
+_lib.rlipv2_box_pair_loss_f32.argtypes = [_p, _p, _i, _p, _p, _p, _p, _p]
+_lib.rlipv2_box_pair_loss_f32.restype = _i
 for _n in ("wait_host_flag", "box_refine_f32", "sine_embed_f32"):
     getattr(_lib, "rlipv2_" + _n).restype = _i
 for _n in ("add_layernorm_fwd_f32", "layernorm_bwd_f32", "relu_bwd_colsum_f32", "adamw_f32", "gather_chunks_f32", "rowmask_bwd_colsum_f32"):
@@ -41,7 +43,7 @@ _lib.rlipv2_fused_launch_count.restype = ctypes.c_ulonglong
 
 EXPORTS = ("rlipv2_add_layernorm_fwd_f32", "rlipv2_layernorm_bwd_f32", "rlipv2_relu_bwd_colsum_f32",
            "rlipv2_adamw_f32", "rlipv2_adamw_scaled_f32", "rlipv2_gather_chunks_f32", "rlipv2_rowmask_bwd_colsum_f32", "rlipv2_wait_host_flag",
-           "rlipv2_box_refine_f32", "rlipv2_sine_embed_f32", "rlipv2_stamp_globaltimer", "rlipv2_layernorm_bwd_acc_f32",
+           "rlipv2_box_refine_f32", "rlipv2_sine_embed_f32", "rlipv2_box_pair_loss_f32", "rlipv2_stamp_globaltimer", "rlipv2_layernorm_bwd_acc_f32",
            "rlipv2_relu_bwd_colsum_acc_f32", "rlipv2_rowmask_bwd_colsum_acc_f32", "rlipv2_fused_error_string", "rlipv2_fused_launch_count")
 
 
@@ -186,6 +188,19 @@ def box_refine(delta, ref, eps=1e-5):
         rc = _lib.rlipv2_box_refine_f32(delta.data_ptr(), ref.data_ptr(), eps, delta.numel(), y.data_ptr(), _stream())
     _check(rc, "rlipv2_box_refine_f32")
     return y
+
+
+def box_pair_loss(src, tgt):
+    """src, tgt [R, 4] contiguous fp32 CUDA (cx, cy, w, h) -> l1 [R], giou_loss [R], dl1 [R, 4], dgiou [R, 4]"""
+    R = src.shape[0]
+    l1 = torch.empty(R, dtype=torch.float32, device=src.device)
+    gl = torch.empty_like(l1)
+    dl1, dgl = torch.empty_like(src), torch.empty_like(src)
+    with torch.cuda.device(src.device):
+        rc = _lib.rlipv2_box_pair_loss_f32(src.data_ptr(), tgt.data_ptr(), R, l1.data_ptr(), gl.data_ptr(),
+                                           dl1.data_ptr(), dgl.data_ptr(), _stream())
+    _check(rc, "rlipv2_box_pair_loss_f32")
+    return l1, gl, dl1, dgl
 
 
 def sine_embed(pos2d):

@@ -86,3 +86,39 @@ def test_wait_host_flag_times_out_instead_of_hanging():
     fused_abi.wait_host_flag(flag, seq, err, timeout_s=0.05)
     torch.cuda.synchronize()
     assert err.item() == 1 and seq.item() == 1
+
+
+@pytest.mark.parametrize("case", ["random", "disjoint", "nested", "identical"])
+def test_box_pair_loss_matches_torch_autograd(case):
+    """rlipv2_box_pair_loss_f32 vs the criterion's torch formulation (hoi.py:4162-4193, util/box_ops.py:19-73): forward
+    values bit-identical (same op order, no FMA contraction), gradients against torch.autograd in fp64"""
+    from rlipv2_b200.criterion import SetCriterionHOI, _BoxPairLoss
+    from rlipv2_b200.nested import box_cxcywh_to_xyxy
+    dev = _dev()
+    g = torch.Generator(device="cpu").manual_seed(11)
+    R = 301
+    mk = lambda: torch.cat((torch.rand(R, 2, generator=g) * 0.6 + 0.2, torch.rand(R, 2, generator=g) * 0.5 + 0.02), 1)
+    s, t = mk(), mk()
+    if case == "disjoint":
+        t[:, :2] = s[:, :2] + 0.8
+    elif case == "nested":
+        t[:, :2] = s[:, :2]
+        t[:, 2:] = s[:, 2:] * 0.3
+    elif case == "identical":
+        t = s.clone()                                     # every min / max is a tie: gradients split evenly
+    s_d = s.to(dev).requires_grad_(True)
+    l1, gl = _BoxPairLoss.apply(s_d, t.to(dev))
+    w1, w2 = torch.randn(R, generator=g), torch.randn(R, generator=g)
+    ((l1 * w1.to(dev)).sum() + (gl * w2.to(dev)).sum()).backward()
+    # forward: the same fp32 expression evaluated by torch on the device
+    s_t = s.to(dev)
+    ref_l1 = (s_t - t.to(dev)).abs().sum(-1)
+    ref_gl = 1 - SetCriterionHOI._paired_giou(box_cxcywh_to_xyxy(s_t), box_cxcywh_to_xyxy(t.to(dev)))
+    torch.testing.assert_close(l1, ref_l1, rtol=1e-6, atol=1e-6)
+    assert torch.equal(gl, ref_gl)
+    # gradient: autograd through the torch formulation in fp64
+    s64 = s.double().requires_grad_(True)
+    l1_64 = (s64 - t.double()).abs().sum(-1)
+    gl_64 = 1 - SetCriterionHOI._paired_giou(box_cxcywh_to_xyxy(s64), box_cxcywh_to_xyxy(t.double()))
+    ((l1_64 * w1.double()).sum() + (gl_64 * w2.double()).sum()).backward()
+    torch.testing.assert_close(s_d.grad.cpu().double(), s64.grad, rtol=1e-4, atol=1e-4)

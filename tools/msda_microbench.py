@@ -46,6 +46,15 @@ def run_case(name, make, N, S, Lq, iters, impls, peak):
         tb = time_rot(b, iters)
         res[iname] = {"fwd_us": tf * 1e6, "fwd_GBs": fwd_b / tf / 1e9, "fwd_frac": fwd_b / tf / 1e9 / peak,
                       "bwd_us": tb * 1e6, "bwd_GBs": bwd_b / tb / 1e9, "bwd_frac": bwd_b / tb / 1e9 / peak}
+        if iname == "ours":                       # backward schedules (include/rlipv2_msda.h): 0 one query / group, 1 paired
+            from rlipv2_b200 import msda_abi
+            keep = msda_abi.backward_variant()
+            for v in (0, 1):
+                msda_abi.set_backward_variant(v)
+                tv = time_rot(b, iters)
+                res[iname][f"bwd_variant{v}_us"] = tv * 1e6
+                res[iname][f"bwd_variant{v}_frac"] = bwd_b / tv / 1e9 / peak
+            msda_abi.set_backward_variant(keep)
     print(json.dumps(res))
     return res
 
@@ -54,7 +63,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", action="store_true")
     ap.add_argument("--iters", type=int, default=50)
-    ap.add_argument("--cases", default="dec16,dec2,encrand2,enc2")
+    ap.add_argument("--cases", default="dec16,dec2,encrand2,enc2,enc2init,enc2n025")
     args = ap.parse_args()
     peak = 6581.2
     try:
@@ -78,8 +87,12 @@ def main():
                  lambda seed: synth.random_inputs(2, 300, synth.LEVELS_MICRO, seed=seed), 2, Sm, 300),
         "encrand2": ("config5 encoder-shaped N=2 Lq=S=13294 (rand loc)",
                      lambda seed: synth.random_inputs(2, Sm, synth.LEVELS_MICRO, seed=seed), 2, Sm, Sm),
-        "enc2": ("encoder call 800x1333 N=2 Lq=S=22223 (local sampling)",
+        "enc2": ("encoder call 800x1333 N=2 Lq=S=22223 (local sampling, offsets = ring + 1 cell of noise)",
                  lambda seed: synth.encoder_inputs(2, synth.LEVELS_800x1333, seed=seed), 2, Se, Se),
+        "enc2init": ("encoder call 800x1333 N=2 Lq=S=22223 (offsets = ring pattern of the initialisation, no noise)",
+                     lambda seed: synth.encoder_inputs(2, synth.LEVELS_800x1333, seed=seed, noise_px=0.0), 2, Se, Se),
+        "enc2n025": ("encoder call 800x1333 N=2 Lq=S=22223 (ring + 0.25 cell of noise)",
+                     lambda seed: synth.encoder_inputs(2, synth.LEVELS_800x1333, seed=seed, noise_px=0.25), 2, Se, Se),
     }
     for key in args.cases.split(","):
         name, make, N, S, Lq = cases[key]

@@ -119,14 +119,6 @@ int rlipv2_msda_proj_ref4_backward_f32(const float *value, const int64_t *spatia
                                        int num_heads, int channels, int num_levels, int num_query, int num_point,
                                        float *grad_value, float *grad_proj, void *stream);
 
-/* Schedule of the fp32 D=32 L=4 P=4 backward for calls with at least 8192 queries (the encoder's self-attention):
- * 0 (default) one query per 8-lane group; 1 "paired": a lane group walks two consecutive queries and shares corner loads
- * and merges grad_value reductions wherever their bilinear footprints coincide or are one column apart.  Same sums for
- * any input; only the (already non-deterministic) fp32 summation order inside grad_value differs.  2 = paired for every
- * query count (tests). */
-void rlipv2_msda_set_backward_variant(int variant);
-int rlipv2_msda_get_backward_variant(void);
-
 /* Human-readable text for a return code of the functions above (static storage). */
 const char *rlipv2_msda_error_string(int code);
 

@@ -41,10 +41,6 @@
 namespace {
 
 std::atomic<unsigned long long> g_launches{0};
-// backward schedule of the fast path for encoder-shaped calls (rlipv2_msda_set_backward_variant): 0 = one query per lane
-// group, 1 = two x-adjacent queries per lane group with shared corner loads / merged reductions ("paired")
-std::atomic<int> g_bwd_variant{0};
-constexpr int kPairedMinQueries = 8192;
 
 constexpr int kFastD = 32;
 constexpr int kFastL = 4;
@@ -448,212 +444,6 @@ msda_bwd_d32_l4p4(const float *__restrict__ value, const int64_t *__restrict__ s
                              scaleH, prep[warp], Q, live, n, S, M, m);
 }
 
-// ---- backward, two queries per lane group ("paired" schedule) ---------------------------------------------------
-// In the encoder (Lq == S, one query per cell in raster order) the two x-adjacent queries Q, Q+1 sample every level at
-// positions one cell (level 0) to 1/8 cell (level 3) apart, so for the same point index their 2x2 corner footprints
-// are usually identical or shifted by exactly one column.  A lane group therefore walks Q and Q+1 together: B's
-// corners that coincide with corners of A reuse A's loaded rows (no second L1 request) and are folded into A's
-// reduction (one red.global.add.v4 instead of two) - the SM->L2 reduction path is what bounds the backward.
-//   same  : B's footprint == A's            4 loads + 4 reductions instead of 8 + 8
-//   shift : B's footprint == A's + 1 column 6 + 6 instead of 8 + 8 (A's right column is B's left column)
-//   else  : nothing shared, 8 + 8
-// The decision is made per point from the corner addresses, so the result is the same sum for ANY sampling pattern
-// (only the fp32 summation order inside grad_value differs, as it does between any two runs of the atomics).
-constexpr int kQueriesPerCtaPaired = 2 * kQueriesPerCta;
-
-__device__ __forceinline__ float dot4(const float4 &v, const float4 &g) {
-    return fmaf(v.x, g.x, fmaf(v.y, g.y, fmaf(v.z, g.z, v.w * g.w)));
-}
-
-__device__ __forceinline__ float group_sum4(float x) {       // over the 4 lanes that share (lane & 4)
-    x += __shfl_xor_sync(0xffffffffu, x, 1);
-    return x + __shfl_xor_sync(0xffffffffu, x, 2);
-}
-
-template <int PROJ>
-__device__ __forceinline__ void bwd_warp_pairs2(const float *__restrict__ value, const PairSrc &src,
-                                                const float *__restrict__ grad_out, float *__restrict__ grad_value,
-                                                float *__restrict__ grad_loc, float *__restrict__ grad_attn,
-                                                const WarpCtx &c, const LevelRow &my, const LevelRow *lvl_tab,
-                                                uint4 *mine, int Qa, int NQ, int Lq, int S, int M, int m)
-{
-    // ---- phase 1: both queries' 16 points -> shared memory (this lane: points 2*sub, 2*sub+1 of each)
-    float4 gq[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int Q = Qa + q;
-        const bool live = Q < NQ;
-        float4 l4;
-        float2 a2;
-        lane_points<PROJ>(src, c, my, Q, M, m, live, l4, a2);
-        const int n = live ? Q / Lq : 0;
-        const uint32_t cell0 = ((uint32_t)n * (uint32_t)S + my.start) * c.MD + (uint32_t)m * kFastD;
-        uint4 p0 = pack_point(l4.x, l4.y, a2.x, my.H, my.W, cell0, c.MD);
-        uint4 p1 = pack_point(l4.z, l4.w, a2.y, my.H, my.W, cell0, c.MD);
-        if (!live) { p0.x &= ~15u; p1.x &= ~15u; }       // dead query: no loads, no reductions
-        mine[(c.grp * 2 + q) * kFastLP + c.sub * 2 + 0] = p0;
-        mine[(c.grp * 2 + q) * kFastLP + c.sub * 2 + 1] = p1;
-        gq[q] = live ? ldg_f4(grad_out + ((size_t)Q * M + m) * kFastD + c.sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncwarp();
-    const float4 gA = gq[0], gB = gq[1];
-    const float *vbase = value + c.sub * 4;
-    float *gbase = grad_value + c.sub * 4;
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    // after pass h this lane holds the reduced partials of point h*4 + (sub & 3) of query Qa + (sub >> 2)
-    const int myq = c.sub >> 2, myj = c.sub & 3;
-    const int Qm = Qa + myq;
-    const bool live_m = Qm < NQ;
-    const size_t pair_m = (size_t)(live_m ? Qm : 0) * M + m;
-    float ka[4] = {0.f, 0.f, 0.f, 0.f}, kx[4] = {0.f, 0.f, 0.f, 0.f}, ky[4] = {0.f, 0.f, 0.f, 0.f};   // PROJ only
-#pragma unroll
-    for (int h = 0; h < kFastL; ++h) {                     // level h = points 4h .. 4h+3
-        const uint32_t rs = (h == 0) ? c.rs0 : (h == 1) ? c.rs1 : (h == 2) ? c.rs2 : c.rs3;
-        float pa[8], pw[8], ph[8];
-#pragma unroll
-        for (int j = 0; j < kFastP; ++j) {
-            const uint4 tA = mine[(c.grp * 2 + 0) * kFastLP + h * 4 + j];
-            const uint4 tB = mine[(c.grp * 2 + 1) * kFastLP + h * 4 + j];
-            const uint32_t bitsA = tA.x & 15u, baseA = tA.x & ~31u, bitsB = tB.x & 15u, baseB = tB.x & ~31u;
-            const uint32_t dxA = ((bitsA & 12u) == 12u) ? c.MD : 0u, dyA = ((bitsA & 3u) == 3u) ? rs : 0u;
-            const uint32_t dxB = ((bitsB & 12u) == 12u) ? c.MD : 0u, dyB = ((bitsB & 3u) == 3u) ? rs : 0u;
-            const bool a1 = (bitsA & 5u) == 5u, a2v = (bitsA & 9u) == 9u, a3 = (bitsA & 6u) == 6u, a4 = (bitsA & 10u) == 10u;
-            const bool b1 = (bitsB & 5u) == 5u, b2 = (bitsB & 9u) == 9u, b3 = (bitsB & 6u) == 6u, b4 = (bitsB & 10u) == 10u;
-            const bool same = (baseB == baseA) && (dxB == dxA) && (dyB == dyA);
-            const bool shift = !same && (dxA != 0u) && (baseB == baseA + dxA) && (dyB == dyA);
-            // B's corner that lands on A's slot k (if any) and whether it is a valid corner
-            const bool u1 = same && b1, u2 = same ? b2 : (shift && b1), u3 = same && b3, u4 = same ? b4 : (shift && b3);
-            // B's corners that need their own load / reduction
-            const bool o1 = b1 && !same && !shift, o2 = b2 && !same, o3 = b3 && !same && !shift, o4 = b4 && !same;
-            const float4 vA1 = (a1 || u1) ? ldg_f4(vbase + baseA) : zero;
-            const float4 vA2 = (a2v || u2) ? ldg_f4(vbase + baseA + dxA) : zero;
-            const float4 vA3 = (a3 || u3) ? ldg_f4(vbase + baseA + dyA) : zero;
-            const float4 vA4 = (a4 || u4) ? ldg_f4(vbase + baseA + dyA + dxA) : zero;
-            const float4 vB1 = o1 ? ldg_f4(vbase + baseB) : zero;
-            const float4 vB2 = o2 ? ldg_f4(vbase + baseB + dxB) : zero;
-            const float4 vB3 = o3 ? ldg_f4(vbase + baseB + dyB) : zero;
-            const float4 vB4 = o4 ? ldg_f4(vbase + baseB + dyB + dxB) : zero;
-            // ---- query A
-            {
-                const float lh = __uint_as_float(tA.y), lw = __uint_as_float(tA.z), a = __uint_as_float(tA.w);
-                const float hh = 1.f - lh, hw = 1.f - lw;
-                const float d1 = a1 ? dot4(vA1, gA) : 0.f, d2 = a2v ? dot4(vA2, gA) : 0.f;
-                const float d3 = a3 ? dot4(vA3, gA) : 0.f, d4 = a4 ? dot4(vA4, gA) : 0.f;
-                const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-                pa[j] = fmaf(w1, d1, fmaf(w2, d2, fmaf(w3, d3, w4 * d4)));          // cuh:155
-                pw[j] = a * fmaf(hh, d2 - d1, lh * (d4 - d3));                      // cuh:121-151
-                ph[j] = a * fmaf(hw, d3 - d1, lw * (d4 - d2));
-            }
-            // ---- query B (corner rows taken from A's registers where the footprints coincide)
-            float sB1, sB2, sB3, sB4;
-            {
-                const float lh = __uint_as_float(tB.y), lw = __uint_as_float(tB.z), a = __uint_as_float(tB.w);
-                const float hh = 1.f - lh, hw = 1.f - lw;
-                const float e1 = same ? dot4(vA1, gB) : (shift ? dot4(vA2, gB) : dot4(vB1, gB));
-                const float e2 = same ? dot4(vA2, gB) : dot4(vB2, gB);
-                const float e3 = same ? dot4(vA3, gB) : (shift ? dot4(vA4, gB) : dot4(vB3, gB));
-                const float e4 = same ? dot4(vA4, gB) : dot4(vB4, gB);
-                const float d1 = b1 ? e1 : 0.f, d2 = b2 ? e2 : 0.f, d3 = b3 ? e3 : 0.f, d4 = b4 ? e4 : 0.f;
-                const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-                pa[4 + j] = fmaf(w1, d1, fmaf(w2, d2, fmaf(w3, d3, w4 * d4)));
-                pw[4 + j] = a * fmaf(hh, d2 - d1, lh * (d4 - d3));
-                ph[4 + j] = a * fmaf(hw, d3 - d1, lw * (d4 - d2));
-                sB1 = b1 ? w1 * a : 0.f; sB2 = b2 ? w2 * a : 0.f; sB3 = b3 ? w3 * a : 0.f; sB4 = b4 ? w4 * a : 0.f;
-            }
-            // ---- grad_value (cuh:125,134,143,152): A's four slots carry B's coinciding corners
-            {
-                const float lh = __uint_as_float(tA.y), lw = __uint_as_float(tA.z), a = __uint_as_float(tA.w);
-                const float hh = 1.f - lh, hw = 1.f - lw;
-                const float s1 = a1 ? hh * hw * a : 0.f, s2 = a2v ? hh * lw * a : 0.f;
-                const float s3 = a3 ? lh * hw * a : 0.f, s4 = a4 ? lh * lw * a : 0.f;
-                const float t1 = same ? sB1 : 0.f, t2 = same ? sB2 : (shift ? sB1 : 0.f);
-                const float t3 = same ? sB3 : 0.f, t4 = same ? sB4 : (shift ? sB3 : 0.f);
-                if (a1 || u1) red_add_v4(gbase + baseA, fmaf(s1, gA.x, t1 * gB.x), fmaf(s1, gA.y, t1 * gB.y),
-                                         fmaf(s1, gA.z, t1 * gB.z), fmaf(s1, gA.w, t1 * gB.w));
-                if (a2v || u2) red_add_v4(gbase + baseA + dxA, fmaf(s2, gA.x, t2 * gB.x), fmaf(s2, gA.y, t2 * gB.y),
-                                          fmaf(s2, gA.z, t2 * gB.z), fmaf(s2, gA.w, t2 * gB.w));
-                if (a3 || u3) red_add_v4(gbase + baseA + dyA, fmaf(s3, gA.x, t3 * gB.x), fmaf(s3, gA.y, t3 * gB.y),
-                                         fmaf(s3, gA.z, t3 * gB.z), fmaf(s3, gA.w, t3 * gB.w));
-                if (a4 || u4) red_add_v4(gbase + baseA + dyA + dxA, fmaf(s4, gA.x, t4 * gB.x), fmaf(s4, gA.y, t4 * gB.y),
-                                         fmaf(s4, gA.z, t4 * gB.z), fmaf(s4, gA.w, t4 * gB.w));
-                if (o1) red_add_v4(gbase + baseB, sB1 * gB.x, sB1 * gB.y, sB1 * gB.z, sB1 * gB.w);
-                if (o2) red_add_v4(gbase + baseB + dxB, sB2 * gB.x, sB2 * gB.y, sB2 * gB.z, sB2 * gB.w);
-                if (o3) red_add_v4(gbase + baseB + dyB, sB3 * gB.x, sB3 * gB.y, sB3 * gB.z, sB3 * gB.w);
-                if (o4) red_add_v4(gbase + baseB + dyB + dxB, sB4 * gB.x, sB4 * gB.y, sB4 * gB.z, sB4 * gB.w);
-            }
-        }
-        // partial index = query * 4 + point: lane `sub` receives query sub >> 2, point h*4 + (sub & 3)
-        const float ga = group_reduce_scatter8(pa, c.sub);
-        const float gw = group_reduce_scatter8(pw, c.sub);
-        const float gh = group_reduce_scatter8(ph, c.sub);
-        const float Wf = (float)lvl_tab[h].W, Hf = (float)lvl_tab[h].H;              // cuh:156-158
-        if (PROJ) {
-            float gx, gy;
-            if (PROJ == 2) {
-                float2 wh = make_float2(0.f, 0.f);
-                if (live_m)
-                    wh = __ldg(reinterpret_cast<const float2 *>(src.ref + ((size_t)Qm * kFastL + h) * 4 + 2));
-                gx = __fmul_rn((gw * Wf) * 0.5f, wh.x) * 0.25f;
-                gy = __fmul_rn((gh * Hf) * 0.5f, wh.y) * 0.25f;
-            } else {
-                gx = __fdiv_rn(gw * Wf, Wf);
-                gy = __fdiv_rn(gh * Hf, Hf);
-            }
-            ka[h] = ga; kx[h] = gx; ky[h] = gy;
-        } else if (live_m) {
-            const int pt_idx = h * 4 + myj;
-            *reinterpret_cast<float2 *>(grad_loc + pair_m * (kFastLP * 2) + pt_idx * 2) = make_float2(gw * Wf, gh * Hf);
-            grad_attn[pair_m * kFastLP + pt_idx] = ga;
-        }
-    }
-    if (PROJ) {
-        // softmax backward over the 16 points of query Qm: this lane holds points myj, 4 + myj, 8 + myj, 12 + myj,
-        // the 4 lanes with the same `myq` hold all 16
-        float A[4], part = 0.f;
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            A[h] = __uint_as_float(mine[(c.grp * 2 + myq) * kFastLP + h * 4 + myj].w);
-            part = fmaf(A[h], ka[h], part);
-        }
-        const float dot = group_sum4(part);
-        if (live_m) {
-            float *row = grad_loc + (size_t)Qm * (size_t)(M * kFastLP * 3);
-            float *goff = row + m * (kFastLP * 2);
-            float *glog = row + M * (kFastLP * 2) + m * kFastLP;
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                *reinterpret_cast<float2 *>(goff + (h * 4 + myj) * 2) = make_float2(kx[h], ky[h]);
-                glog[h * 4 + myj] = A[h] * (ka[h] - dot);
-            }
-        }
-    }
-    __syncwarp();
-}
-
-template <int MINB, int PROJ = 0>
-__global__ void __launch_bounds__(kThreads, MINB)
-msda_bwd2_d32_l4p4(const float *__restrict__ value, const int64_t *__restrict__ shapes,
-                   const int64_t *__restrict__ lsi, const float *__restrict__ loc,
-                   const float *__restrict__ attn, const float *__restrict__ grad_out,
-                   int NQ, int Lq, int S, int M, float *__restrict__ grad_value,
-                   float *__restrict__ grad_loc, float *__restrict__ grad_attn)
-{
-    const PairSrc src = PROJ ? PairSrc{nullptr, nullptr, loc, attn} : PairSrc{loc, attn, nullptr, nullptr};
-    __shared__ __align__(16) uint4 prep[kWarpsPerCta][8 * kFastLP];
-    __shared__ LevelRow lvl_tab[kFastL];
-    load_level_table(lvl_tab, shapes, lsi, (uint32_t)M * kFastD);
-    const WarpCtx c = make_ctx(lvl_tab, M);
-    const LevelRow my = lvl_tab[c.sub >> 1];
-    const int warp = threadIdx.x >> 5;
-    const int Qa = blockIdx.x * kQueriesPerCtaPaired + warp * 8 + c.grp * 2;     // this group: queries Qa, Qa + 1
-    const int heads_per = (M + gridDim.y - 1) / gridDim.y;
-    const int m_begin = blockIdx.y * heads_per;
-    const int m_end = min(M, m_begin + heads_per);
-    for (int m = m_begin; m < m_end; ++m)
-        bwd_warp_pairs2<PROJ>(value, src, grad_out, grad_value, grad_loc, grad_attn, c, my, lvl_tab, prep[warp], Qa,
-                              NQ, Lq, S, M, m);
-}
-
 // ---------------------------------------------------------------------------------------------
 // Generic path: any channels / levels / points, float or double.
 // ---------------------------------------------------------------------------------------------
@@ -806,16 +596,6 @@ inline dim3 fast_grid(int NQ, int num_heads) {
     return dim3((unsigned)gx, (unsigned)gy, 1);
 }
 
-inline bool use_paired(int NQ) {
-    const int v = g_bwd_variant.load(std::memory_order_relaxed);
-    return v == 2 || (v == 1 && NQ >= kPairedMinQueries);
-}
-
-// paired backward: 64 queries per CTA, all heads in one CTA (only used for NQ >= kPairedMinQueries)
-inline dim3 paired_grid(int NQ) {
-    return dim3((unsigned)((NQ + kQueriesPerCtaPaired - 1) / kQueriesPerCtaPaired), 1, 1);
-}
-
 inline int grid_for(long long work, int per_block) {
     long long b = (work + per_block - 1) / per_block;
     const long long cap = 148ll * 64;     // grid-stride beyond this
@@ -879,16 +659,10 @@ int backward_impl(const T *value, const int64_t *shapes, const int64_t *lsi, con
     if (allow_fast) {
         const int NQ = batch * num_query;
         const dim3 grid = fast_grid(NQ, num_heads);
-        if (use_paired(NQ))
-            msda_bwd2_d32_l4p4<2><<<paired_grid(NQ), kThreads, 0, stream>>>(
-                (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn,
-                (const float *)grad_out, NQ, num_query, spatial_size, num_heads, (float *)grad_value,
-                (float *)grad_loc, (float *)grad_attn);
-        else
-            msda_bwd_d32_l4p4<2><<<grid, kThreads, 0, stream>>>(
-                (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn,
-                (const float *)grad_out, NQ, num_query, spatial_size, num_heads, (float *)grad_value,
-                (float *)grad_loc, (float *)grad_attn);
+        msda_bwd_d32_l4p4<2><<<grid, kThreads, 0, stream>>>(
+            (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn,
+            (const float *)grad_out, NQ, num_query, spatial_size, num_heads, (float *)grad_value,
+            (float *)grad_loc, (float *)grad_attn);
     } else {
         msda_bwd_generic<T><<<grid_for(pairs * 32, 256), 256, 0, stream>>>(
             value, shapes, lsi, loc, attn, grad_out, pairs, num_query, spatial_size, num_heads,
@@ -949,17 +723,9 @@ int proj_backward_impl(const float *value, const int64_t *shapes, const int64_t 
     if (NQ == 0) return 0;
     if (!value || !shapes || !lsi || !ref || !proj || !grad_out || !grad_proj) return RLIPV2_MSDA_EINVAL;
     const dim3 grid = fast_grid(NQ, num_heads);
-    const bool paired = use_paired(NQ);
-    if (ref_dim == 4) {
-        if (paired)
-            msda_bwd2_d32_l4p4<2, 2><<<paired_grid(NQ), kThreads, 0, stream>>>(
-                value, shapes, lsi, proj, ref, grad_out, NQ, num_query, spatial_size, num_heads, grad_value, grad_proj, nullptr);
-        else
-            msda_bwd_d32_l4p4<2, 2><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, grad_out, NQ, num_query,
-                                                                    spatial_size, num_heads, grad_value, grad_proj, nullptr);
-    } else if (paired)
-        msda_bwd2_d32_l4p4<2, 1><<<paired_grid(NQ), kThreads, 0, stream>>>(
-            value, shapes, lsi, proj, ref, grad_out, NQ, num_query, spatial_size, num_heads, grad_value, grad_proj, nullptr);
+    if (ref_dim == 4)
+        msda_bwd_d32_l4p4<2, 2><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, grad_out, NQ, num_query,
+                                                                spatial_size, num_heads, grad_value, grad_proj, nullptr);
     else
         msda_bwd_d32_l4p4<2, 1><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, grad_out, NQ, num_query,
                                                                 spatial_size, num_heads, grad_value, grad_proj, nullptr);
@@ -1076,13 +842,6 @@ const char *rlipv2_msda_error_string(int code)
 }
 
 int rlipv2_msda_abi_version(void) { return RLIPV2_MSDA_ABI_VERSION; }
-
-void rlipv2_msda_set_backward_variant(int variant)
-{
-    g_bwd_variant.store(variant == 1 || variant == 2 ? variant : 0, std::memory_order_relaxed);
-}
-
-int rlipv2_msda_get_backward_variant(void) { return g_bwd_variant.load(std::memory_order_relaxed); }
 
 
 unsigned long long rlipv2_msda_launch_count(void)

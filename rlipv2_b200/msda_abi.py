@@ -35,9 +35,6 @@ _lib.rlipv2_msda_proj_ref4_backward_f32.argtypes = [_p] * 6 + _DIMS + [_p] * 3
 for _f in ("forward_f32", "forward_f64", "backward_f32", "backward_f64", "proj_forward_f32", "proj_backward_f32",
            "proj_ref4_forward_f32", "proj_ref4_backward_f32"):
     getattr(_lib, "rlipv2_msda_" + _f).restype = _i
-_lib.rlipv2_msda_set_backward_variant.argtypes = [_i]
-_lib.rlipv2_msda_set_backward_variant.restype = None
-_lib.rlipv2_msda_get_backward_variant.restype = _i
 _lib.rlipv2_msda_error_string.argtypes = [_i]
 _lib.rlipv2_msda_error_string.restype = ctypes.c_char_p
 _lib.rlipv2_msda_abi_version.restype = _i
@@ -49,21 +46,7 @@ if _lib.rlipv2_msda_abi_version() != ABI_VERSION:
 EXPORTS = ("rlipv2_msda_forward_f32", "rlipv2_msda_forward_f64", "rlipv2_msda_backward_f32",
            "rlipv2_msda_backward_f64", "rlipv2_msda_proj_forward_f32", "rlipv2_msda_proj_backward_f32",
            "rlipv2_msda_proj_ref4_forward_f32", "rlipv2_msda_proj_ref4_backward_f32",
-           "rlipv2_msda_error_string", "rlipv2_msda_abi_version", "rlipv2_msda_launch_count",
-           "rlipv2_msda_set_backward_variant", "rlipv2_msda_get_backward_variant")
-
-
-if os.environ.get("RLIPV2_MSDA_BWD_VARIANT"):                       # A/B switch for measurements
-    _lib.rlipv2_msda_set_backward_variant(int(os.environ["RLIPV2_MSDA_BWD_VARIANT"]))
-
-
-def set_backward_variant(v):
-    """0: one query per lane group; 1: paired schedule for encoder-shaped calls (include/rlipv2_msda.h)"""
-    _lib.rlipv2_msda_set_backward_variant(int(v))
-
-
-def backward_variant():
-    return int(_lib.rlipv2_msda_get_backward_variant())
+           "rlipv2_msda_error_string", "rlipv2_msda_abi_version", "rlipv2_msda_launch_count")
 
 
 def library_path():

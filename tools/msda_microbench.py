@@ -46,15 +46,6 @@ def run_case(name, make, N, S, Lq, iters, impls, peak):
         tb = time_rot(b, iters)
         res[iname] = {"fwd_us": tf * 1e6, "fwd_GBs": fwd_b / tf / 1e9, "fwd_frac": fwd_b / tf / 1e9 / peak,
                       "bwd_us": tb * 1e6, "bwd_GBs": bwd_b / tb / 1e9, "bwd_frac": bwd_b / tb / 1e9 / peak}
-        if iname == "ours":                       # backward schedules (include/rlipv2_msda.h): 0 one query / group, 1 paired
-            from rlipv2_b200 import msda_abi
-            keep = msda_abi.backward_variant()
-            for v in (0, 1):
-                msda_abi.set_backward_variant(v)
-                tv = time_rot(b, iters)
-                res[iname][f"bwd_variant{v}_us"] = tv * 1e6
-                res[iname][f"bwd_variant{v}_frac"] = bwd_b / tv / 1e9 / peak
-            msda_abi.set_backward_variant(keep)
     print(json.dumps(res))
     return res
 

@@ -30,6 +30,31 @@ _OWN_BWD = os.environ.get("RLIPV2_OWN_BWD", "0") == "1"
 _FFN_BWD = os.environ.get("RLIPV2_FFN_BWD", "hybrid")
 _OWN_WGRAD = os.environ.get("RLIPV2_OWN_WGRAD", "1") != "0"
 _OWN_BWD_MIN_ROWS = int(os.environ.get("RLIPV2_OWN_BWD_MIN_ROWS", "4096"))
+# Parameter gradients of the small linears (decoders, heads, ALIF, RobertaLayer, text tower: a few hundred to ~1300 rows)
+# on a side stream.  Their backward is a chain of launch-bound 5-8 us GEMMs; only the input gradient is on the chain to
+# the next layer, the weight / bias gradient is not needed before the optimizer.  Active only when the gradient is
+# accumulated in place into the step's flat gradient buffer (`_fuse_grad`), so nothing is handed back to autograd from
+# the side stream; the train step joins it after backward() (`join_param_grad_stream`).
+_WGRAD_STREAM = os.environ.get("RLIPV2_WGRAD_STREAM", "1") != "0"
+_WGRAD_STREAM_MAX_ROWS = int(os.environ.get("RLIPV2_WGRAD_STREAM_MAX_ROWS", "4096"))
+_param_grad_streams = {}
+_param_grad_pending = set()
+
+
+def _param_grad_stream(device):
+    st = _param_grad_streams.get(device)
+    if st is None:
+        st = _param_grad_streams[device] = torch.cuda.Stream(device)
+    return st
+
+
+def join_param_grad_stream(device=None):
+    """make the current stream wait for the parameter-gradient side stream(s) (call after backward(), before the
+    gradients are read)"""
+    for dev in list(_param_grad_pending):
+        if device is None or dev == device:
+            torch.cuda.current_stream(dev).wait_stream(_param_grad_streams[dev])
+            _param_grad_pending.discard(dev)
 
 
 def set_matmul_precision(mode: str, tcgen05: bool = True, fused: bool = True):
@@ -84,19 +109,42 @@ class _LinearTF32(torch.autograd.Function):
         gb = None
         b_acc = ctx.b_acc.grad if ctx.b_acc is not None and ctx.needs_input_grad[2] else None
         w_acc = ctx.w_acc.grad if ctx.w_acc is not None and ctx.needs_input_grad[1] else None
+        T, N, K = g.shape[0], g.shape[1], w.shape[1]
+        # parameter gradients off the critical chain (small problems whose gradients accumulate in place)
+        side = None
+        if (_WGRAD_STREAM and g.is_cuda and T <= _WGRAD_STREAM_MAX_ROWS and w_acc is not None
+                and (not ctx.has_bias or not ctx.needs_input_grad[2] or b_acc is not None)):
+            side = _param_grad_stream(g.device)
+        plain_bias = rm is None and y is None and g.shape[1] % 32 == 0           # column sums only, g unchanged
         if rm is not None:
             # rows zeroed in the forward carry no gradient (N % 128 == 0 on this path, so the kernel applies)
             g, gb = _fused().rowmask_bwd_colsum(g, rm, acc=b_acc)
         elif g.shape[1] % 32 == 0:
-            # one pass: ReLU mask (when fused in the forward) + bias-gradient column sum
-            g, gb = _fused().relu_bwd_colsum(g, y, acc=b_acc)
+            if not (side is not None and plain_bias):
+                # one pass: ReLU mask (when fused in the forward) + bias-gradient column sum
+                g, gb = _fused().relu_bwd_colsum(g, y, acc=b_acc)
         else:
             if y is not None:
                 g = g * (y > 0)
             gb = g.sum(0)
+            if side is not None and b_acc is not None:
+                b_acc.add_(gb)
+                gb = None
         gx = gw = None
-        T, N, K = g.shape[0], g.shape[1], w.shape[1]
         big = T >= _OWN_BWD_MIN_ROWS and _abi().grads_supported(T, N, K)
+        if side is not None:
+            cur = torch.cuda.current_stream(g.device)
+            side.wait_stream(cur)                        # g (masked) is complete on `cur`; x2 long since
+            with torch.cuda.stream(side):
+                if plain_bias and ctx.has_bias and ctx.needs_input_grad[2]:
+                    _fused().relu_bwd_colsum(g, None, acc=b_acc)
+                w_acc.addmm_(g.t(), x2)                  # cuBLAS with beta = 1: grad view += g^T x
+            g.record_stream(side)
+            x2.record_stream(side)
+            _param_grad_pending.add(g.device)
+            if ctx.needs_input_grad[0]:
+                gx = (g @ w).view(*grad_out.shape[:-1], K)
+            return gx, None, None, None, None
         if ctx.needs_input_grad[0]:
             gx = (_abi().dgrad_tf32(g, w)[0] if _OWN_BWD and big else g @ w).view(*grad_out.shape[:-1], K)
         if ctx.needs_input_grad[1]:

@@ -193,11 +193,13 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
             for p in self.params:
                 p.grad = None
             total.backward()
+            dense.join_param_grad_stream()
             self._gather_grads()
         else:
             if not self.early_zero:
                 self.flat_grad.zero_()
             total.backward()
+        dense.join_param_grad_stream()               # parameter gradients formed on the side stream (dense.py)
         if self.fused_clip:
             self.flat.allreduce_sum_()               # one NCCL all-reduce of the flat buffer (world > 1)
             self._adamw_step(self.flat.clip_scale(self.clip_max_norm))   # clip_grad_norm_ = one norm; scale in AdamW

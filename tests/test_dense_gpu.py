@@ -265,6 +265,7 @@ def test_fused_gradient_accumulation_into_flat_views(T, mode):
             # the weight is used twice: both uses must land in the same view
             y = y + dense.linear(xx, w, b, row_mask=mask) if mode != "relu" else y + dense.linear_relu(xx, w, b)
             y.backward(go)
+            dense.join_param_grad_stream()            # small problems form their parameter gradients on a side stream
             return flat, xx.grad
 
         flat_f, gx_f = run(True)

@@ -128,8 +128,16 @@ class MSDeformAttn(nn.Module):
         xavier_uniform_(self.output_proj.weight.data)
         constant_(self.output_proj.bias.data, 0.)
 
+    def project_value(self, input_flatten, input_padding_mask=None):
+        """value_proj + `masked_fill(padding_mask, 0)` (:98-100): the mask rides in the GEMM epilogue.  Callers whose
+        `input_flatten` is ready long before the query (the decoders: the same encoder memory for every layer) can
+        evaluate this ahead of time / on another stream and hand the result to forward(value=...)."""
+        N, Len_in, _ = input_flatten.shape
+        value = dense.linear(input_flatten, self.value_proj.weight, self.value_proj.bias, row_mask=input_padding_mask)
+        return value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
+
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes,
-                input_level_start_index, input_padding_mask=None, spatial_shapes_host=None):
+                input_level_start_index, input_padding_mask=None, spatial_shapes_host=None, value=None):
         """Arguments as ms_deform_attn.py:82-94.  ``spatial_shapes_host`` (optional, a python list
         of (H, W)) lets callers that already know the level shapes skip the device->host sync the
         reference's ``assert (shapes[:,0]*shapes[:,1]).sum() == Len_in`` costs on every call
@@ -141,9 +149,8 @@ class MSDeformAttn(nn.Module):
         else:
             assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
 
-        # value_proj + `masked_fill(padding_mask, 0)` (:98-100): the mask rides in the GEMM epilogue
-        value = dense.linear(input_flatten, self.value_proj.weight, self.value_proj.bias, row_mask=input_padding_mask)
-        value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
+        if value is None:
+            value = self.project_value(input_flatten, input_padding_mask)
         if (_FUSED_PROLOGUE and not reference_points.requires_grad and value.is_cuda
                 and input_flatten.dtype == torch.float32 and self.d_model // self.n_heads == 32
                 and reference_points.shape[-1] in ((2, 4) if _FUSED_PROLOGUE_REF4 else (2,))

@@ -54,6 +54,9 @@ def _level_tensors(shapes_host, device):
     return _LEVEL_CACHE[key]
 
 
+_VALUE_STREAM = os.environ.get("RLIPV2_VALUE_STREAM", "1") != "0"   # decoder value projections on a side stream
+
+
 def _get_clones(module, n):
     return nn.ModuleList([copy.deepcopy(module) for _ in range(n)])
 
@@ -337,14 +340,14 @@ class DeformableTransformerDecoderLayer(nn.Module):
         self.norm3 = nn.LayerNorm(d_model)
 
     def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index,
-                src_padding_mask=None, spatial_shapes_host=None):
+                src_padding_mask=None, spatial_shapes_host=None, value=None):
         if self.do_self_attn:
             qk = tgt if query_pos is None else tgt + query_pos
             tgt2 = self.self_attn(qk, tgt)
             tgt = dense.add_layer_norm(self.dropout2(tgt2), tgt, self.norm2.weight, self.norm2.bias, self.norm2.eps)
         q = tgt if query_pos is None else tgt + query_pos
         tgt2 = self.cross_attn(q, reference_points, src, src_spatial_shapes, level_start_index,
-                               src_padding_mask, spatial_shapes_host=spatial_shapes_host)
+                               src_padding_mask, spatial_shapes_host=spatial_shapes_host, value=value)
         tgt = dense.add_layer_norm(self.dropout1(tgt2), tgt, self.norm1.weight, self.norm1.bias, self.norm1.eps)
         h = self.dropout3(dense.linear_relu(tgt, self.linear1.weight, self.linear1.bias))
         tgt2 = self.dropout4(dense.linear(h, self.linear2.weight, self.linear2.bias))
@@ -386,6 +389,26 @@ class DABDeformableTransformerDecoderHOI(nn.Module):
         pair_num = obj_ref.shape[1]
         vr4 = torch.cat([src_valid_ratios, src_valid_ratios], -1)[:, None]       # [bs, 1, L, 4]
         inter, inter_sub, inter_obj = [], [], []
+        # Every layer's cross-attention projects the same encoder memory with its own value_proj (44k rows: the only
+        # large GEMM of the decoder, ~30 us forward and ~80 us backward per layer).  None of them depends on the
+        # queries, so they run on a side stream beside the chain of small per-query kernels (forward here, and -
+        # autograd replays nodes on the stream of their forward - the backward too).
+        values = [None] * len(self.layers)
+        if _VALUE_STREAM and src.is_cuda:
+            cur = torch.cuda.current_stream(src.device)
+            if getattr(self, "_value_stream", None) is None:
+                self._value_stream = torch.cuda.Stream(src.device)
+            side = self._value_stream
+            side.wait_stream(cur)
+            values, value_ready = [], []
+            with torch.cuda.stream(side):
+                for layer in self.layers:
+                    values.append(layer.cross_attn.project_value(src, src_padding_mask))
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    value_ready.append(ev)
+            for v in values:
+                v.record_stream(cur)
         # refined boxes with their autograd history: the pair decoder's are exactly the model's box
         # predictions (hoi.py:2122-2141 recomputes the same MLP on the same inputs), so the head reuses them
         refined = self.refined_boxes = []
@@ -396,8 +419,10 @@ class DABDeformableTransformerDecoderHOI(nn.Module):
                 ref_input = 0.5 * (sub_ref + obj_ref)[:, :, None] * vr4
             raw_query_pos = self.ref_point_head(gen_sineembed_for_position(ref_input[:, :, 0, :]))
             query_pos_l = raw_query_pos if lid == 0 else self.query_scale(output) * raw_query_pos
+            if values[lid] is not None:
+                torch.cuda.current_stream(src.device).wait_event(value_ready[lid])
             output = layer(output, query_pos_l, ref_input, src, src_spatial_shapes, src_level_start_index,
-                           src_padding_mask, spatial_shapes_host=spatial_shapes_host)
+                           src_padding_mask, spatial_shapes_host=spatial_shapes_host, value=values[lid])
             # iterative box refinement; the refined anchors are detached (:1511-1541)
             if self.sub_bbox_embed is not None:
                 sub_in = output[:, :pair_num] if self.ParSe else output

@@ -48,6 +48,28 @@ def _param_grad_stream(device):
     return st
 
 
+class _ParamGradSide:
+    """`with _ParamGradSide(dev, t1, t2, ...)`: the body runs on the parameter-gradient side stream, after everything
+    issued so far on the current stream; the tensors it reads are kept alive for that stream."""
+
+    def __init__(self, device, *reads):
+        self.device, self.reads = device, reads
+
+    def __enter__(self):
+        self.side = _param_grad_stream(self.device)
+        self.side.wait_stream(torch.cuda.current_stream(self.device))
+        self.ctx = torch.cuda.stream(self.side)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        self.ctx.__exit__(*a)
+        for t in self.reads:
+            if t is not None:
+                t.record_stream(self.side)
+        _param_grad_pending.add(self.device)
+
+
 def join_param_grad_stream(device=None):
     """make the current stream wait for the parameter-gradient side stream(s) (call after backward(), before the
     gradients are read)"""
@@ -133,17 +155,15 @@ class _LinearTF32(torch.autograd.Function):
         gx = gw = None
         big = T >= _OWN_BWD_MIN_ROWS and _abi().grads_supported(T, N, K)
         if side is not None:
-            cur = torch.cuda.current_stream(g.device)
-            side.wait_stream(cur)                        # g (masked) is complete on `cur`; x2 long since
-            with torch.cuda.stream(side):
+            with _ParamGradSide(g.device, g, x2):        # g (masked) is complete on the current stream; x2 long since
                 if plain_bias and ctx.has_bias and ctx.needs_input_grad[2]:
                     _fused().relu_bwd_colsum(g, None, acc=b_acc)
-                w_acc.addmm_(g.t(), x2)                  # cuBLAS with beta = 1: grad view += g^T x
-            g.record_stream(side)
-            x2.record_stream(side)
-            _param_grad_pending.add(g.device)
+                if big and _OWN_WGRAD and (_OWN_BWD or N * K <= 384 * 256):
+                    _abi().wgrad_tf32(g, x2, acc=w_acc)  # split-K tcgen05 kernel, reduces straight into the view
+                else:
+                    w_acc.addmm_(g.t(), x2)              # cuBLAS with beta = 1: grad view += g^T x
             if ctx.needs_input_grad[0]:
-                gx = (g @ w).view(*grad_out.shape[:-1], K)
+                gx = (_abi().dgrad_tf32(g, w)[0] if _OWN_BWD and big else g @ w).view(*grad_out.shape[:-1], K)
             return gx, None, None, None, None
         if ctx.needs_input_grad[0]:
             gx = (_abi().dgrad_tf32(g, w)[0] if _OWN_BWD and big else g @ w).view(*grad_out.shape[:-1], K)
@@ -192,6 +212,20 @@ class _FFNReLU(torch.autograd.Function):
         g = g if g.is_contiguous() else g.contiguous()
         acc = lambda p: p.grad if (p is not None and getattr(p, "_fuse_grad", False) and p.grad is not None) else None
         w1p, b1p, w2p, b2p = ctx.params
+        T = g.shape[0]
+        if (_WGRAD_STREAM and T <= _WGRAD_STREAM_MAX_ROWS and all(acc(p) is not None for p in ctx.params)):
+            # the chain to the previous layer is gh -> gx; the two weight gradients and db2 run beside it
+            with _ParamGradSide(g.device, g, h):
+                _fused().relu_bwd_colsum(g, None, acc=acc(b2p))
+                abi.wgrad_tf32(g, h, acc=acc(w2p))
+            gh, gb1 = abi.dgrad_tf32(g, w2, relu_out=h)
+            b1p.grad.add_(gb1)
+            with _ParamGradSide(g.device, gh, x2):
+                abi.wgrad_tf32(gh, x2, acc=acc(w1p))
+            gx = None
+            if ctx.needs_input_grad[0]:
+                gx = (gh @ w1 if _FFN_BWD == "hybrid" else abi.dgrad_tf32(gh, w1)[0]).view(*grad_out.shape[:-1], w1.shape[1])
+            return gx, None, None, None, None
         _, gb2 = _fused().relu_bwd_colsum(g, None, acc=acc(b2p))
         gw2 = abi.wgrad_tf32(g, h, acc=acc(w2p))
         gh, gb1 = abi.dgrad_tf32(g, w2, relu_out=h)

@@ -162,11 +162,21 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
 
     def _forward_and_costs(self):
         self._stamp(0)
+        zero_side = None
         if self.early_zero and not self.gather_grads and getattr(self, "flat_grad", None) is not None:
-            self.flat_grad.zero_()
+            # 850 MB memset beside the (launch-bound) start of the text tower / backbone stem, joined below
+            cur = torch.cuda.current_stream(self.device)
+            if getattr(self, "_zero_stream", None) is None:
+                self._zero_stream = torch.cuda.Stream(self.device)
+            zero_side = self._zero_stream
+            zero_side.wait_stream(cur)
+            with torch.cuda.stream(zero_side):
+                self.flat_grad.zero_()
         cache = self.module(self.s_samples, encode_and_save=True, text=self.s_tok, targets=self.s_targets)
         outputs = self.module(self.s_samples, encode_and_save=False, memory_cache=cache, text=self.s_tok,
                               targets=self.s_targets)
+        if zero_side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(zero_side)
         layers = self.criterion.layers_of(outputs)
         C, cost_lists = self.criterion.matcher.compute_costs_layers(layers, self.s_targets)   # all layers, one pass
         self.h_cost.copy_(C, non_blocking=True)

@@ -14,6 +14,7 @@ import torchvision
 from torch import nn
 from torchvision.models._utils import IntermediateLayerGetter
 
+from . import dense
 from .nested import NestedTensor
 
 
@@ -42,6 +43,7 @@ class FrozenBatchNorm2d(nn.Module):
 
 
 _FUSED_CONV = os.environ.get("RLIPV2_FUSED_CONV", "1") != "0"      # A/B switch for measurements
+_CONV_WGRAD_STREAM = os.environ.get("RLIPV2_CONV_WGRAD_STREAM", "1") != "0"   # conv weight gradients on the side stream
 # channels_last activations through the backbone: cuDNN's TF32 kernels are NHWC-native, so NCHW tensors cost a
 # nchwToNhwc / nhwcToNchw pair around every convolution (3.3 ms per step); with BN folded and bias / residual /
 # ReLU fused into the convolutions there is no NCHW-favouring elementwise pass left (measured: 44.0 -> 39.5 ms).
@@ -55,7 +57,7 @@ class _ConvBiasReLU(torch.autograd.Function):
     3-4 kernels -> 1 in the forward of every trainable bottleneck convolution."""
 
     @staticmethod
-    def forward(ctx, x, w, b, residual, stride, padding, dilation, groups):
+    def forward(ctx, x, w, b, residual, stride, padding, dilation, groups, leaf=None, leaf_scale=None):
         if residual is not None:
             y = torch.cudnn_convolution_add_relu(x, w, residual, 1.0, b, stride, padding, dilation, groups)
         else:
@@ -63,6 +65,10 @@ class _ConvBiasReLU(torch.autograd.Function):
         ctx.save_for_backward(x, w, y)
         ctx.conf = (stride, padding, dilation, groups)
         ctx.has_residual = residual is not None
+        # `w` = leaf * leaf_scale (BN folded in); when the leaf's .grad is a view of the step's flat gradient buffer the
+        # weight gradient is formed and accumulated on the parameter-gradient side stream (dense.py), off the chain of
+        # input gradients that the previous block is waiting for
+        ctx.leaf, ctx.leaf_scale = leaf, leaf_scale
         return y
 
     @staticmethod
@@ -70,11 +76,26 @@ class _ConvBiasReLU(torch.autograd.Function):
         x, w, y = ctx.saved_tensors
         stride, padding, dilation, groups = ctx.conf
         g = torch.ops.aten.threshold_backward(grad_out, y, 0)
-        gx, gw, _ = torch.ops.aten.convolution_backward(
-            g, x, w, None, stride, padding, dilation, False, [0, 0], groups,
-            [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        leaf = ctx.leaf
+        side = (ctx.needs_input_grad[1] and leaf is not None and dense._WGRAD_STREAM and _CONV_WGRAD_STREAM
+                and getattr(leaf, "_fuse_grad", False)
+                and leaf.grad is not None and g.is_cuda)
+        if side:
+            with dense._ParamGradSide(g.device, g, x):
+                _, gw, _ = torch.ops.aten.convolution_backward(
+                    g, x, w, None, stride, padding, dilation, False, [0, 0], groups, [False, True, False])
+                leaf.grad.addcmul_(gw, ctx.leaf_scale.view(-1, 1, 1, 1))
+            gx = None
+            if ctx.needs_input_grad[0]:
+                gx, _, _ = torch.ops.aten.convolution_backward(
+                    g, x, w, None, stride, padding, dilation, False, [0, 0], groups, [True, False, False])
+            gw = None
+        else:
+            gx, gw, _ = torch.ops.aten.convolution_backward(
+                g, x, w, None, stride, padding, dilation, False, [0, 0], groups,
+                [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
         gres = g if (ctx.has_residual and ctx.needs_input_grad[3]) else None
-        return gx, gw, None, gres, None, None, None, None
+        return gx, gw, None, gres, None, None, None, None, None, None
 
 
 class PositionEmbeddingSine(nn.Module):
@@ -189,7 +210,9 @@ class Backbone(nn.Module):
         fused = x.is_cuda and conv.groups == 1 and (relu or residual is not None) and _FUSED_CONV
         if fused:
             if torch.is_grad_enabled() and (w.requires_grad or x.requires_grad):
-                return _ConvBiasReLU.apply(x, w, b, residual, conv.stride, conv.padding, conv.dilation, conv.groups)
+                leaf = conv.weight if conv.weight.requires_grad else None
+                return _ConvBiasReLU.apply(x, w, b, residual, conv.stride, conv.padding, conv.dilation, conv.groups,
+                                           leaf, cls._bn_affine(bn)[0] if leaf is not None else None)
             # cuDNN's fused conv + bias (+ residual) + ReLU epilogue (no autograd needed here)
             if residual is not None:
                 return torch.cudnn_convolution_add_relu(x, w, residual, 1.0, b, conv.stride, conv.padding,

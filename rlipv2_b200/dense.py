@@ -30,13 +30,15 @@ _OWN_BWD = os.environ.get("RLIPV2_OWN_BWD", "0") == "1"
 _FFN_BWD = os.environ.get("RLIPV2_FFN_BWD", "hybrid")
 _OWN_WGRAD = os.environ.get("RLIPV2_OWN_WGRAD", "1") != "0"
 _OWN_BWD_MIN_ROWS = int(os.environ.get("RLIPV2_OWN_BWD_MIN_ROWS", "4096"))
-# Parameter gradients of the small linears (decoders, heads, ALIF, RobertaLayer, text tower: a few hundred to ~1300 rows)
-# on a side stream.  Their backward is a chain of launch-bound 5-8 us GEMMs; only the input gradient is on the chain to
-# the next layer, the weight / bias gradient is not needed before the optimizer.  Active only when the gradient is
+# Parameter gradients on a side stream.  Only the input gradient of a layer is on the chain to the previous layer; the
+# weight / bias gradient is not needed before the optimizer.  For the small linears (decoders, heads, ALIF, RobertaLayer,
+# text tower: chains of launch-bound 5-8 us GEMMs) this halves the chain; for the encoder's 44k-token layers the weight
+# gradients fill the SMs the latency-bound MSDeformAttn backward leaves idle.  Active only when the gradient is
 # accumulated in place into the step's flat gradient buffer (`_fuse_grad`), so nothing is handed back to autograd from
 # the side stream; the train step joins it after backward() (`join_param_grad_stream`).
 _WGRAD_STREAM = os.environ.get("RLIPV2_WGRAD_STREAM", "1") != "0"
-_WGRAD_STREAM_MAX_ROWS = int(os.environ.get("RLIPV2_WGRAD_STREAM_MAX_ROWS", "4096"))
+# (measured r01s4d: every size on the side stream 28.65 vs 29.5 ms/step with only the <= 4096-row problems there)
+_WGRAD_STREAM_MAX_ROWS = int(os.environ.get("RLIPV2_WGRAD_STREAM_MAX_ROWS", str(1 << 30)))
 _param_grad_streams = {}
 _param_grad_pending = set()
 

@@ -43,7 +43,7 @@ class FrozenBatchNorm2d(nn.Module):
 
 
 _FUSED_CONV = os.environ.get("RLIPV2_FUSED_CONV", "1") != "0"      # A/B switch for measurements
-_CONV_WGRAD_STREAM = os.environ.get("RLIPV2_CONV_WGRAD_STREAM", "1") != "0"   # conv weight gradients on the side stream
+_CONV_WGRAD_STREAM = os.environ.get("RLIPV2_CONV_WGRAD_STREAM", "0") != "0"   # conv weight gradients on the side stream (measured r01s4e: 29.95 vs 29.67 ms/step without - off)
 # channels_last activations through the backbone: cuDNN's TF32 kernels are NHWC-native, so NCHW tensors cost a
 # nchwToNhwc / nhwcToNchw pair around every convolution (3.3 ms per step); with BN folded and bias / residual /
 # ReLU fused into the convolutions there is no NCHW-favouring elementwise pass left (measured: 44.0 -> 39.5 ms).

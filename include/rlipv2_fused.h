@@ -107,6 +107,19 @@ int rlipv2_sine_embed_f32(const float *pos, int rows, int n, float *out, void *s
 int rlipv2_box_pair_loss_f32(const float *src, const float *tgt, int rows, float *l1, float *giou_loss, float *dl1,
                              float *dgiou, void *stream);
 
+/* nn.GroupNorm(32, 256) of the input projections (/root/reference/models/hoi.py:1937-1952) on token-major activations:
+ * x [N, HW, 256] (what an NHWC convolution produces) -> out rows [n * out_batch_stride + hw * 256 ...], i.e. straight
+ * into this level's rows of the encoder's [N, sum HW, 256] token buffer (out points at the level's first row,
+ * out_batch_stride = sum HW * 256).  stats: scratch of N*32*2 doubles; mean / rstd [N, 32] are kept for the backward.
+ * Backward: dy addressed like `out`, dx [N, HW, 256]; dgamma / dbeta [256] are ADDED to (caller zero-fills or passes the
+ * running gradient); sums: scratch of N*32*2 doubles.  Only C = 256, G = 32 (returns ESHAPE otherwise). */
+int rlipv2_groupnorm_tokens_fwd_f32(const float *x, const float *gamma, const float *beta, float eps, int N, int HW,
+                                    int C, int G, double *stats, float *out, long long out_batch_stride, float *mean,
+                                    float *rstd, void *stream);
+int rlipv2_groupnorm_tokens_bwd_f32(const float *dy, long long dy_batch_stride, const float *x, const float *mean,
+                                    const float *rstd, const float *gamma, int N, int HW, int C, int G, double *sums,
+                                    float *dx, float *dgamma, float *dbeta, void *stream);
+
 const char *rlipv2_fused_error_string(int code);
 unsigned long long rlipv2_fused_launch_count(void);
 

@@ -331,6 +331,138 @@ box_pair_loss_kernel(const float *__restrict__ src, const float *__restrict__ tg
                                                      -0.5f * (g_a1y - g_a0y));
 }
 
+// ---- GroupNorm(32 groups, 256 channels) on token-major activations ------------------------------------------
+// The input projections of RLIP_ParSeDA (/root/reference/models/hoi.py:1937-1952: 1x1 / 3x3 conv + nn.GroupNorm(32, 256)
+// per feature level) feed the encoder, which wants tokens: [N, sum_l H_l W_l, 256].  cuDNN's TF32 convolutions produce
+// NHWC (= token-major) outputs; torch's GroupNorm converts them to NCHW, normalises, and flatten + transpose + cat
+// convert back.  These kernels normalise the token-major tensor in place of all that and write straight into the
+// level's rows of the concatenated buffer.  Thread t of a 256-thread CTA owns channels 4*(t & 63) .. +3 (a group =
+// 8 channels = two neighbouring lanes) of rows (t >> 6) + 4k of the CTA's 64-row chunk.
+constexpr int kGnC = 256, kGnG = 32, kGnRows = 64;
+
+__global__ void __launch_bounds__(256)
+gn_tok_stats_kernel(const float *__restrict__ x, int HW, double *__restrict__ stats /* [N, 32, 2] */)
+{
+    const int n = blockIdx.y, c4 = threadIdx.x & 63, r0 = threadIdx.x >> 6;
+    const int row_end = min(HW, (int)(blockIdx.x + 1) * kGnRows);
+    const float4 *xp = reinterpret_cast<const float4 *>(x + (size_t)n * HW * kGnC);
+    float s = 0.f, ss = 0.f;
+    for (int r = blockIdx.x * kGnRows + r0; r < row_end; r += 4) {
+        const float4 v = xp[(size_t)r * 64 + c4];
+        s += (v.x + v.y) + (v.z + v.w);
+        ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss))));
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    __shared__ float part[4][kGnG][2];
+    if ((c4 & 1) == 0) { part[r0][c4 >> 1][0] = s; part[r0][c4 >> 1][1] = ss; }
+    __syncthreads();
+    if (threadIdx.x < 2 * kGnG) {
+        const int g = threadIdx.x >> 1, k = threadIdx.x & 1;
+        const double v = (double)part[0][g][k] + (double)part[1][g][k] + (double)part[2][g][k] + (double)part[3][g][k];
+        atomicAdd(stats + ((size_t)n * kGnG + g) * 2 + k, v);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gn_tok_apply_kernel(const float *__restrict__ x, const double *__restrict__ stats, const float *__restrict__ gamma,
+                    const float *__restrict__ beta, float eps, int N, int HW, float *__restrict__ out,
+                    long long out_batch_stride, float *__restrict__ mean, float *__restrict__ rstd)
+{
+    const long long total = (long long)N * HW * 64;
+    const double inv_m = 1.0 / ((double)HW * 8.0);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i & 63);
+        const long long row = i >> 6;                    // n * HW + hw
+        const int n = (int)(row / HW), hw = (int)(row - (long long)n * HW), g = c4 >> 1;
+        const double mu = stats[((size_t)n * kGnG + g) * 2] * inv_m;
+        const double var = stats[((size_t)n * kGnG + g) * 2 + 1] * inv_m - mu * mu;
+        const float m = (float)mu, rs = rsqrtf((float)(var > 0.0 ? var : 0.0) + eps);
+        if (hw == 0 && (c4 & 1) == 0) { mean[n * kGnG + g] = m; rstd[n * kGnG + g] = rs; }
+        const float4 v = reinterpret_cast<const float4 *>(x)[i];
+        const float4 ga = __ldg(reinterpret_cast<const float4 *>(gamma) + c4);
+        const float4 be = __ldg(reinterpret_cast<const float4 *>(beta) + c4);
+        float4 o;
+        o.x = fmaf((v.x - m) * rs, ga.x, be.x); o.y = fmaf((v.y - m) * rs, ga.y, be.y);
+        o.z = fmaf((v.z - m) * rs, ga.z, be.z); o.w = fmaf((v.w - m) * rs, ga.w, be.w);
+        *reinterpret_cast<float4 *>(out + (size_t)n * out_batch_stride + (size_t)hw * kGnC + c4 * 4) = o;
+    }
+}
+
+// backward, pass 1: per (n, group) A = sum dy gamma xhat, B = sum dy gamma; per channel dgamma += sum dy xhat,
+// dbeta += sum dy (added into the given buffers)
+__global__ void __launch_bounds__(256)
+gn_tok_bwd_stats_kernel(const float *__restrict__ dy, long long dy_batch_stride, const float *__restrict__ x,
+                        const float *__restrict__ mean, const float *__restrict__ rstd, const float *__restrict__ gamma,
+                        int HW, double *__restrict__ sums /* [N, 32, 2] */, float *__restrict__ dgamma,
+                        float *__restrict__ dbeta)
+{
+    const int n = blockIdx.y, c4 = threadIdx.x & 63, r0 = threadIdx.x >> 6, g = c4 >> 1;
+    const int row_end = min(HW, (int)(blockIdx.x + 1) * kGnRows);
+    const float m = mean[n * kGnG + g], rs = rstd[n * kGnG + g];
+    const float4 ga = __ldg(reinterpret_cast<const float4 *>(gamma) + c4);
+    const float4 *xp = reinterpret_cast<const float4 *>(x + (size_t)n * HW * kGnC);
+    const float *dp = dy + (size_t)n * dy_batch_stride;
+    float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = blockIdx.x * kGnRows + r0; r < row_end; r += 4) {
+        const float4 v = xp[(size_t)r * 64 + c4];
+        const float4 d = *reinterpret_cast<const float4 *>(dp + (size_t)r * kGnC + c4 * 4);
+        dg.x = fmaf(d.x, (v.x - m) * rs, dg.x); dg.y = fmaf(d.y, (v.y - m) * rs, dg.y);
+        dg.z = fmaf(d.z, (v.z - m) * rs, dg.z); dg.w = fmaf(d.w, (v.w - m) * rs, dg.w);
+        db.x += d.x; db.y += d.y; db.z += d.z; db.w += d.w;
+    }
+    float A = fmaf(ga.x, dg.x, fmaf(ga.y, dg.y, fmaf(ga.z, dg.z, ga.w * dg.w)));
+    float B = fmaf(ga.x, db.x, fmaf(ga.y, db.y, fmaf(ga.z, db.z, ga.w * db.w)));
+    A += __shfl_xor_sync(0xffffffffu, A, 1);
+    B += __shfl_xor_sync(0xffffffffu, B, 1);
+    __shared__ float part[4][kGnG][2];
+    __shared__ float4 pg[4][64], pb[4][64];
+    if ((c4 & 1) == 0) { part[r0][g][0] = A; part[r0][g][1] = B; }
+    pg[r0][c4] = dg;
+    pb[r0][c4] = db;
+    __syncthreads();
+    if (threadIdx.x < 2 * kGnG) {
+        const int gg = threadIdx.x >> 1, k = threadIdx.x & 1;
+        const double v = (double)part[0][gg][k] + (double)part[1][gg][k] + (double)part[2][gg][k] + (double)part[3][gg][k];
+        atomicAdd(sums + ((size_t)n * kGnG + gg) * 2 + k, v);
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 128) {
+        const int c = threadIdx.x - 64;
+        const float4 a = pg[0][c], b = pg[1][c], cc = pg[2][c], d = pg[3][c];
+        atomicAdd(dgamma + c * 4 + 0, (a.x + b.x) + (cc.x + d.x)); atomicAdd(dgamma + c * 4 + 1, (a.y + b.y) + (cc.y + d.y));
+        atomicAdd(dgamma + c * 4 + 2, (a.z + b.z) + (cc.z + d.z)); atomicAdd(dgamma + c * 4 + 3, (a.w + b.w) + (cc.w + d.w));
+    } else if (threadIdx.x >= 128 && threadIdx.x < 192) {
+        const int c = threadIdx.x - 128;
+        const float4 a = pb[0][c], b = pb[1][c], cc = pb[2][c], d = pb[3][c];
+        atomicAdd(dbeta + c * 4 + 0, (a.x + b.x) + (cc.x + d.x)); atomicAdd(dbeta + c * 4 + 1, (a.y + b.y) + (cc.y + d.y));
+        atomicAdd(dbeta + c * 4 + 2, (a.z + b.z) + (cc.z + d.z)); atomicAdd(dbeta + c * 4 + 3, (a.w + b.w) + (cc.w + d.w));
+    }
+}
+
+// backward, pass 2: dx = rstd * (dy gamma - (B + xhat A) / m)
+__global__ void __launch_bounds__(256)
+gn_tok_bwd_apply_kernel(const float *__restrict__ dy, long long dy_batch_stride, const float *__restrict__ x,
+                        const float *__restrict__ mean, const float *__restrict__ rstd, const float *__restrict__ gamma,
+                        const double *__restrict__ sums, int N, int HW, float *__restrict__ dx)
+{
+    const long long total = (long long)N * HW * 64;
+    const float inv_m = 1.f / ((float)HW * 8.f);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i & 63);
+        const long long row = i >> 6;
+        const int n = (int)(row / HW), hw = (int)(row - (long long)n * HW), g = c4 >> 1;
+        const float m = mean[n * kGnG + g], rs = rstd[n * kGnG + g];
+        const float A = (float)sums[((size_t)n * kGnG + g) * 2] * inv_m, B = (float)sums[((size_t)n * kGnG + g) * 2 + 1] * inv_m;
+        const float4 v = reinterpret_cast<const float4 *>(x)[i];
+        const float4 d = *reinterpret_cast<const float4 *>(dy + (size_t)n * dy_batch_stride + (size_t)hw * kGnC + c4 * 4);
+        const float4 ga = __ldg(reinterpret_cast<const float4 *>(gamma) + c4);
+        float4 o;
+        o.x = rs * (d.x * ga.x - fmaf((v.x - m) * rs, A, B)); o.y = rs * (d.y * ga.y - fmaf((v.y - m) * rs, A, B));
+        o.z = rs * (d.z * ga.z - fmaf((v.z - m) * rs, A, B)); o.w = rs * (d.w * ga.w - fmaf((v.w - m) * rs, A, B));
+        reinterpret_cast<float4 *>(dx)[i] = o;
+    }
+}
+
 // Sine embedding of anchor coordinates (gen_sineembed_for_position, deformable_transformer.py:1777-1802):
 // pos [R, n] (x, y[, w, h]) -> out [R, n*128] in the order (y, x[, w, h]); feature k of a coordinate p is
 // sin(2 pi p / T_k) for even k, cos(2 pi p / T_k) for odd k, T_k = 10000^(2 floor(k/2) / 128).
@@ -513,6 +645,47 @@ int rlipv2_box_pair_loss_f32(const float *src, const float *tgt, int rows, float
     if (!src || !tgt || !l1 || !giou_loss || !dl1 || !dgiou || rows < 0) return RLIPV2_FUSED_EINVAL;
     if (((uintptr_t)src | (uintptr_t)tgt | (uintptr_t)dl1 | (uintptr_t)dgiou) & 15) return RLIPV2_FUSED_EINVAL;
     box_pair_loss_kernel<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(src, tgt, rows, l1, giou_loss, dl1, dgiou);
+    return done();
+}
+
+int rlipv2_groupnorm_tokens_fwd_f32(const float *x, const float *gamma, const float *beta, float eps, int N, int HW,
+                                    int C, int G, double *stats, float *out, long long out_batch_stride, float *mean,
+                                    float *rstd, void *stream)
+{
+    if (N == 0 || HW == 0) return 0;
+    if (C != kGnC || G != kGnG) return RLIPV2_FUSED_ESHAPE;
+    if (!x || !gamma || !beta || !stats || !out || !mean || !rstd || N < 0 || HW < 0 || (out_batch_stride & 3))
+        return RLIPV2_FUSED_EINVAL;
+    if (((uintptr_t)x | (uintptr_t)out | (uintptr_t)gamma | (uintptr_t)beta) & 15) return RLIPV2_FUSED_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)N * kGnG * 2 * sizeof(double), s);
+    if (e != cudaSuccess) return (int)e;
+    gn_tok_stats_kernel<<<dim3((HW + kGnRows - 1) / kGnRows, N), 256, 0, s>>>(x, HW, stats);
+    long long blocks = ((long long)N * HW * 64 + 255) / 256;
+    if (blocks > kSMs * 16) blocks = kSMs * 16;
+    gn_tok_apply_kernel<<<(int)blocks, 256, 0, s>>>(x, stats, gamma, beta, eps, N, HW, out, out_batch_stride, mean, rstd);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return done();
+}
+
+int rlipv2_groupnorm_tokens_bwd_f32(const float *dy, long long dy_batch_stride, const float *x, const float *mean,
+                                    const float *rstd, const float *gamma, int N, int HW, int C, int G, double *sums,
+                                    float *dx, float *dgamma, float *dbeta, void *stream)
+{
+    if (N == 0 || HW == 0) return 0;
+    if (C != kGnC || G != kGnG) return RLIPV2_FUSED_ESHAPE;
+    if (!dy || !x || !mean || !rstd || !gamma || !sums || !dx || !dgamma || !dbeta || N < 0 || HW < 0 || (dy_batch_stride & 3))
+        return RLIPV2_FUSED_EINVAL;
+    if (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)gamma) & 15) return RLIPV2_FUSED_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)N * kGnG * 2 * sizeof(double), s);
+    if (e != cudaSuccess) return (int)e;
+    gn_tok_bwd_stats_kernel<<<dim3((HW + kGnRows - 1) / kGnRows, N), 256, 0, s>>>(dy, dy_batch_stride, x, mean, rstd, gamma,
+                                                                                HW, sums, dgamma, dbeta);
+    long long blocks = ((long long)N * HW * 64 + 255) / 256;
+    if (blocks > kSMs * 16) blocks = kSMs * 16;
+    gn_tok_bwd_apply_kernel<<<(int)blocks, 256, 0, s>>>(dy, dy_batch_stride, x, mean, rstd, gamma, sums, N, HW, dx);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return done();
 }
 

@@ -337,6 +337,73 @@ def add_layer_norm(x, residual, weight, bias, eps):
     return F.layer_norm(x + residual, (x.shape[-1],), weight, bias, eps)
 
 
+# ---- input projections: GroupNorm on token-major activations, all feature levels into one token buffer -------------
+_GN_TOKENS = os.environ.get("RLIPV2_GN_TOKENS", "1") != "0"
+
+
+class _GroupNormTokensMulti(torch.autograd.Function):
+    """[x_l: conv outputs [N, 256, H_l, W_l] in channels_last memory] -> GroupNorm(32) of each, written as rows of one
+    [N, sum_l H_l W_l, 256] tensor (what `src.flatten(2).transpose(1, 2)` + `torch.cat` builds in the reference,
+    dab_deformable/deformable_transformer.py:452-470) - csrc/fused_ops.cu gn_tok_* kernels."""
+
+    @staticmethod
+    def forward(ctx, eps, n_levels, *args):
+        f = _fused()
+        xs, gammas, betas = args[:n_levels], args[n_levels:2 * n_levels], args[2 * n_levels:]
+        N, C = xs[0].shape[:2]
+        hws = [x.shape[2] * x.shape[3] for x in xs]
+        S = sum(hws)
+        out = torch.empty((N, S, C), dtype=torch.float32, device=xs[0].device)
+        saved, start = [], 0
+        for x, g, b, hw in zip(xs, gammas, betas, hws):
+            xt = x.permute(0, 2, 3, 1)                         # [N, H, W, C]: contiguous for channels_last tensors
+            xt = (xt if xt.is_contiguous() else xt.contiguous()).view(N, hw, C)
+            mean, rstd = f.groupnorm_tokens_fwd(xt, g, b, eps, out[:, start], S * C)
+            saved += [xt, mean, rstd, g]
+            start += hw
+        ctx.save_for_backward(*saved)
+        ctx.meta = (n_levels, N, C, S, [tuple(x.shape) for x in xs], hws)
+        ctx.params = (gammas, betas)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        f = _fused()
+        n_levels, N, C, S, shapes, hws = ctx.meta
+        saved = ctx.saved_tensors
+        dy = dy if dy.is_contiguous() else dy.contiguous()
+        gammas, betas = ctx.params
+        dxs, dgs, dbs, start = [], [], [], 0
+        for l in range(n_levels):
+            xt, mean, rstd, g = saved[4 * l:4 * l + 4]
+            gp, bp = gammas[l], betas[l]
+            fuse = (getattr(gp, "_fuse_grad", False) and getattr(bp, "_fuse_grad", False) and gp.grad is not None
+                    and bp.grad is not None and gp.grad.is_contiguous() and bp.grad.is_contiguous())
+            dg = gp.grad if fuse else torch.zeros(C, dtype=torch.float32, device=dy.device)
+            db = bp.grad if fuse else torch.zeros(C, dtype=torch.float32, device=dy.device)
+            dx = f.groupnorm_tokens_bwd(dy[:, start], S * C, xt, mean, rstd, g, dg, db)
+            _, _, H, W = shapes[l]
+            dxs.append(dx.view(N, H, W, C).permute(0, 3, 1, 2))
+            dgs.append(None if fuse else dg)
+            dbs.append(None if fuse else db)
+            start += hws[l]
+        return (None, None) + tuple(dxs) + tuple(dgs) + tuple(dbs)
+
+
+def group_norm_tokens_supported(xs, norms):
+    return (_GN_TOKENS and _USE_FUSED and all(x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 256
+                                             for x in xs)
+            and all(isinstance(n, torch.nn.GroupNorm) and n.num_groups == 32 and n.num_channels == 256 and n.affine
+                    for n in norms))
+
+
+def group_norm_tokens(xs, norms):
+    """GroupNorm(32, 256) of every level's projected feature map, flattened to tokens and concatenated: [N, S, 256]"""
+    eps = norms[0].eps
+    assert all(n.eps == eps for n in norms)
+    return _GroupNormTokensMulti.apply(eps, len(xs), *xs, *[n.weight for n in norms], *[n.bias for n in norms])
+
+
 # ---- DAB decoder small-op chains (csrc/fused_ops.cu: box_refine_kernel, sine_embed_kernel) ---------------------
 _SMALL_OPS = os.environ.get("RLIPV2_SMALL_OPS", "1") != "0"
 

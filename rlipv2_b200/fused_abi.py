@@ -33,6 +33,10 @@ _lib.rlipv2_box_refine_f32.argtypes = [_p, _p, _f, _ll, _p, _p]
 _lib.rlipv2_sine_embed_f32.argtypes = [_p, _i, _i, _p, _p]
 _lib.rlipv2_box_pair_loss_f32.argtypes = [_p, _p, _i, _p, _p, _p, _p, _p]
 _lib.rlipv2_box_pair_loss_f32.restype = _i
+_lib.rlipv2_groupnorm_tokens_fwd_f32.argtypes = [_p, _p, _p, _f, _i, _i, _i, _i, _p, _p, _ll, _p, _p, _p]
+_lib.rlipv2_groupnorm_tokens_fwd_f32.restype = _i
+_lib.rlipv2_groupnorm_tokens_bwd_f32.argtypes = [_p, _ll, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]
+_lib.rlipv2_groupnorm_tokens_bwd_f32.restype = _i
 for _n in ("wait_host_flag", "box_refine_f32", "sine_embed_f32"):
     getattr(_lib, "rlipv2_" + _n).restype = _i
 for _n in ("add_layernorm_fwd_f32", "layernorm_bwd_f32", "relu_bwd_colsum_f32", "adamw_f32", "gather_chunks_f32", "rowmask_bwd_colsum_f32"):
@@ -43,7 +47,7 @@ _lib.rlipv2_fused_launch_count.restype = ctypes.c_ulonglong
 
 EXPORTS = ("rlipv2_add_layernorm_fwd_f32", "rlipv2_layernorm_bwd_f32", "rlipv2_relu_bwd_colsum_f32",
            "rlipv2_adamw_f32", "rlipv2_adamw_scaled_f32", "rlipv2_gather_chunks_f32", "rlipv2_rowmask_bwd_colsum_f32", "rlipv2_wait_host_flag",
-           "rlipv2_box_refine_f32", "rlipv2_sine_embed_f32", "rlipv2_box_pair_loss_f32", "rlipv2_stamp_globaltimer", "rlipv2_layernorm_bwd_acc_f32",
+           "rlipv2_box_refine_f32", "rlipv2_sine_embed_f32", "rlipv2_box_pair_loss_f32", "rlipv2_groupnorm_tokens_fwd_f32", "rlipv2_groupnorm_tokens_bwd_f32", "rlipv2_stamp_globaltimer", "rlipv2_layernorm_bwd_acc_f32",
            "rlipv2_relu_bwd_colsum_acc_f32", "rlipv2_rowmask_bwd_colsum_acc_f32", "rlipv2_fused_error_string", "rlipv2_fused_launch_count")
 
 
@@ -201,6 +205,36 @@ def box_pair_loss(src, tgt):
                                            dl1.data_ptr(), dgl.data_ptr(), _stream())
     _check(rc, "rlipv2_box_pair_loss_f32")
     return l1, gl, dl1, dgl
+
+
+def groupnorm_tokens_fwd(x_tok, gamma, beta, eps, out_rows, out_batch_stride, groups=32):
+    """x_tok [N, HW, C] contiguous fp32 CUDA -> writes GroupNorm(x) into `out_rows` (a view whose data_ptr is the
+    level's first row of a [N, S, C] buffer; rows of image n start at n * out_batch_stride elements).
+    -> (mean [N, G], rstd [N, G])"""
+    N, HW, C = x_tok.shape
+    stats = torch.empty((N, groups, 2), dtype=torch.float64, device=x_tok.device)
+    mean = torch.empty((N, groups), dtype=torch.float32, device=x_tok.device)
+    rstd = torch.empty_like(mean)
+    with torch.cuda.device(x_tok.device):
+        rc = _lib.rlipv2_groupnorm_tokens_fwd_f32(x_tok.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, N, HW, C, groups,
+                                                  stats.data_ptr(), out_rows.data_ptr(), out_batch_stride, mean.data_ptr(),
+                                                  rstd.data_ptr(), _stream())
+    _check(rc, "rlipv2_groupnorm_tokens_fwd_f32")
+    return mean, rstd
+
+
+def groupnorm_tokens_bwd(dy_rows, dy_batch_stride, x_tok, mean, rstd, gamma, dgamma, dbeta, groups=32):
+    """dy_rows: view at the level's first row of the [N, S, C] output gradient; dgamma / dbeta [C] are added to.
+    -> dx [N, HW, C]"""
+    N, HW, C = x_tok.shape
+    sums = torch.empty((N, groups, 2), dtype=torch.float64, device=x_tok.device)
+    dx = torch.empty_like(x_tok)
+    with torch.cuda.device(x_tok.device):
+        rc = _lib.rlipv2_groupnorm_tokens_bwd_f32(dy_rows.data_ptr(), dy_batch_stride, x_tok.data_ptr(), mean.data_ptr(),
+                                                  rstd.data_ptr(), gamma.data_ptr(), N, HW, C, groups, sums.data_ptr(),
+                                                  dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _stream())
+    _check(rc, "rlipv2_groupnorm_tokens_bwd_f32")
+    return dx
 
 
 def sine_embed(pos2d):

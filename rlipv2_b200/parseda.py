@@ -21,6 +21,11 @@ from .parseda_transformer import MLP
 
 
 _TEXT_STREAM = os.environ.get("RLIPV2_TEXT_STREAM", "1") != "0"      # A/B switch for measurements
+class FlatLevels(list):
+    """per-level [N, C, H, W] views of one token buffer `flat` [N, sum HW, C] (the transformer takes `flat` as is)"""
+    flat = None
+
+
 _STACKED_HEADS = os.environ.get("RLIPV2_STACKED_HEADS", "1") != "0"  # label-text heads of all decoder levels in one pass
 
 
@@ -101,16 +106,37 @@ class RLIP_ParSeDA(nn.Module):
             text = self.transformer.encode_text_async(text, samples.tensors.device)   # overlaps the backbone
         features, pos = self.backbone(samples)
         srcs, masks = [], []
-        for l, feat in enumerate(features):
-            src, mask = feat.decompose()
-            srcs.append(self.input_proj[l](src))
-            masks.append(mask)
-        for l in range(len(srcs), self.num_feature_levels):
-            src = self.input_proj[l](features[-1].tensors if l == len(features) else srcs[-1])
-            mask = F.interpolate(samples.mask[None].float(), size=src.shape[-2:]).to(torch.bool)[0]
-            pos.append(self.backbone[1](NestedTensor(src, mask)).to(src.dtype))
-            srcs.append(src)
-            masks.append(mask)
+        norms = [p[1] for p in self.input_proj]
+        if (self.num_feature_levels <= len(features) + 1
+                and dense.group_norm_tokens_supported([f.tensors for f in features], norms)):
+            # GPU path: the projections' convolutions (cuDNN, NHWC outputs), then ONE fused op that applies every
+            # level's GroupNorm on the token-major data and writes the encoder's [N, sum HW, 256] token buffer directly
+            # (no NCHW round trip, no flatten / transpose / cat copies); `srcs` are views of that buffer
+            convs = [self.input_proj[l][0](feat.tensors) for l, feat in enumerate(features)]
+            masks = [feat.mask for feat in features]
+            for l in range(len(features), self.num_feature_levels):
+                convs.append(self.input_proj[l][0](features[-1].tensors))
+                mask = F.interpolate(samples.mask[None].float(), size=convs[-1].shape[-2:]).to(torch.bool)[0]
+                pos.append(self.backbone[1](NestedTensor(convs[-1], mask)).to(convs[-1].dtype))
+                masks.append(mask)
+            flat = dense.group_norm_tokens(convs, norms[:len(convs)])
+            srcs, start = FlatLevels(), 0
+            for c in convs:
+                n_, ch, h, w = c.shape
+                srcs.append(flat[:, start:start + h * w].view(n_, h, w, ch).permute(0, 3, 1, 2))
+                start += h * w
+            srcs.flat = flat
+        else:
+            for l, feat in enumerate(features):
+                src, mask = feat.decompose()
+                srcs.append(self.input_proj[l](src))
+                masks.append(mask)
+            for l in range(len(srcs), self.num_feature_levels):
+                src = self.input_proj[l](features[-1].tensors if l == len(features) else srcs[-1])
+                mask = F.interpolate(samples.mask[None].float(), size=src.shape[-2:]).to(torch.bool)[0]
+                pos.append(self.backbone[1](NestedTensor(src, mask)).to(src.dtype))
+                srcs.append(src)
+                masks.append(mask)
         query_embeds = torch.cat((self.tgt_embed.weight, self.verb_tgt_embed.weight, self.refpoint_embed.weight), dim=1)
         return self.transformer(srcs=srcs, masks=masks, pos_embeds=pos, query_embed=query_embeds, text=text,
                                 encode_and_save=True)

@@ -596,7 +596,9 @@ class RLIP_ParSeDABDeformableTransformer_v2(nn.Module):
             src_flatten.append(src.flatten(2).transpose(1, 2))
             mask_flatten.append(mask.flatten(1))
             lvl_pos_flatten.append(pos_embed.flatten(2).transpose(1, 2) + self.level_embed[lvl].view(1, 1, -1))
-        src_flatten = torch.cat(src_flatten, 1)
+        # levels that are already rows of one token buffer (parseda.py FlatLevels) need no concatenation
+        pre_flat = getattr(srcs, "flat", None)
+        src_flatten = pre_flat if pre_flat is not None else torch.cat(src_flatten, 1)
         mask_flatten = torch.cat(mask_flatten, 1)
         lvl_pos_flatten = torch.cat(lvl_pos_flatten, 1)
         device = src_flatten.device

@@ -84,3 +84,50 @@ def test_flat_adamw_grad_scale_equals_prescaled_gradient():
         res.append((p, m, v))
     for a, b in zip(*res):
         assert torch.equal(a, b)          # the same fp32 product, formed in the kernel instead of by torch
+
+
+@pytest.mark.parametrize("channels_last", [True, False])
+@pytest.mark.parametrize("fuse", [False, True])
+def test_group_norm_tokens_matches_torch(channels_last, fuse):
+    """dense.group_norm_tokens (csrc/fused_ops.cu gn_tok_*): GroupNorm(32, 256) of every feature level written as rows
+    of one [N, sum HW, 256] token tensor == F.group_norm + flatten(2).transpose(1, 2) + cat (the reference's input
+    projections + dab_deformable/deformable_transformer.py:452-470), forward and backward"""
+    from rlipv2_b200 import dense
+    torch.manual_seed(3)
+    N = 2
+    sizes = [(25, 42), (13, 21), (7, 11), (1, 3)]             # HW = 1050, 273, 77, 3: chunk tails, tiny level
+    norms = [torch.nn.GroupNorm(32, 256).cuda() for _ in sizes]
+    for n in norms:
+        with torch.no_grad():
+            n.weight.uniform_(0.5, 1.5)
+            n.bias.normal_()
+    xs = []
+    for h, w in sizes:
+        x = torch.randn(N, 256, h, w, device="cuda") * 2 + 0.7
+        if channels_last:
+            x = x.contiguous(memory_format=torch.channels_last)
+        xs.append(x.requires_grad_(True))
+    assert dense.group_norm_tokens_supported(xs, norms)
+    S = sum(h * w for h, w in sizes)
+    go = torch.randn(N, S, 256, device="cuda")
+    # reference formulation in fp64
+    xr = [x.detach().double().requires_grad_(True) for x in xs]
+    pr = [(n.weight.detach().double().requires_grad_(True), n.bias.detach().double().requires_grad_(True)) for n in norms]
+    ref = torch.cat([torch.nn.functional.group_norm(x, 32, w, b, n.eps).flatten(2).transpose(1, 2)
+                     for x, (w, b), n in zip(xr, pr, norms)], 1)
+    ref.backward(go.double())
+    if fuse:
+        for n in norms:
+            for p in (n.weight, n.bias):
+                p.grad = torch.full_like(p, 0.25)
+                p._fuse_grad = True
+    out = dense.group_norm_tokens(xs, norms)
+    assert out.shape == (N, S, 256) and out.is_contiguous()
+    out.backward(go)
+    torch.testing.assert_close(out.double(), ref, rtol=1e-4, atol=1e-4)
+    for x, r in zip(xs, xr):
+        torch.testing.assert_close(x.grad.double(), r.grad, rtol=1e-3, atol=1e-4 * float(r.grad.abs().max()) + 1e-6)
+    for n, (w, b) in zip(norms, pr):
+        off = 0.25 if fuse else 0.0
+        torch.testing.assert_close(n.weight.grad.double() - off, w.grad, rtol=1e-3, atol=1e-4 * float(w.grad.abs().max()))
+        torch.testing.assert_close(n.bias.grad.double() - off, b.grad, rtol=1e-3, atol=1e-4 * float(b.grad.abs().max()))

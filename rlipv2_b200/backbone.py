@@ -43,6 +43,7 @@ class FrozenBatchNorm2d(nn.Module):
 
 
 _FUSED_CONV = os.environ.get("RLIPV2_FUSED_CONV", "1") != "0"      # A/B switch for measurements
+_POS_STREAM = os.environ.get("RLIPV2_POS_STREAM", "1") != "0"       # masks + position embeddings beside the backbone
 _CONV_WGRAD_STREAM = os.environ.get("RLIPV2_CONV_WGRAD_STREAM", "0") != "0"   # conv weight gradients on the side stream (measured r01s4e: 29.95 vs 29.67 ms/step without - off)
 # channels_last activations through the backbone: cuDNN's TF32 kernels are NHWC-native, so NCHW tensors cost a
 # nchwToNhwc / nhwcToNchw pair around every convolution (3.3 ms per step); with BN folded and bias / residual /
@@ -256,13 +257,15 @@ class Backbone(nn.Module):
                 outs[body.return_layers[name]] = x
         return outs
 
-    def forward(self, tensor_list: NestedTensor) -> Dict[str, NestedTensor]:
+    def forward(self, tensor_list: NestedTensor, defer_masks: bool = False) -> Dict[str, NestedTensor]:
         xs = self._forward_folded(tensor_list.tensors) if self.fold_bn else self.body(tensor_list.tensors)
         out = {}
         for name, x in xs.items():
             m = tensor_list.mask
             assert m is not None
-            mask = F.interpolate(m[None].float(), size=x.shape[-2:]).to(torch.bool)[0]
+            # `defer_masks` (Joiner on a GPU): the masks only need the feature maps' shapes, so the caller forms them
+            # (and the position embeddings) on a side stream beside the convolutions
+            mask = None if defer_masks else F.interpolate(m[None].float(), size=x.shape[-2:]).to(torch.bool)[0]
             out[name] = NestedTensor(x, mask)
         return out
 
@@ -276,6 +279,27 @@ class Joiner(nn.Sequential):
         self.num_channels = backbone.num_channels
 
     def forward(self, tensor_list: NestedTensor):
+        x_in = tensor_list.tensors
+        if _POS_STREAM and x_in.is_cuda and isinstance(self[0], Backbone):
+            # The per-level padding masks and sine position embeddings (position_encoding.py:22-58: ~30 small kernels
+            # per level, no gradients) depend on the input mask and on the feature maps' SHAPES only.  They are issued
+            # on a side stream that forks before the backbone's convolutions and joins after them.
+            cur = torch.cuda.current_stream(x_in.device)
+            if getattr(self, "_pos_stream", None) is None:
+                self._pos_stream = torch.cuda.Stream(x_in.device)
+            side = self._pos_stream
+            side.wait_stream(cur)                               # fork point: before the convolutions are issued
+            xs = self[0](tensor_list, defer_masks=True)
+            out = [x for _, x in sorted(xs.items())]
+            with torch.cuda.stream(side):
+                m = tensor_list.mask[None].float()
+                for x in out:
+                    x.mask = F.interpolate(m, size=x.tensors.shape[-2:]).to(torch.bool)[0]
+                pos = [self[1](x).to(x.tensors.dtype) for x in out]
+            cur.wait_stream(side)
+            for t in [x.mask for x in out] + pos:
+                t.record_stream(cur)
+            return out, pos
         xs = self[0](tensor_list)
         out: List[NestedTensor] = [x for _, x in sorted(xs.items())]
         pos = [self[1](x).to(x.tensors.dtype) for x in out]

@@ -120,6 +120,20 @@ int rlipv2_groupnorm_tokens_bwd_f32(const float *dy, long long dy_batch_stride, 
                                     const float *rstd, const float *gamma, int N, int HW, int C, int G, double *sums,
                                     float *dx, float *dgamma, float *dbeta, void *stream);
 
+/* Multi-head attention over very short sequences (T <= 8 tokens, head dim 64): the self-attention of the text tower's
+ * RoBERTa layers on the label strings (HF transformers modeling_roberta.eager_attention_forward: scores = q k^T * scale
+ * + mask, softmax, dropout, probs v; called through /root/reference/models/dab_deformable/deformable_transformer.py:497-502).
+ * q, k, v, out, grad_out, dq, dk, dv: [B, T, H, 64] (the layout of the projections); mask: additive [B, T] over the keys
+ * or NULL; dropout_p in [0, 1): kept elements are scaled by 1 / (1 - p), the keep decision is a hash of (*seed, salt,
+ * element) - `seed` is a device int64, `salt` distinguishes call sites; the forward stores the seed it read in
+ * *seed_used (may be NULL) and the backward must be given that value to regenerate the mask. */
+int rlipv2_short_attention_fwd_f32(const float *q, const float *k, const float *v, const float *mask, int B, int H, int T,
+                                   int D, float scale, double dropout_p, const long long *seed, unsigned salt, float *out,
+                                   long long *seed_used, void *stream);
+int rlipv2_short_attention_bwd_f32(const float *q, const float *k, const float *v, const float *mask, const float *grad_out,
+                                   int B, int H, int T, int D, float scale, double dropout_p, const long long *seed,
+                                   unsigned salt, float *dq, float *dk, float *dv, void *stream);
+
 const char *rlipv2_fused_error_string(int code);
 unsigned long long rlipv2_fused_launch_count(void);
 

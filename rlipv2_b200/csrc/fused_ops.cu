@@ -331,6 +331,146 @@ box_pair_loss_kernel(const float *__restrict__ src, const float *__restrict__ tg
                                                      -0.5f * (g_a1y - g_a0y));
 }
 
+// ---- attention over very short sequences (the text tower's label strings: 3-8 tokens) ---------------------------
+// HF RobertaSelfAttention's eager path (transformers modeling_roberta.eager_attention_forward, called by the reference at
+// /root/reference/models/dab_deformable/deformable_transformer.py:497-502 for every label string, every step) issues
+// bmm + scale + mask add + softmax + dropout + bmm + transpose copy per layer - 7 launches forward, ~10 backward, for
+// 256 x 12 problems of 5 x 5 scores; the batched-GEMM kernels alone take 37 + 9 us.  Here one warp owns one
+// (label, head): q, k, v [T <= 8, 64] go to shared memory, lane (i, j) forms score (i, j), lane i the softmax of row i,
+// and every lane two of the 64 output channels.  Inputs / outputs are addressed as [B, T, H, 64] (the layout the
+// q/k/v projections produce and the output projection consumes): no transposes.  Dropout keeps an element when a
+// splitmix64 hash of (seed, salt, element index) clears the threshold; the backward regenerates the same mask.
+constexpr int kSaT = 8, kSaD = 64, kSaWarps = 4;
+
+__device__ __forceinline__ bool sa_keep(unsigned long long seed, unsigned salt, unsigned idx, unsigned thresh) {
+    unsigned long long z = seed * 0x9E3779B97F4A7C15ull + ((unsigned long long)salt << 32 | idx) + 0xD1B54A32D192ED03ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (unsigned)(z >> 32) >= thresh;
+}
+
+struct SaSmem {
+    float q[kSaT][kSaD], k[kSaT][kSaD], v[kSaT][kSaD], g[kSaT][kSaD];
+    float p[kSaT][kSaT], pd[kSaT][kSaT], ds[kSaT][kSaT];
+};
+
+// scores -> softmax probabilities p and dropped / rescaled probabilities pd, both in shared memory
+__device__ __forceinline__ void sa_probs(SaSmem &sm, const float *__restrict__ mask, int b, int h, int H, int T, int lane,
+                                         float scale, unsigned thresh, float inv_keep, unsigned long long seed,
+                                         unsigned salt)
+{
+    for (int e = lane; e < T * T; e += 32) {
+        const int i = e / T, j = e - i * T;
+        float acc = 0.f;
+#pragma unroll 16
+        for (int d = 0; d < kSaD; ++d) acc = fmaf(sm.q[i][(d + lane) & 63], sm.k[j][(d + lane) & 63], acc);
+        sm.p[i][j] = acc * scale + (mask ? mask[(size_t)b * T + j] : 0.f);
+    }
+    __syncwarp();
+    if (lane < T) {
+        const int i = lane;
+        float mx = -INFINITY;
+        for (int j = 0; j < T; ++j) mx = fmaxf(mx, sm.p[i][j]);
+        float e[kSaT], sum = 0.f;
+        for (int j = 0; j < T; ++j) { e[j] = expf(sm.p[i][j] - mx); sum += e[j]; }
+        for (int j = 0; j < T; ++j) {
+            const float pr = __fdiv_rn(e[j], sum);
+            sm.p[i][j] = pr;
+            bool keep = true;
+            if (thresh) keep = sa_keep(seed, salt, (unsigned)(((b * H + h) * kSaT + i) * kSaT + j), thresh);
+            sm.pd[i][j] = keep ? pr * inv_keep : 0.f;
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kSaWarps * 32)
+short_attn_fwd_kernel(const float *__restrict__ q, const float *__restrict__ k, const float *__restrict__ v,
+                      const float *__restrict__ mask, int B, int H, int T, float scale, unsigned thresh, float inv_keep,
+                      const long long *__restrict__ seed_ptr, unsigned salt, float *__restrict__ out,
+                      long long *__restrict__ seed_used)
+{
+    __shared__ SaSmem smem[kSaWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bh = blockIdx.x * kSaWarps + warp;
+    const unsigned long long seed = seed_ptr ? (unsigned long long)*seed_ptr : 0ull;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && seed_used) *seed_used = (long long)seed;
+    if (bh >= B * H) return;
+    const int b = bh / H, h = bh - b * H;
+    SaSmem &sm = smem[warp];
+    for (int t = 0; t < T; ++t) {
+        const size_t base = (((size_t)b * T + t) * H + h) * kSaD + lane * 2;
+        *reinterpret_cast<float2 *>(&sm.q[t][lane * 2]) = *reinterpret_cast<const float2 *>(q + base);
+        *reinterpret_cast<float2 *>(&sm.k[t][lane * 2]) = *reinterpret_cast<const float2 *>(k + base);
+        *reinterpret_cast<float2 *>(&sm.v[t][lane * 2]) = *reinterpret_cast<const float2 *>(v + base);
+    }
+    __syncwarp();
+    sa_probs(sm, mask, b, h, H, T, lane, scale, thresh, inv_keep, seed, salt);
+    for (int i = 0; i < T; ++i) {
+        float2 o = make_float2(0.f, 0.f);
+        for (int j = 0; j < T; ++j) {
+            const float w = sm.pd[i][j];
+            o.x = fmaf(w, sm.v[j][lane * 2], o.x);
+            o.y = fmaf(w, sm.v[j][lane * 2 + 1], o.y);
+        }
+        *reinterpret_cast<float2 *>(out + (((size_t)b * T + i) * H + h) * kSaD + lane * 2) = o;
+    }
+}
+
+__global__ void __launch_bounds__(kSaWarps * 32)
+short_attn_bwd_kernel(const float *__restrict__ q, const float *__restrict__ k, const float *__restrict__ v,
+                      const float *__restrict__ mask, const float *__restrict__ gout, int B, int H, int T, float scale,
+                      unsigned thresh, float inv_keep, const long long *__restrict__ seed_ptr, unsigned salt,
+                      float *__restrict__ dq, float *__restrict__ dk, float *__restrict__ dv)
+{
+    __shared__ SaSmem smem[kSaWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bh = blockIdx.x * kSaWarps + warp;
+    if (bh >= B * H) return;
+    const unsigned long long seed = seed_ptr ? (unsigned long long)*seed_ptr : 0ull;
+    const int b = bh / H, h = bh - b * H;
+    SaSmem &sm = smem[warp];
+    for (int t = 0; t < T; ++t) {
+        const size_t base = (((size_t)b * T + t) * H + h) * kSaD + lane * 2;
+        *reinterpret_cast<float2 *>(&sm.q[t][lane * 2]) = *reinterpret_cast<const float2 *>(q + base);
+        *reinterpret_cast<float2 *>(&sm.k[t][lane * 2]) = *reinterpret_cast<const float2 *>(k + base);
+        *reinterpret_cast<float2 *>(&sm.v[t][lane * 2]) = *reinterpret_cast<const float2 *>(v + base);
+        *reinterpret_cast<float2 *>(&sm.g[t][lane * 2]) = *reinterpret_cast<const float2 *>(gout + base);
+    }
+    __syncwarp();
+    sa_probs(sm, mask, b, h, H, T, lane, scale, thresh, inv_keep, seed, salt);
+    // d pd (i, j) = <gout_i, v_j>; through the dropout: d p = d pd * (pd / p) (0 where dropped)
+    for (int e = lane; e < T * T; e += 32) {
+        const int i = e / T, j = e - i * T;
+        float acc = 0.f;
+#pragma unroll 16
+        for (int d = 0; d < kSaD; ++d) acc = fmaf(sm.g[i][(d + lane) & 63], sm.v[j][(d + lane) & 63], acc);
+        sm.ds[i][j] = sm.pd[i][j] != 0.f ? acc * inv_keep : 0.f;          // = d p (i, j)
+    }
+    __syncwarp();
+    if (lane < T) {                                                        // softmax backward of row `lane`
+        const int i = lane;
+        float dot = 0.f;
+        for (int j = 0; j < T; ++j) dot = fmaf(sm.ds[i][j], sm.p[i][j], dot);
+        for (int j = 0; j < T; ++j) sm.ds[i][j] = sm.p[i][j] * (sm.ds[i][j] - dot);
+    }
+    __syncwarp();
+    for (int t = 0; t < T; ++t) {
+        float2 aq = make_float2(0.f, 0.f), ak = make_float2(0.f, 0.f), av = make_float2(0.f, 0.f);
+        for (int u = 0; u < T; ++u) {
+            const float s_tu = sm.ds[t][u], s_ut = sm.ds[u][t], p_ut = sm.pd[u][t];
+            aq.x = fmaf(s_tu, sm.k[u][lane * 2], aq.x); aq.y = fmaf(s_tu, sm.k[u][lane * 2 + 1], aq.y);
+            ak.x = fmaf(s_ut, sm.q[u][lane * 2], ak.x); ak.y = fmaf(s_ut, sm.q[u][lane * 2 + 1], ak.y);
+            av.x = fmaf(p_ut, sm.g[u][lane * 2], av.x); av.y = fmaf(p_ut, sm.g[u][lane * 2 + 1], av.y);
+        }
+        const size_t base = (((size_t)b * T + t) * H + h) * kSaD + lane * 2;
+        *reinterpret_cast<float2 *>(dq + base) = make_float2(aq.x * scale, aq.y * scale);
+        *reinterpret_cast<float2 *>(dk + base) = make_float2(ak.x * scale, ak.y * scale);
+        *reinterpret_cast<float2 *>(dv + base) = av;
+    }
+}
+
 // ---- GroupNorm(32 groups, 256 channels) on token-major activations ------------------------------------------
 // The input projections of RLIP_ParSeDA (/root/reference/models/hoi.py:1937-1952: 1x1 / 3x3 conv + nn.GroupNorm(32, 256)
 // per feature level) feed the encoder, which wants tokens: [N, sum_l H_l W_l, 256].  cuDNN's TF32 convolutions produce
@@ -645,6 +785,43 @@ int rlipv2_box_pair_loss_f32(const float *src, const float *tgt, int rows, float
     if (!src || !tgt || !l1 || !giou_loss || !dl1 || !dgiou || rows < 0) return RLIPV2_FUSED_EINVAL;
     if (((uintptr_t)src | (uintptr_t)tgt | (uintptr_t)dl1 | (uintptr_t)dgiou) & 15) return RLIPV2_FUSED_EINVAL;
     box_pair_loss_kernel<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(src, tgt, rows, l1, giou_loss, dl1, dgiou);
+    return done();
+}
+
+static inline unsigned sa_threshold(double p) {
+    if (p <= 0.0) return 0u;
+    double t = p * 4294967296.0;
+    return t >= 4294967295.0 ? 4294967295u : (unsigned)t;
+}
+
+int rlipv2_short_attention_fwd_f32(const float *q, const float *k, const float *v, const float *mask, int B, int H, int T,
+                                   int D, float scale, double dropout_p, const long long *seed, unsigned salt, float *out,
+                                   long long *seed_used, void *stream)
+{
+    if (B == 0 || H == 0 || T == 0) return 0;
+    if (D != kSaD || T > kSaT || T < 0) return RLIPV2_FUSED_ESHAPE;
+    if (!q || !k || !v || !out || B < 0 || H < 0 || dropout_p < 0.0 || dropout_p >= 1.0) return RLIPV2_FUSED_EINVAL;
+    if (dropout_p > 0.0 && !seed) return RLIPV2_FUSED_EINVAL;
+    if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 7) return RLIPV2_FUSED_EINVAL;
+    const int blocks = (B * H + kSaWarps - 1) / kSaWarps;
+    short_attn_fwd_kernel<<<blocks, kSaWarps * 32, 0, (cudaStream_t)stream>>>(
+        q, k, v, mask, B, H, T, scale, sa_threshold(dropout_p), (float)(1.0 / (1.0 - dropout_p)), seed, salt, out, seed_used);
+    return done();
+}
+
+int rlipv2_short_attention_bwd_f32(const float *q, const float *k, const float *v, const float *mask, const float *grad_out,
+                                   int B, int H, int T, int D, float scale, double dropout_p, const long long *seed,
+                                   unsigned salt, float *dq, float *dk, float *dv, void *stream)
+{
+    if (B == 0 || H == 0 || T == 0) return 0;
+    if (D != kSaD || T > kSaT || T < 0) return RLIPV2_FUSED_ESHAPE;
+    if (!q || !k || !v || !grad_out || !dq || !dk || !dv || B < 0 || H < 0 || dropout_p < 0.0 || dropout_p >= 1.0)
+        return RLIPV2_FUSED_EINVAL;
+    if (dropout_p > 0.0 && !seed) return RLIPV2_FUSED_EINVAL;
+    const int blocks = (B * H + kSaWarps - 1) / kSaWarps;
+    short_attn_bwd_kernel<<<blocks, kSaWarps * 32, 0, (cudaStream_t)stream>>>(
+        q, k, v, mask, grad_out, B, H, T, scale, sa_threshold(dropout_p), (float)(1.0 / (1.0 - dropout_p)), seed, salt, dq,
+        dk, dv);
     return done();
 }
 

@@ -33,6 +33,11 @@ _lib.rlipv2_box_refine_f32.argtypes = [_p, _p, _f, _ll, _p, _p]
 _lib.rlipv2_sine_embed_f32.argtypes = [_p, _i, _i, _p, _p]
 _lib.rlipv2_box_pair_loss_f32.argtypes = [_p, _p, _i, _p, _p, _p, _p, _p]
 _lib.rlipv2_box_pair_loss_f32.restype = _i
+_u = ctypes.c_uint
+_lib.rlipv2_short_attention_fwd_f32.argtypes = [_p, _p, _p, _p, _i, _i, _i, _i, _f, _d, _p, _u, _p, _p, _p]
+_lib.rlipv2_short_attention_fwd_f32.restype = _i
+_lib.rlipv2_short_attention_bwd_f32.argtypes = [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _d, _p, _u, _p, _p, _p, _p]
+_lib.rlipv2_short_attention_bwd_f32.restype = _i
 _lib.rlipv2_groupnorm_tokens_fwd_f32.argtypes = [_p, _p, _p, _f, _i, _i, _i, _i, _p, _p, _ll, _p, _p, _p]
 _lib.rlipv2_groupnorm_tokens_fwd_f32.restype = _i
 _lib.rlipv2_groupnorm_tokens_bwd_f32.argtypes = [_p, _ll, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]
@@ -47,7 +52,8 @@ _lib.rlipv2_fused_launch_count.restype = ctypes.c_ulonglong
 
 EXPORTS = ("rlipv2_add_layernorm_fwd_f32", "rlipv2_layernorm_bwd_f32", "rlipv2_relu_bwd_colsum_f32",
            "rlipv2_adamw_f32", "rlipv2_adamw_scaled_f32", "rlipv2_gather_chunks_f32", "rlipv2_rowmask_bwd_colsum_f32", "rlipv2_wait_host_flag",
-           "rlipv2_box_refine_f32", "rlipv2_sine_embed_f32", "rlipv2_box_pair_loss_f32", "rlipv2_groupnorm_tokens_fwd_f32", "rlipv2_groupnorm_tokens_bwd_f32", "rlipv2_stamp_globaltimer", "rlipv2_layernorm_bwd_acc_f32",
+           "rlipv2_box_refine_f32", "rlipv2_sine_embed_f32", "rlipv2_box_pair_loss_f32", "rlipv2_groupnorm_tokens_fwd_f32", "rlipv2_groupnorm_tokens_bwd_f32",
+           "rlipv2_short_attention_fwd_f32", "rlipv2_short_attention_bwd_f32", "rlipv2_stamp_globaltimer", "rlipv2_layernorm_bwd_acc_f32",
            "rlipv2_relu_bwd_colsum_acc_f32", "rlipv2_rowmask_bwd_colsum_acc_f32", "rlipv2_fused_error_string", "rlipv2_fused_launch_count")
 
 
@@ -235,6 +241,36 @@ def groupnorm_tokens_bwd(dy_rows, dy_batch_stride, x_tok, mean, rstd, gamma, dga
                                                   dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _stream())
     _check(rc, "rlipv2_groupnorm_tokens_bwd_f32")
     return dx
+
+
+SHORT_ATTN_MAX_T, SHORT_ATTN_D = 8, 64
+
+
+def short_attention_fwd(q, k, v, mask, scale, dropout_p, seed, salt):
+    """q, k, v [B, T, H, 64] contiguous fp32 CUDA (T <= 8); mask additive [B, T] or None; seed: device int64 [1] (needed
+    when dropout_p > 0) -> (out [B, T, H, 64], seed_used int64 [1])"""
+    B, T, H, D = q.shape
+    out = torch.empty_like(q)
+    seed_used = torch.empty(1, dtype=torch.int64, device=q.device)
+    with torch.cuda.device(q.device):
+        rc = _lib.rlipv2_short_attention_fwd_f32(q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                                 mask.data_ptr() if mask is not None else None, B, H, T, D, scale,
+                                                 float(dropout_p), seed.data_ptr() if seed is not None else None, int(salt),
+                                                 out.data_ptr(), seed_used.data_ptr(), _stream())
+    _check(rc, "rlipv2_short_attention_fwd_f32")
+    return out, seed_used
+
+
+def short_attention_bwd(q, k, v, mask, grad_out, scale, dropout_p, seed_used, salt):
+    B, T, H, D = q.shape
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    with torch.cuda.device(q.device):
+        rc = _lib.rlipv2_short_attention_bwd_f32(q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                                 mask.data_ptr() if mask is not None else None, grad_out.data_ptr(), B, H, T, D,
+                                                 scale, float(dropout_p), seed_used.data_ptr(), int(salt), dq.data_ptr(),
+                                                 dk.data_ptr(), dv.data_ptr(), _stream())
+    _check(rc, "rlipv2_short_attention_bwd_f32")
+    return dq, dk, dv
 
 
 def sine_embed(pos2d):

@@ -489,8 +489,9 @@ class RLIP_ParSeDABDeformableTransformer_v2(nn.Module):
         self.pass_pos_and_query = pass_pos_and_query
         self.tokenizer, self.text_encoder = build_text_encoder(
             text_encoder_type, synthetic=getattr(args, "synthetic_text_encoder", None))
-        from .text_encoder import route_through_dense_seam
+        from .text_encoder import route_through_dense_seam, use_short_attention
         route_through_dense_seam(self.text_encoder)
+        use_short_attention(self.text_encoder)
         if freeze_text_encoder:
             for p in self.text_encoder.parameters():
                 p.requires_grad_(False)

@@ -79,12 +79,93 @@ def pooled_text(text_encoder, input_ids, attention_mask):
     here (same values: 0 / finfo.min) and the model's own embeddings -> encoder -> pooler are called
     directly; every arithmetic op is still HF's."""
     te = text_encoder
-    if (getattr(te.config, "_attn_implementation", None) == "eager" and hasattr(te, "embeddings")
+    if (getattr(te.config, "_attn_implementation", None) in ("eager", _ATTN_KEY) and hasattr(te, "embeddings")
             and hasattr(te, "encoder") and getattr(te, "pooler", None) is not None):
+        if getattr(te.config, "_attn_implementation", None) == _ATTN_KEY and te.training and input_ids.is_cuda:
+            _dropout_seed(input_ids.device).add_(1)                 # fresh dropout masks for this pass
         emb = te.embeddings(input_ids=input_ids)
         ext = (1.0 - attention_mask[:, None, None, :].to(emb.dtype)) * torch.finfo(emb.dtype).min
         return te.pooler(te.encoder(emb, attention_mask=ext).last_hidden_state)
     return te(input_ids=input_ids, attention_mask=attention_mask).pooler_output
+
+
+# ---- short-sequence attention for the label strings (csrc/fused_ops.cu short_attn_*) --------------------------------
+_SHORT_ATTN = os.environ.get("RLIPV2_SHORT_ATTN", "1") != "0"
+_ATTN_KEY = "rlipv2_short"
+_seeds = {}
+
+
+def _dropout_seed(device):
+    """device-resident int64 counter the dropout masks are hashed from (advanced once per text-tower forward)"""
+    s = _seeds.get(device)
+    if s is None:
+        s = _seeds[device] = torch.zeros(1, dtype=torch.int64, device=device) + (torch.initial_seed() % (2 ** 62))
+    return s
+
+
+class _ShortAttention(torch.autograd.Function):
+    """softmax(q k^T * scale + mask) (dropout) v for T <= 8 tokens, head dim 64; one kernel each way.
+    q, k, v: [B, H, T, 64] views of [B, T, H * 64] projections (HF layout) -> [B, T, H, 64]"""
+
+    @staticmethod
+    def forward(ctx, q, k, v, mask, scale, dropout_p, seed, salt):
+        from . import fused_abi
+        qt, kt, vt = (t.transpose(1, 2) for t in (q, k, v))            # [B, T, H, 64]: contiguous for HF's views
+        qt, kt, vt = (t if t.is_contiguous() else t.contiguous() for t in (qt, kt, vt))
+        out, seed_used = fused_abi.short_attention_fwd(qt, kt, vt, mask, scale, dropout_p, seed if dropout_p > 0 else None,
+                                                       salt)
+        ctx.save_for_backward(qt, kt, vt, mask, seed_used)
+        ctx.conf = (scale, dropout_p, salt)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from . import fused_abi
+        qt, kt, vt, mask, seed_used = ctx.saved_tensors
+        scale, dropout_p, salt = ctx.conf
+        g = grad_out if grad_out.is_contiguous() else grad_out.contiguous()
+        dq, dk, dv = fused_abi.short_attention_bwd(qt, kt, vt, mask, g, scale, dropout_p, seed_used, salt)
+        return dq.transpose(1, 2), dk.transpose(1, 2), dv.transpose(1, 2), None, None, None, None, None
+
+
+def _short_attention_forward(module, query, key, value, attention_mask, dropout=0.0, scaling=None, **kwargs):
+    """attention interface of HF's RobertaSelfAttention (same contract as modeling_roberta.eager_attention_forward):
+    -> (attn_output [B, T, H, D], attn_weights)"""
+    from transformers.models.roberta.modeling_roberta import eager_attention_forward
+    from . import fused_abi
+    B, H, T, D = query.shape
+    ok = (query.is_cuda and query.dtype == torch.float32 and D == fused_abi.SHORT_ATTN_D and T <= fused_abi.SHORT_ATTN_MAX_T
+          and key.shape == query.shape and value.shape == query.shape
+          and (attention_mask is None or (attention_mask.dtype == torch.float32 and attention_mask.numel() == B * T)))
+    if not ok:
+        return eager_attention_forward(module, query, key, value, attention_mask, dropout=dropout, scaling=scaling, **kwargs)
+    if scaling is None:
+        scaling = D ** -0.5
+    mask = attention_mask.reshape(B, T).contiguous() if attention_mask is not None else None
+    p = float(dropout) if module.training else 0.0
+    out = _ShortAttention.apply(query, key, value, mask, float(scaling), p, _dropout_seed(query.device),
+                                int(getattr(module, "_rlipv2_salt", 0)))
+    return out, None
+
+
+def use_short_attention(text_encoder):
+    """route the tower's self-attention through the short-sequence kernel (label strings are 3-8 tokens); longer inputs,
+    CPU tensors and other dtypes fall through to HF's eager attention inside the interface function"""
+    if not _SHORT_ATTN:
+        return text_encoder
+    try:
+        from transformers import AttentionInterface
+        AttentionInterface.register(_ATTN_KEY, _short_attention_forward)
+    except Exception:                                   # older transformers: keep HF's eager attention
+        return text_encoder
+    salt = 0
+    for m in text_encoder.modules():
+        if m.__class__.__name__ == "RobertaSelfAttention":
+            m._rlipv2_salt = salt
+            salt += 1
+    if salt:
+        text_encoder.config._attn_implementation = _ATTN_KEY
+    return text_encoder
 
 
 def route_through_dense_seam(text_encoder):

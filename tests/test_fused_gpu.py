@@ -131,3 +131,64 @@ def test_group_norm_tokens_matches_torch(channels_last, fuse):
         off = 0.25 if fuse else 0.0
         torch.testing.assert_close(n.weight.grad.double() - off, w.grad, rtol=1e-3, atol=1e-4 * float(w.grad.abs().max()))
         torch.testing.assert_close(n.bias.grad.double() - off, b.grad, rtol=1e-3, atol=1e-4 * float(b.grad.abs().max()))
+
+
+def _sa_inputs(B, H, T, seed, pad=True):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    mk = lambda: torch.randn(B, T, H * 64, device="cuda", generator=g).view(B, T, H, 64).transpose(1, 2)   # HF's views
+    q, k, v = mk(), mk(), mk()
+    lens = torch.randint(1, T + 1, (B,), device="cuda", generator=g) if pad else torch.full((B,), T, device="cuda")
+    keep = (torch.arange(T, device="cuda")[None] < lens[:, None]).float()
+    mask = ((1.0 - keep) * torch.finfo(torch.float32).min)[:, None, None, :]
+    return q, k, v, mask
+
+
+@pytest.mark.parametrize("B,H,T", [(256, 12, 5), (7, 3, 8), (1, 1, 1), (33, 12, 3)])
+def test_short_attention_matches_hf_eager(B, H, T):
+    """rlipv2_short_attention_* (text tower, label strings) against HF's eager_attention_forward, forward + backward"""
+    from transformers.models.roberta.modeling_roberta import eager_attention_forward
+    from rlipv2_b200.text_encoder import _short_attention_forward
+
+    M = lambda: torch.nn.Module().eval()                 # eval mode: the dropout argument must be ignored
+    q, k, v, mask = _sa_inputs(B, H, T, seed=B + T)
+    go = torch.randn(B, T, H, 64, device="cuda")
+    res = []
+    for fn in (eager_attention_forward, _short_attention_forward):
+        qq, kk, vv = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
+        out, _ = fn(M(), qq, kk, vv, mask, dropout=0.1, scaling=0.125)
+        assert out.shape == (B, T, H, 64)
+        (out * go).sum().backward()
+        res.append((out.detach(), qq.grad, kk.grad, vv.grad))
+    for a, b in zip(res[1], res[0]):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5 * float(b.abs().max()) + 1e-6)
+
+
+def test_short_attention_dropout_is_consistent_between_forward_and_backward():
+    from rlipv2_b200.text_encoder import _ShortAttention
+    B, H, T, p = 64, 12, 5, 0.1
+    q, k, v, mask = _sa_inputs(B, H, T, seed=1, pad=False)
+    seed = torch.tensor([12345], dtype=torch.int64, device="cuda")
+    m2 = mask.reshape(B, T).contiguous()
+    run = lambda qq, kk, vv, salt=3: _ShortAttention.apply(qq, kk, vv, m2, 0.125, p, seed, salt)
+    # keep rate: uniform probabilities (q = 0), v = 1 -> every output element = (#kept / T) / (1 - p), mean 1
+    ones = torch.ones_like(v)
+    o = run(torch.zeros_like(q), k, ones)
+    assert abs(float(o.mean()) - 1.0) < 0.02
+    frac_dropped = float((run(torch.zeros_like(q), k, ones, salt=4) != o).float().mean())
+    assert frac_dropped > 0.1                                        # another call site draws another mask
+    # the mask is a function of (seed, salt, element): linear in v for fixed q, k
+    v2 = torch.randn_like(v)
+    torch.testing.assert_close(run(q, k, v + v2), run(q, k, v) + run(q, k, v2), rtol=1e-4, atol=1e-4)
+    # adjoint identity through the dropped attention: <go, out(v)> = <dv, v>, and a directional derivative in q, k
+    qq, kk, vv = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
+    go = torch.randn(B, T, H, 64, device="cuda")
+    out = run(qq, kk, vv)
+    (out * go).sum().backward()
+    lhs, rhs = float((go.double() * out.double()).sum()), float((vv.grad.double() * v.double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1.0)
+    dq, dk = torch.randn_like(q), torch.randn_like(k)
+    eps = 1e-2
+    f = lambda s: float((run(q + s * eps * dq, k + s * eps * dk, v).double() * go.double()).sum())
+    num = (f(1) - f(-1)) / (2 * eps)
+    ana = float((qq.grad.double() * dq.double()).sum() + (kk.grad.double() * dk.double()).sum())
+    assert abs(num - ana) <= 2e-2 * max(abs(ana), 1.0), (num, ana)

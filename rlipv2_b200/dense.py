@@ -36,6 +36,8 @@ _OWN_BWD_MIN_ROWS = int(os.environ.get("RLIPV2_OWN_BWD_MIN_ROWS", "4096"))
 # gradients fill the SMs the latency-bound MSDeformAttn backward leaves idle.  Active only when the gradient is
 # accumulated in place into the step's flat gradient buffer (`_fuse_grad`), so nothing is handed back to autograd from
 # the side stream; the train step joins it after backward() (`join_param_grad_stream`).
+_LIBRARY_SMALL = os.environ.get("RLIPV2_TEXT_LIBRARY_GEMM", "1") != "0"
+_LIBRARY_SMALL_MAX_ROWS = 4096
 _WGRAD_STREAM = os.environ.get("RLIPV2_WGRAD_STREAM", "1") != "0"
 # (measured r01s4d: every size on the side stream 28.65 vs 29.5 ms/step with only the <= 4096-row problems there)
 _WGRAD_STREAM_MAX_ROWS = int(os.environ.get("RLIPV2_WGRAD_STREAM_MAX_ROWS", str(1 << 30)))
@@ -104,7 +106,7 @@ class _LinearTF32(torch.autograd.Function):
     """y = act(x W^T + b) on the tcgen05 kernel; backward = cuBLAS TF32 GEMMs + fused mask."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act, row_mask=None):
+    def forward(ctx, x, weight, bias, act, row_mask=None, library_small=False):
         abi = _abi()
         x2 = x.reshape(-1, x.shape[-1])
         if not x2.is_contiguous():
@@ -114,7 +116,12 @@ class _LinearTF32(torch.autograd.Function):
         if row_mask is not None:
             rm = row_mask.reshape(-1)
             rm = rm if rm.is_contiguous() else rm.contiguous()
-        y = abi.linear_tf32(x2, w, bias, act, rm)
+        if library_small and act == 0 and rm is None and x2.shape[0] <= _LIBRARY_SMALL_MAX_ROWS and w.shape[1] >= 512:
+            # plain small-M / long-K linears of the (third-party, HF) text tower: cuBLAS' split-K kernels are 2-3x faster
+            # than one 128-row tile per CTA here (profiles/dense_microbench_r01_v3_small_grids.jsonl); backward unchanged
+            y = F.linear(x2, w, bias)
+        else:
+            y = abi.linear_tf32(x2, w, bias, act, rm)
         ctx.act = act
         ctx.has_bias = bias is not None
         # parameters whose .grad is a view of the step's flat gradient buffer (train_step marks them `_fuse_grad`):
@@ -166,7 +173,7 @@ class _LinearTF32(torch.autograd.Function):
                     w_acc.addmm_(g.t(), x2)              # cuBLAS with beta = 1: grad view += g^T x
             if ctx.needs_input_grad[0]:
                 gx = (_abi().dgrad_tf32(g, w)[0] if _OWN_BWD and big else g @ w).view(*grad_out.shape[:-1], K)
-            return gx, None, None, None, None
+            return gx, None, None, None, None, None
         if ctx.needs_input_grad[0]:
             gx = (_abi().dgrad_tf32(g, w)[0] if _OWN_BWD and big else g @ w).view(*grad_out.shape[:-1], K)
         if ctx.needs_input_grad[1]:
@@ -182,7 +189,7 @@ class _LinearTF32(torch.autograd.Function):
                 gw = g.t() @ x2
         if not (ctx.has_bias and ctx.needs_input_grad[2]):
             gb = None
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None
 
 
 class _FFNReLU(torch.autograd.Function):
@@ -302,10 +309,11 @@ def _tcgen05_ok(x, weight):
     return M > 0 and _abi().supported(M, weight.shape[0], weight.shape[1])
 
 
-def linear(x, weight, bias=None, row_mask=None):
-    """x W^T + b; `row_mask` (bool, x.shape[:-1]): those rows of the result are zero (masked_fill folded in)"""
+def linear(x, weight, bias=None, row_mask=None, library_small=False):
+    """x W^T + b; `row_mask` (bool, x.shape[:-1]): those rows of the result are zero (masked_fill folded in);
+    `library_small`: the caller allows the cuBLAS forward for small-M / long-K problems (text tower)"""
     if _tcgen05_ok(x, weight):
-        return _LinearTF32.apply(x, weight, bias, 0, row_mask)
+        return _LinearTF32.apply(x, weight, bias, 0, row_mask, library_small and _LIBRARY_SMALL)
     y = F.linear(x, weight, bias)
     return y if row_mask is None else y.masked_fill(row_mask[..., None], float(0))
 

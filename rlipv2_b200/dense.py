@@ -36,7 +36,7 @@ _OWN_BWD_MIN_ROWS = int(os.environ.get("RLIPV2_OWN_BWD_MIN_ROWS", "4096"))
 # gradients fill the SMs the latency-bound MSDeformAttn backward leaves idle.  Active only when the gradient is
 # accumulated in place into the step's flat gradient buffer (`_fuse_grad`), so nothing is handed back to autograd from
 # the side stream; the train step joins it after backward() (`join_param_grad_stream`).
-_LIBRARY_SMALL = os.environ.get("RLIPV2_TEXT_LIBRARY_GEMM", "1") != "0"
+_LIBRARY_SMALL = os.environ.get("RLIPV2_TEXT_LIBRARY_GEMM", "0") != "0"      # measured r01s4g: 27.6 vs 27.7 ms/step - no gain, off
 _LIBRARY_SMALL_MAX_ROWS = 4096
 _WGRAD_STREAM = os.environ.get("RLIPV2_WGRAD_STREAM", "1") != "0"
 # (measured r01s4d: every size on the side stream 28.65 vs 29.5 ms/step with only the <= 4096-row problems there)

@@ -163,10 +163,11 @@ def msda_roofline(device):
     pk = peaks()
     return {"bound": "hbm", "kernel": "msda_bwd_d32_l4p4 (encoder call, N=2, S=Lq=22223): 273.1 MB algorithmic / launch",
             "achieved": bwd_b / tb / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": bwd_b / tb / 1e9 / pk["hbm_gbs"],
-            "peak_src": pk["src"], "traffic": 344.5e6, "traffic_src": "ncu dram__bytes_read+write, profiles/msda_r01.md",
+            "peak_src": pk["src"], "traffic": 344.0e6,
+            "traffic_src": "ncu --set full dram__bytes_read+write per launch, profiles/msda_r01_final_enc_ncu.txt",
             "us": tb * 1e6,
             "fwd": {"kernel": "msda_fwd_d32_l4p4: 159.3 MB algorithmic / launch", "achieved": fwd_b / tf / 1e9,
-                    "frac": fwd_b / tf / 1e9 / pk["hbm_gbs"], "us": tf * 1e6, "traffic": 141.8e6}}
+                    "frac": fwd_b / tf / 1e9 / pk["hbm_gbs"], "us": tf * 1e6, "traffic": 141.9e6}}
 
 
 def alif_tensor_roofline(device):
@@ -214,7 +215,8 @@ def alif_tensor_roofline(device):
     return {"bound": "tensor", "kernel": "linear_tf32_kernel (tcgen05.mma kind::tf32) on the 6 ALIF projections of one fusion layer, batch 2",
             "achieved": flops / t / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / t / 1e12 / peak, "peak_src": src,
             "us_per_layer": t * 1e6, "flops_per_layer": flops,
-            "ncu": "sm__pipe_tensor_cycles_active 27.8 % on the l_proj GEMM (profiles/dense_r01_v1_alif_ncu.txt); "
+            "ncu": "sm__pipe_tensor_cycles_active 14.0 % (v_proj, K = 256) .. 27.8 % (l_proj, K = 768) "
+                   "(profiles/dense_r01_final_alif_ncu.txt, dense_r01_v1_alif_ncu.txt); "
                    "M = 512-546 rows fill 16-64 of 148 SMs: the GEMMs are latency-bound (6-stage TMA ring for these grids)",
             "timing": "CUDA-graph replay of the 6 launches x 10, CUDA events"}
 

@@ -20,7 +20,10 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:msda
    python tools/msda_profile_target.py --case enc2 --iters 1 > gpurun_out/${TAG}_ncu_msda.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:linear_tf32 -c 6 -f -o gpurun_out/${TAG}_alif_linear \
    python tools/dense_microbench.py ALIF > gpurun_out/${TAG}_ncu_alif.log 2>&1
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "timed/" \
+# RLIPV2_FLAG_WAIT=0: under ncu every graph node is replayed alone, so a backward graph parked on the host flag would sit
+# out its 10 s timeout per step (the r01final capture took 15 minutes that way); with the flag wait off the host solves
+# the assignment before it launches the backward graph - same kernels, same launch list.
+RLIPV2_FLAG_WAIT=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "timed/" \
    --graph-profiling node --csv --log-file gpurun_out/${TAG}_launches.csv \
    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/${TAG}_ncu_bench.log 2>&1
 wc -l gpurun_out/${TAG}_launches.csv

@@ -84,10 +84,15 @@ def test_two_gloo_ranks():
         procs = [ctx.Process(target=_worker, args=(r, port, q)) for r in range(WORLD)]
         for p in procs:
             p.start()
-        try:
-            res = sorted([q.get(timeout=240) for _ in range(WORLD)], key=lambda r: r[0])
-        except Exception:
-            res = None
+        got, waited = [], 0
+        while len(got) < WORLD and waited < 240:
+            try:
+                got.append(q.get(timeout=5))
+            except Exception:
+                waited += 5
+                if any(p.exitcode not in (None, 0) for p in procs):      # a rank died (e.g. the port was taken)
+                    break
+        res = sorted(got, key=lambda r: r[0]) if len(got) == WORLD else None
         for p in procs:
             p.join(60)
             if p.is_alive():

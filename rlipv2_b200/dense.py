@@ -1,15 +1,22 @@
 """Dense-contraction seam of the hot path.
 
-Every GEMM-shaped op of ALIF, the RobertaLayer stack and the deformable encoder/decoder FFNs goes
-through these functions, so the module code stays independent of how the contraction is executed.
+Every GEMM-shaped op of ALIF, the RobertaLayer stack, the text tower and the deformable encoder/decoder goes through
+these functions, so the module code stays independent of how the contraction is executed.
 
 Two execution modes (`set_matmul_precision`):
   'fp32'  IEEE fp32 products through cuBLAS - used by the parity tests against the reference fixtures;
-  'tf32'  TF32 tensor-core products, fp32 accumulation - what the reference's pinned torch 1.10 does by
-          default on tensor-core GPUs.  Forward linears whose shape the hand-written tcgen05 kernel
-          supports (N % 128 == 0, K % 32 == 0; csrc/dense_tf32.cu, include/rlipv2_dense.h) run on it with
-          bias / ReLU fused in the epilogue; their backward GEMMs and the remaining shapes are cuBLAS
-          TF32 (round-1 state).
+  'tf32'  TF32 tensor-core products, fp32 accumulation - what the reference's pinned torch 1.10 does by default on
+          tensor-core GPUs, and what bench.py measures.  Forward linears whose shape the hand-written tcgen05 kernel
+          supports (N % 128 == 0, K % 32 == 0; csrc/dense_tf32.cu, include/rlipv2_dense.h) run on it with bias / ReLU /
+          GELU / row mask fused in the epilogue.  Backward: split-K tcgen05 weight gradients for tall-skinny shapes, the
+          encoder FFN's gated input gradient + both weight gradients on tcgen05 (`_FFNReLU`), cuBLAS TF32 for the rest;
+          bias / LayerNorm gradients from the fused kernels of csrc/fused_ops.cu.
+What the custom autograd functions add on top of the kernels (all of it only when the train step has made the parameters'
+`.grad` views of its flat gradient buffer and marked them `_fuse_grad`):
+  * parameter gradients are ADDED into those views by the producing kernel (GEMM beta = 1, reductions without zero-fill)
+    instead of being handed to ~600 AccumulateGrad kernels;
+  * they are issued on a side stream (`_ParamGradSide`), off the chain of input gradients the previous layer waits for;
+    `join_param_grad_stream()` must be called before the gradients are read.
 There is no CPU implementation behind the tcgen05 path; CPU tensors only ever reach the torch ops.
 """
 import math

@@ -108,7 +108,8 @@ class RLIP_ParSeDA(nn.Module):
         srcs, masks = [], []
         norms = [p[1] for p in self.input_proj]
         if (self.num_feature_levels <= len(features) + 1
-                and dense.group_norm_tokens_supported([f.tensors for f in features], norms)):
+                and dense.group_norm_tokens_supported([f.tensors for f in features], [p[0] for p in self.input_proj],
+                                                      norms)):
             # GPU path: the projections' convolutions (cuDNN, NHWC outputs), then ONE fused op that applies every
             # level's GroupNorm on the token-major data and writes the encoder's [N, sum HW, 256] token buffer directly
             # (no NCHW round trip, no flatten / transpose / cat copies); `srcs` are views of that buffer

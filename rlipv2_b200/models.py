@@ -1,4 +1,5 @@
-"""build_model(args) -> (model, criterion, postprocessors): the `--RLIP_ParSeDA_v2` branch of
+"""build_model(args) -> (model, criterion, postprocessors): the `--RLIP_ParSeDA_v2` branch (the hot path) and the
+`--RLIP_ParSe` branch (BASELINE config 1, the CPU plumbing case) of
 /root/reference/models/detr.py:320-701 (reached through models/__init__.py:15-16).
 
 `args` is the reference's own argparse namespace (main.py:38-491), so main.py / engine.py can call
@@ -46,20 +47,39 @@ def build_weight_dict(args):
     return w
 
 
+def _build_parse(args):
+    """detr.py:330-332 (vanilla single-level backbone, models/backbone.py:174-181) + :402-414"""
+    from .backbone import Backbone, Joiner, PositionEmbeddingSine
+    from .parse_detr import RLIP_ParSe, build_parse_transformer
+    if getattr(args, "position_embedding", "sine") not in ("v2", "sine"):
+        raise NotImplementedError("the RLIP scripts use the sine position embedding")
+    backbone = Joiner(Backbone(args.backbone, args.lr_backbone > 0, bool(args.masks), args.dilation,
+                               getattr(args, "backbone_weights", None)),
+                      PositionEmbeddingSine(args.hidden_dim // 2, normalize=True))
+    cross_modal = args.verb_loss_type == "cross_modal_matching" and args.obj_loss_type == "cross_modal_matching"
+    return RLIP_ParSe(backbone, build_parse_transformer(args), num_queries=args.num_queries,
+                      contrastive_align_loss=cross_modal, contrastive_hdim=64, aux_loss=args.aux_loss,
+                      subject_class=args.subject_class, use_no_verb_token=getattr(args, "use_no_verb_token", False), args=args)
+
+
 def build_model(args):
-    if not getattr(args, "RLIP_ParSeDA_v2", False):
-        raise NotImplementedError("rlipv2_b200 implements the --RLIP_ParSeDA_v2 model only")
+    parse = bool(getattr(args, "RLIP_ParSe", False))
+    if not (getattr(args, "RLIP_ParSeDA_v2", False) or parse):
+        raise NotImplementedError("rlipv2_b200 implements the --RLIP_ParSeDA_v2 and --RLIP_ParSe models only")
     if not (args.hoi or args.sgg or getattr(args, "cross_modal_pretrain", False)):
-        raise NotImplementedError("ParSeDA runs with --hoi, --sgg or --cross_modal_pretrain")
+        raise NotImplementedError("the RLIP models run with --hoi, --sgg or --cross_modal_pretrain")
     device = torch.device(args.device)
-    backbone = build_backbone(args)
-    transformer = build_parseda_transformer(args)
     matcher = build_matcher(args)
-    model = RLIP_ParSeDA(backbone, transformer, num_queries=args.num_queries,
-                         num_feature_levels=args.num_feature_levels, aux_loss=args.aux_loss,
-                         with_box_refine=args.with_box_refine, two_stage=args.two_stage, use_dab=True,
-                         num_patterns=args.num_patterns, random_refpoints_xy=args.random_refpoints_xy,
-                         subject_class=args.subject_class, pseudo_verb=getattr(args, "pseudo_verb", False), args=args)
+    if parse:
+        model = _build_parse(args)
+    else:
+        backbone = build_backbone(args)
+        transformer = build_parseda_transformer(args)
+        model = RLIP_ParSeDA(backbone, transformer, num_queries=args.num_queries,
+                             num_feature_levels=args.num_feature_levels, aux_loss=args.aux_loss,
+                             with_box_refine=args.with_box_refine, two_stage=args.two_stage, use_dab=True,
+                             num_patterns=args.num_patterns, random_refpoints_xy=args.random_refpoints_xy,
+                             subject_class=args.subject_class, pseudo_verb=getattr(args, "pseudo_verb", False), args=args)
     losses = ["obj_labels", "verb_labels", "sub_obj_boxes", "obj_cardinality"]
     for flag in ("entropy_bound", "kl_divergence", "verb_gt_recon", "ranking_verb", "no_verb_bce_focal", "verb_hm",
                  "semantic_similar", "verb_threshold", "masked_entity_modeling", "verb_tagger"):

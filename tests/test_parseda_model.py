@@ -144,3 +144,49 @@ def test_full_step_golden(device, request):
                     float(np.linalg.norm(sample - ref) / (np.linalg.norm(ref) + 1e-12)))
     bad = {k: v for k, v in worst.items() if v[0] > 2e-3 or v[1] > 5e-3}
     assert not bad, f"gradient mismatch (norm rel err, sample rel err): {bad}"
+
+
+@pytest.mark.parametrize("device", DEVICES)
+def test_pretrain_step_golden(device, request):
+    """BASELINE config 3's model flags (`--cross_modal_pretrain --pseudo_verb` instead of `--hoi`): pseudo relation labels
+    (hoi.py:2197-2239) and their use in the verb loss (hoi.py:3925-4028) against the reference's own modules
+    (oracle/gen_golden_pretrain.py), same inputs / weights as the fine-tune fixture"""
+    _fp32()
+    if device == "cpu":
+        request.getfixturevalue("msda_cpu_stub")
+    from oracle.gen_golden_model import OBJ_NAMES, VERB_NAMES
+    from rlipv2_b200 import models
+    g, gs = _load("parseda_pretrain_step.npz"), _load("parseda_step.npz")
+    model, criterion, _ = models.build_model(_args(device, hoi=False, cross_modal_pretrain=True, pseudo_verb=True))
+    det_fill_(model, seed=3)
+    model.to(device).eval()
+    criterion.to(device).eval()
+    imgs = [torch.from_numpy(gs["img0"]).to(device), torch.from_numpy(gs["img1"]).to(device)]
+    targets = [{k: torch.from_numpy(gs[f"tgt{i}_{k}"]).to(device)
+                for k in ("obj_labels", "sub_labels", "verb_labels", "sub_boxes", "obj_boxes")} for i in range(2)]
+    text = [(OBJ_NAMES, VERB_NAMES)]
+    cache = model(imgs, encode_and_save=True, text=text, targets=targets)
+    out = model(imgs, encode_and_save=False, memory_cache=cache, text=text, targets=targets)
+    loss_dict = criterion(out, targets)
+    wd = criterion.weight_dict
+    total = sum(loss_dict[k] * wd[k] for k in loss_dict if k in wd)
+    total.backward()
+    c = lambda t: t.detach().cpu().numpy()
+    tol = dict(rtol=1e-3, atol=2e-4)
+    assert int((g["target_verb_sim"] > 0).sum()) > 0                      # the fixture does carry pseudo labels
+    np.testing.assert_allclose(c(out["target_verb_sim"]), g["target_verb_sim"], **tol)
+    for aux in out["aux_outputs"]:
+        np.testing.assert_allclose(c(aux["target_verb_sim"]), g["target_verb_sim"], **tol)
+    for k in ("pred_sub_logits", "pred_obj_logits", "pred_verb_logits", "pred_sub_boxes", "pred_obj_boxes"):
+        np.testing.assert_allclose(c(out[k]), g["out_" + k], **tol)
+    for b, (i, j) in enumerate(criterion.matcher({k: v for k, v in out.items() if k != "aux_outputs"}, targets)):
+        np.testing.assert_array_equal(i.numpy(), g[f"match_{b}_i"])
+        np.testing.assert_array_equal(j.numpy(), g[f"match_{b}_j"])
+    gold_keys = sorted(k[len("loss_"):] for k in g if k.startswith("loss_"))
+    assert sorted(loss_dict.keys()) == gold_keys
+    for k, v in loss_dict.items():
+        np.testing.assert_allclose(float(v), float(g["loss_" + k]), rtol=1e-3, atol=1e-4, err_msg=k)
+    np.testing.assert_allclose(float(total), float(g["total_loss"]), rtol=1e-3)
+    params = model.state_dict(keep_vars=True)
+    for k in [k[len("gradnorm_"):] for k in g if k.startswith("gradnorm_")]:
+        np.testing.assert_allclose(float(params[k].grad.norm()), float(g["gradnorm_" + k]), rtol=3e-3, err_msg=k)

@@ -6,7 +6,8 @@ torch 2.11 / transformers 5.5 without network access:
 
   1. a stub module named `MultiScaleDeformableAttention` (ms_deform_attn_func.py:22 imports it);
   2. transformers 4.5-era helper names expected by models/modeling_roberta.py:24,26;
-  3. a `timm` stub (models/fuse_helper.py:13 imports DropPath);
+  3. a `timm` stub (models/fuse_helper.py:13 and models/swin/swin_transformer.py:21 import DropPath, to_2tuple,
+     trunc_normal_);
   4. offline RoBERTa: `from_pretrained` of tokenizer/model/config return a random-init roberta-base
      shaped model and a deterministic fake tokenizer (dab_deformable/deformable_transformer.py:296,334-335);
   5. `torch.load` of the hard-coded ResNet-50 path returns torchvision's random state_dict
@@ -82,12 +83,19 @@ def install():
         timm_layers = types.ModuleType("timm.models.layers")
 
         class DropPath(torch.nn.Module):
+            """timm is absent: per-sample stochastic depth with timm's published semantics (identity in eval mode,
+            which is all the fixtures use; Swin backbones are built with drop_path_rate > 0)"""
+
             def __init__(self, p=0.0):
                 super().__init__()
-                assert p == 0.0
+                self.drop_prob = float(p)
 
             def forward(self, x):
-                return x
+                if self.drop_prob == 0.0 or not self.training:
+                    return x
+                keep = 1.0 - self.drop_prob
+                m = x.new_empty((x.shape[0],) + (1,) * (x.ndim - 1)).bernoulli_(keep)
+                return x * (m / keep if keep > 0 else m)
 
         timm_layers.DropPath = DropPath
         timm_layers.to_2tuple = lambda x: (x, x)

@@ -100,10 +100,13 @@ class _ConvBiasReLU(torch.autograd.Function):
 
 
 class PositionEmbeddingSine(nn.Module):
-    """Normalised 2-D sine embedding over the un-padded extent (position_encoding.py:22-58)."""
+    """Normalised 2-D sine embedding over the un-padded extent (position_encoding.py:22-58).  `offset` is subtracted
+    from the cumulative cell index before normalising: 0 for the ResNet wrapper, 0.5 (cell centres) for the Swin
+    wrapper's copy (swin/position_encoding.py:34-35)."""
 
-    def __init__(self, num_pos_feats=64, temperature=10000, normalize=False, scale=None):
+    def __init__(self, num_pos_feats=64, temperature=10000, normalize=False, scale=None, offset=0.0):
         super().__init__()
+        self.offset = float(offset)
         self.num_pos_feats = num_pos_feats
         self.temperature = temperature
         self.normalize = normalize
@@ -119,8 +122,12 @@ class PositionEmbeddingSine(nn.Module):
         x_embed = not_mask.cumsum(2, dtype=torch.float32)
         if self.normalize:
             eps = 1e-6
-            y_embed = y_embed / (y_embed[:, -1:, :] + eps) * self.scale
-            x_embed = x_embed / (x_embed[:, :, -1:] + eps) * self.scale
+            if self.offset:
+                y_embed = (y_embed - self.offset) / (y_embed[:, -1:, :] + eps) * self.scale
+                x_embed = (x_embed - self.offset) / (x_embed[:, :, -1:] + eps) * self.scale
+            else:
+                y_embed = y_embed / (y_embed[:, -1:, :] + eps) * self.scale
+                x_embed = x_embed / (x_embed[:, :, -1:] + eps) * self.scale
         dim_t = torch.arange(self.num_pos_feats, dtype=torch.float32, device=mask.device)
         dim_t = self.temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / self.num_pos_feats)
         pos_x = x_embed[:, :, :, None] / dim_t
@@ -280,7 +287,7 @@ class Joiner(nn.Sequential):
 
     def forward(self, tensor_list: NestedTensor):
         x_in = tensor_list.tensors
-        if _POS_STREAM and x_in.is_cuda and isinstance(self[0], Backbone):
+        if _POS_STREAM and x_in.is_cuda and hasattr(self[0], "strides"):
             # The per-level padding masks and sine position embeddings (position_encoding.py:22-58: ~30 small kernels
             # per level, no gradients) depend on the input mask and on the feature maps' SHAPES only.  They are issued
             # on a side stream that forks before the backbone's convolutions and joins after them.
@@ -309,10 +316,14 @@ class Joiner(nn.Sequential):
 def build_backbone(args):
     """build_DDETR_backbone (DDETR_backbone.py:163-169) minus the hard-coded weight path: pass
     `args.backbone_weights` (a resnet50 state_dict file) to start from pretrained weights."""
-    if "swin" in args.backbone:
-        raise NotImplementedError("Swin backbones (config 4) are outside round 1's scope")
     if getattr(args, "position_embedding", "sine") not in ("v2", "sine"):
         raise NotImplementedError("ParSeDA scripts use the sine position embedding")
+    if "swin" in args.backbone:
+        # detr.py:326-327 -> models/swin/backbone.py:194-205 (BASELINE config 4: --backbone swin_large)
+        from .swin import SwinBackbone
+        backbone = SwinBackbone(args.backbone, args.num_feature_levels, getattr(args, "pretrained_swin", ""),
+                                getattr(args, "use_checkpoint", False), getattr(args, "drop_path_rate", 0.2), args.dilation)
+        return Joiner(backbone, PositionEmbeddingSine(args.hidden_dim // 2, normalize=True, offset=0.5))
     position_embedding = PositionEmbeddingSine(args.hidden_dim // 2, normalize=True)
     backbone = Backbone(args.backbone, args.lr_backbone > 0, args.masks or (args.num_feature_levels > 1),
                         args.dilation, getattr(args, "backbone_weights", None))

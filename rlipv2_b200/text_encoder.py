@@ -155,7 +155,12 @@ def use_short_attention(text_encoder):
         return text_encoder
     try:
         from transformers import AttentionInterface
+        from transformers.masking_utils import AttentionMaskInterface, eager_mask
         AttentionInterface.register(_ATTN_KEY, _short_attention_forward)
+        # callers that invoke the tower directly (`model.transformer.text_encoder(**tokens)`, engine.py:377) go through
+        # HF's own mask construction, which looks the mask builder up under the attention key: without this entry the
+        # raw 0/1 padding mask would reach the attention function unexpanded
+        AttentionMaskInterface.register(_ATTN_KEY, eager_mask)
     except Exception:                                   # older transformers: keep HF's eager attention
         return text_encoder
     salt = 0

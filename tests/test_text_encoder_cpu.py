@@ -43,6 +43,10 @@ def test_attention_hook_and_dense_seam_leave_cpu_results_unchanged():
     assert salts == list(range(len(salts))) and len(salts) == 2
     out = pooled_text(enc, ids, mask)
     assert torch.equal(out, ref)                                    # CPU tensors fall through to HF's eager attention
+    # a caller that invokes the tower directly (engine.py:377, the evaluation loop) goes through HF's own mask
+    # construction under the registered attention key: padded tokens must stay masked there as well
+    direct = enc(input_ids=ids, attention_mask=mask).pooler_output
+    torch.testing.assert_close(direct, ref, rtol=1e-5, atol=1e-6)
     (out.sum()).backward()                                          # and autograd still reaches the parameters
     assert enc.encoder.layer[0].attention.self.query.weight.grad is not None
 

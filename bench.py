@@ -225,10 +225,11 @@ def alif_tensor_roofline(device):
 # workload: full train step
 # ------------------------------------------------------------------------------------------------
 def run_train_step(args, rank, world, device):
-    from rlipv2_b200 import dense, dense_abi, fused_abi, msda_abi, train_step
+    from rlipv2_b200 import dense, dense_abi, fused_abi, lsap_abi, msda_abi, train_step
     text = train_step.synthetic_text(170, 85)
     images_h, targets_h = train_step.synthetic_batch(BATCH, 800, 1333, seed=rank)
-    own = lambda: msda_abi.launch_count() + dense_abi.launch_count() + fused_abi.launch_count()
+    own = lambda: (msda_abi.launch_count() + dense_abi.launch_count() + fused_abi.launch_count()
+                   + lsap_abi.launch_count())
     loss = None
     if args.graphs:
         ts = train_step.GraphedParSeDATrainStep(device=str(device), precision=args.precision, seed=0)

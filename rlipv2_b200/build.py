@@ -26,6 +26,7 @@ TARGETS = {
     "librlipv2_msda.so": (["msda.cu"], []),
     "librlipv2_dense.so": (["dense_tf32.cu"], []),
     "librlipv2_fused.so": (["fused_ops.cu"], []),
+    "librlipv2_lsap.so": (["lsap.cu"], []),
 }
 
 

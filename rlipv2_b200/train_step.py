@@ -153,6 +153,10 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         # instead of at the head of the backward graph (on the critical path behind the assignment)
         self.early_zero = os.environ.get("RLIPV2_EARLY_ZERO", "1") != "0"
         self.stamps = None                      # diagnostic globaltimer stamps (RLIPV2_STAMPS=1, tools/step_anatomy.py)
+        # assignment problems solved on the device by rlipv2_lsap_f32 (bit-identical to scipy, tests/test_lsap_core.py):
+        # no cost D2H, no host solve, no index H2D, no flag wait - the two graphs replay back to back without the host.
+        # Opt-in until it has its A/B on the B200 (written after round 1's GPU budget was spent).
+        self.device_lsap = os.environ.get("RLIPV2_DEVICE_LSAP", "0") == "1"
 
     # the piece of work each graph records -------------------------------------------------------------
     def _stamp(self, i):
@@ -179,7 +183,11 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
             torch.cuda.current_stream(self.device).wait_stream(zero_side)
         layers = self.criterion.layers_of(outputs)
         C, cost_lists = self.criterion.matcher.compute_costs_layers(layers, self.s_targets)   # all layers, one pass
-        self.h_cost.copy_(C, non_blocking=True)
+        if self.device_lsap:
+            from . import lsap_abi
+            lsap_abi.solve(C, self.lsap_plan, self.s_I, self.s_J)
+        else:
+            self.h_cost.copy_(C, non_blocking=True)
         self._stamp(1)
         giou = -torch.stack([cl[0] for cl in cost_lists]) if self.criterion.giou_verb_label else None
         return outputs, giou
@@ -187,7 +195,7 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
     def _loss_backward_step(self, outputs, giou, graph_head=False):
         from .criterion import StackedMatches
         self._stamp(2)
-        if graph_head:
+        if graph_head and not self.device_lsap:
             # captured as the first nodes of graph B: wait for the host's publication of this replay, then fetch
             # the matched indices from the pinned buffers (memcpy nodes with fixed addresses)
             from . import fused_abi
@@ -245,6 +253,8 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
     def _solve_assignment(self):
         """host: LSAP on the pinned cost tensor [layers, bs, nq, T] -> the static device index buffers
         (stacked layout of criterion.StackedMatches: ordered layer, image, match), one H2D copy each"""
+        if self.device_lsap:
+            return                              # _forward_and_costs already left the indices in s_I / s_J
         o = 0
         for li in range(self.h_cost.shape[0]):
             for i, j in self.criterion.matcher.solve(self.h_cost[li], self.sizes):
@@ -273,6 +283,10 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
 
     def check(self):
         """raise if a replay's flag wait timed out (the host never published its assignment)"""
+        if self.device_lsap:
+            from . import lsap_abi
+            lsap_abi.check(self.lsap_plan)
+            return
         if self.captured and self.flag_wait and int(self.d_err.item()) != 0:
             raise RuntimeError(f"backward graph replay {int(self.d_err.item())} timed out waiting for the host assignment")
 
@@ -289,6 +303,11 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         self.h_I, self.h_J = torch.zeros(K, dtype=torch.long).pin_memory(), torch.zeros(K, dtype=torch.long).pin_memory()
         self.s_I, self.s_J = torch.zeros(K, dtype=torch.long, device=dev), torch.zeros(K, dtype=torch.long, device=dev)
         self.np_cost, self.np_I, self.np_J = self.h_cost.numpy(), self.h_I.numpy(), self.h_J.numpy()
+        if self.device_lsap:
+            from . import lsap_abi
+            self.lsap_plan = lsap_abi.Plan(self.sizes, nq, n_layers, dev)
+            assert self.lsap_plan.K == K and self.lsap_plan.ks == self.ks
+            self.flag_wait = False              # nothing for graph B to wait for
         self.h_flag = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.np_flag = self.h_flag.numpy()
         self.d_seq = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -356,8 +375,9 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
                 self._loss_backward_step(outputs, giou)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        from . import dense_abi, fused_abi, msda_abi
-        own = lambda: msda_abi.launch_count() + dense_abi.launch_count() + fused_abi.launch_count()
+        from . import dense_abi, fused_abi, lsap_abi, msda_abi
+        own = lambda: (msda_abi.launch_count() + dense_abi.launch_count() + fused_abi.launch_count()
+                       + lsap_abi.launch_count())
         l0 = own()
         self.graph_a = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_a, stream=self.cap_stream):
@@ -396,6 +416,9 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
     def replay(self):
         """One step on the batch currently held by the static buffers."""
         self.graph_a.replay()
+        if self.device_lsap:
+            self.graph_b.replay()               # the indices are already in s_I / s_J when graph A ends
+            return self.s_loss
         self.done_a.record()
         if not self.flag_wait:
             self.done_a.synchronize()           # costs are in pinned memory now

@@ -227,12 +227,22 @@ def alif_tensor_roofline(device):
 def run_train_step(args, rank, world, device):
     from rlipv2_b200 import dense, dense_abi, fused_abi, lsap_abi, msda_abi, train_step
     text = train_step.synthetic_text(170, 85)
-    images_h, targets_h = train_step.synthetic_batch(BATCH, 800, 1333, seed=rank)
+    batch = args.per_gpu_batch or BATCH
+    images_h, targets_h = train_step.synthetic_batch(batch, 800, 1333, seed=rank)
+    model_args = None
+    if args.backbone != "resnet50" or args.pretrain:
+        # other BASELINE configs on the same step (not the headline line): config 3 = --pretrain (relational pre-training
+        # flags), config 4 = --backbone swin_large --per-gpu-batch 1 (drop_path_rate 0.5)
+        from rlipv2_b200 import models
+        extra = dict(hoi=False, cross_modal_pretrain=True, pseudo_verb=True) if args.pretrain else {}
+        model_args = models.default_args(device=str(device), num_queries=NUM_QUERIES, synthetic_text_encoder=True,
+                                         backbone=args.backbone, drop_path_rate=0.5 if "swin" in args.backbone else 0.2,
+                                         **extra)
     own = lambda: (msda_abi.launch_count() + dense_abi.launch_count() + fused_abi.launch_count()
                    + lsap_abi.launch_count())
     loss = None
     if args.graphs:
-        ts = train_step.GraphedParSeDATrainStep(device=str(device), precision=args.precision, seed=0)
+        ts = train_step.GraphedParSeDATrainStep(args=model_args, device=str(device), precision=args.precision, seed=0)
         ts.capture(images_h, targets_h, text, warmup=max(1, args.warmup - 1))
         per_step = ts.own_launches_per_step            # this repo's kernel nodes in the two captured graphs
 
@@ -243,7 +253,7 @@ def run_train_step(args, rank, world, device):
         def e2e(i):
             float(ts.step(images_h, targets_h))             # H2D inside, loss read back (4 bytes D2H)
     else:
-        ts = train_step.ParSeDATrainStep(device=str(device), precision=args.precision, seed=0)
+        ts = train_step.ParSeDATrainStep(args=model_args, device=str(device), precision=args.precision, seed=0)
         samples, targets = ts.to_device(images_h, targets_h)
         per_step = None
 
@@ -270,19 +280,22 @@ def run_train_step(args, rank, world, device):
     ms, ms_e2e = max_over_ranks([ms, ms_e2e], device, world)
     nparams = sum(p.numel() for p in ts.params)
     line = {
-        "metric": METRIC, "value": BATCH * world / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
+        "metric": METRIC if model_args is None else METRIC.replace("R50", args.backbone) + (" (pre-train flags)" if args.pretrain else ""),
+        "value": batch * world / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 storage, " + ("tf32 tensor-core products" if dense.matmul_precision() == "tf32" else "fp32 products"),
         "data": "synthetic",
-        "config": {"workload": "train_step: RLIPv2-ParSeDA R50 HICO-DET fine-tune step (BASELINE config 2), batch 2 x 3x800x1333 "
-                               "per GPU, 300 queries, 256 label strings, AdamW, clip 0.1, random-init weights",
-                   "per_gpu_batch": BATCH, "global_batch": BATCH * world, "trainable_params": nparams,
+        "config": {"workload": ("train_step: RLIPv2-ParSeDA R50 HICO-DET fine-tune step (BASELINE config 2), batch 2 x 3x800x1333 "
+                                "per GPU, 300 queries, 256 label strings, AdamW, clip 0.1, random-init weights") if model_args is None else
+                               (f"train_step: RLIPv2-ParSeDA {args.backbone}, {'relational pre-train' if args.pretrain else 'HICO-DET fine-tune'} "
+                                f"flags, batch {batch} x 3x800x1333 per GPU, 300 queries, 256 label strings, AdamW, clip 0.1, random-init weights"),
+                   "per_gpu_batch": batch, "global_batch": batch * world, "trainable_params": nparams,
                    "l2": "working set >> L2 (activations > 2 GB per image)",
                    "execution": "2 CUDA graphs per step + host LSAP" if args.graphs else "eager",
                    "parallelism": (f"dp{world} (flat-gradient NCCL all-reduce in graph)" if args.graphs else
                                    f"dp{world} (DDP static_graph, NCCL)") if world > 1 else "dp1"},
         "clocks": clk.summary(), "gpu_launches": int(launches), "final_loss": final_loss,
-        "e2e": {"value": BATCH * world / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
+        "e2e": {"value": batch * world / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
     }
     if rank == 0 and not args.no_roofline:
@@ -358,6 +371,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train_step", choices=["train_step", "msda_step"])
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--backbone", default="resnet50", help="train_step only: e.g. swin_large (BASELINE config 4; not the headline)")
+    ap.add_argument("--per-gpu-batch", type=int, default=0, help="train_step only: images per GPU (default 2)")
+    ap.add_argument("--pretrain", action="store_true", help="train_step only: --cross_modal_pretrain --pseudo_verb flags (config 3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true", help="A/B runs: skip the kernel micro-benchmarks")
     ap.add_argument("--no-graphs", dest="graphs", action="store_false", help="eager step instead of CUDA graphs")

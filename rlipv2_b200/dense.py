@@ -81,6 +81,11 @@ class _ParamGradSide:
         _param_grad_pending.add(self.device)
 
 
+def pending_param_grad_streams():
+    """the side streams that hold parameter-gradient work issued since the last join"""
+    return [_param_grad_streams[dev] for dev in _param_grad_pending]
+
+
 def join_param_grad_stream(device=None):
     """make the current stream wait for the parameter-gradient side stream(s) (call after backward(), before the
     gradients are read)"""

@@ -82,3 +82,93 @@ class FlatParams:
         if max_norm > 0:
             coef = torch.clamp(max_norm / (self.flat_grad.norm() + 1e-6), max=1.0)
             self.flat_grad.mul_(coef)
+
+
+class EarlyReducer:
+    """All-reduce ranges of the flat gradient buffer as soon as `grad_ready` markers say they are final, on a
+    communication stream beside the rest of the backward - the flat-buffer counterpart of DDP's bucket hooks
+    (main.py:515-517).  Sum semantics (like `allreduce_sum_`): `clip_scale` folds the 1 / world into the optimizer.
+
+    entries: [(tags, start, end)] - launch the all-reduce of flat_grad[start:end] once every tag of `tags` has fired.
+    Stream order: a marker fires on the stream its activation was produced on; an event is recorded there at that moment
+    and the launch waits for the events of all the entry's tags - NOT for the streams' later tails (when the last tag
+    fires the host may already have queued the backbone's backward on the main stream; waiting for that would undo
+    the overlap).  wait_streams: callable -> the SIDE streams that may hold gradient writes of the ranges (parameter-
+    gradient stream of dense.py, label / value-projection / criterion streams); they carry nothing but such work, so the
+    launch waits for their tails.  While a CUDA graph is being captured, side streams that are not part of the capture
+    are skipped (nothing of this backward can be on them).
+    Every rank must see the same entries and the same firing order (same model, same autograd graph: it does).
+
+        reducer.begin()            # before loss.backward(); markers call reducer.on_tag(tag) from the backward
+        loss.backward()
+        reducer.finish()           # all-reduce whatever was not launched early, then join the communication stream
+    """
+
+    def __init__(self, flat, entries, wait_streams=None, force=False):
+        self.flat = flat
+        self.entries = [(frozenset(t), int(s), int(e)) for t, s, e in entries if e > s]
+        for _, s, e in self.entries:
+            assert 0 <= s < e <= flat.flat_grad.numel()
+        ordered = sorted((s, e) for _, s, e in self.entries)
+        assert all(a[1] <= b[0] for a, b in zip(ordered, ordered[1:])), "early-reduce ranges overlap"
+        self.wait_streams = wait_streams or (lambda: [])
+        self.active = force or world_size() > 1
+        self.cuda = flat.flat_grad.is_cuda
+        self.comm = torch.cuda.Stream(flat.flat_grad.device) if self.cuda else None
+        self.fired, self.launched, self.events = set(), [], {}
+
+    def begin(self):
+        self.fired, self.launched, self.events = set(), [], {}
+
+    def _reduce(self, start, end):
+        if world_size() > 1:
+            dist.all_reduce(self.flat.flat_grad[start:end])
+
+    def on_tag(self, tag):
+        if not self.active:
+            return
+        if tag in self.fired:
+            return
+        self.fired.add(tag)
+        if self.cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.flat.flat_grad.device))
+            self.events[tag] = ev
+        for tags, start, end in self.entries:
+            if (start, end) in self.launched or not tags <= self.fired:
+                continue
+            self.launched.append((start, end))
+            if self.cuda:
+                for t in tags:
+                    self.comm.wait_event(self.events[t])
+                capturing = torch.cuda.is_current_stream_capturing()
+                for s in self.wait_streams():
+                    if capturing:
+                        with torch.cuda.stream(s):
+                            if not torch.cuda.is_current_stream_capturing():
+                                continue
+                    self.comm.wait_stream(s)
+                with torch.cuda.stream(self.comm):
+                    self._reduce(start, end)
+            else:
+                self._reduce(start, end)
+
+    def remaining(self):
+        """the parts of the buffer no early launch covered, as maximal ranges"""
+        out, pos = [], 0
+        for s, e in sorted(self.launched):
+            if s > pos:
+                out.append((pos, s))
+            pos = max(pos, e)
+        n = self.flat.flat_grad.numel()
+        if pos < n:
+            out.append((pos, n))
+        return out
+
+    def finish(self):
+        if not self.active:
+            return
+        for s, e in self.remaining():
+            self._reduce(s, e)
+        if self.cuda and self.launched:                 # (an unused communication stream is not part of a capture)
+            torch.cuda.current_stream(self.flat.flat_grad.device).wait_stream(self.comm)

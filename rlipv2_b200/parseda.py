@@ -15,7 +15,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import dense
+from . import dense, grad_ready
 from .nested import NestedTensor, inverse_sigmoid, nested_tensor_from_tensor_list
 from .parseda_transformer import MLP
 
@@ -105,6 +105,8 @@ class RLIP_ParSeDA(nn.Module):
         if _TEXT_STREAM and samples.tensors.is_cuda and self.transformer._is_label_text(text):
             text = self.transformer.encode_text_async(text, samples.tensors.device)   # overlaps the backbone
         features, pos = self.backbone(samples)
+        for i, feat in enumerate(features):              # no-ops unless the data-parallel step installed a callback
+            feat.tensors = grad_ready.mark(feat.tensors, f"image{i}")
         srcs, masks = [], []
         norms = [p[1] for p in self.input_proj]
         if (self.num_feature_levels <= len(features) + 1

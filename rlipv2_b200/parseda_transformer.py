@@ -29,7 +29,7 @@ from torch import nn
 from torch.nn.init import normal_
 from torch.nn.utils.rnn import pad_sequence
 
-from . import dense
+from . import dense, grad_ready
 from .alif import FeatureResizer, RLIPv2_VLFuse
 from .ms_deform_attn import MSDeformAttn
 from .nested import inverse_sigmoid
@@ -541,6 +541,7 @@ class RLIP_ParSeDABDeformableTransformer_v2(nn.Module):
         sums = tok["sums"]
         obj_pred_names_sums = torch.tensor(sums)
         pooled = pooled_text(self.text_encoder, tok["input_ids"], tok["attention_mask"])
+        pooled = grad_ready.mark(pooled, "text")         # no-op unless the data-parallel step installed a callback
         i, objs, preds = 0, [], []
         for n_obj, n_pred in sums:
             objs.append(pooled[i:i + n_obj])

@@ -48,6 +48,29 @@ def synthetic_batch(batch, height=800, width=1333, n_obj=170, n_verb=85, triplet
     return images, targets
 
 
+TEXT_TOWER_SPLIT = 6          # text-tower layers [split, 12) + pooler are reduced when the backward passes layer `split`
+
+
+def early_reduce_entries(names, offsets, group_ranges, image_tags=None):
+    """[(tags, start, end)] for flat_dp.EarlyReducer from the flat layout of the graphed step (groups in the order of
+    main.py:525-537: everything else | backbone | text encoder; parameters in named_parameters order inside a group).
+    image_tags: the 'image<i>' markers the forward applies (default: three backbone levels)."""
+    tags0 = {t for t in (image_tags or {"image0", "image1", "image2"}) if t.startswith("image")} | {"text"}
+    entries = [(tags0, group_ranges[0][0], group_ranges[0][1])]
+
+    def first(prefix):
+        for n, o in zip(names, offsets):
+            if "text_encoder" in n and prefix in n:
+                return o
+        return None
+
+    lo, mid, end = first("encoder.layer.0."), first(f"encoder.layer.{TEXT_TOWER_SPLIT}."), group_ranges[2][1]
+    if lo is not None and mid is not None and group_ranges[2][0] <= lo < mid < end:
+        entries.append(({"text_mid"}, mid, end))            # layers split.. and the pooler (named after the layers)
+        entries.append(({"text_emb"}, lo, mid))             # layers 0 .. split-1
+    return entries
+
+
 class ParSeDATrainStep:
     """model + criterion + optimizer; `step(images_host, targets_host, text)` runs one iteration and
     returns the (device) total loss."""
@@ -157,6 +180,14 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         # no cost D2H, no host solve, no index H2D, no flag wait - the two graphs replay back to back without the host.
         # Opt-in until it has its A/B on the B200 (written after round 1's GPU budget was spent).
         self.device_lsap = os.environ.get("RLIPV2_DEVICE_LSAP", "0") == "1"
+        # world > 1: ranges of the flat gradient buffer all-reduced on a communication stream as soon as grad_ready
+        # markers say they are final (transformer + heads when the backward reaches the backbone features; text-tower
+        # layers as their half of the tower finishes), instead of one all-reduce behind the whole backward.  Opt-in until
+        # it has its 2- and 8-GPU A/B (written after round 1's GPU budget was spent).
+        # ("force": install the markers / events / communication stream at world size 1 too - plumbing test on one GPU)
+        self.overlap_allreduce = os.environ.get("RLIPV2_ALLREDUCE_OVERLAP", "0") in ("1", "force") and not self.gather_grads
+        self.overlap_force = os.environ.get("RLIPV2_ALLREDUCE_OVERLAP", "0") == "force"
+        self.reducer = None
 
     # the piece of work each graph records -------------------------------------------------------------
     def _stamp(self, i):
@@ -216,9 +247,14 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         else:
             if not self.early_zero:
                 self.flat_grad.zero_()
+            if self.reducer is not None:
+                self.reducer.begin()
             total.backward()
         dense.join_param_grad_stream()               # parameter gradients formed on the side stream (dense.py)
-        if self.fused_clip:
+        if self.reducer is not None and self.fused_clip:
+            self.reducer.finish()                    # whatever the markers did not launch early + join the comm stream
+            self._adamw_step(self.flat.clip_scale(self.clip_max_norm))
+        elif self.fused_clip:
             self.flat.allreduce_sum_()               # one NCCL all-reduce of the flat buffer (world > 1)
             self._adamw_step(self.flat.clip_scale(self.clip_max_norm))   # clip_grad_norm_ = one norm; scale in AdamW
         else:
@@ -241,6 +277,36 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         fused_abi.gather_chunks(self.d_gather, n, self.flat_grad)
         for p in self.params:                                       # the buffers are free for reuse from here on
             p.grad = None
+
+    def _install_early_reducer(self, names, force=False):
+        """names: parameter names in the order of self.params / self.param_offsets (group by group)"""
+        from . import grad_ready
+        from .flat_dp import EarlyReducer
+        entries = early_reduce_entries(names, self.param_offsets, self.group_ranges)
+        self.reducer = EarlyReducer(self.flat, entries, wait_streams=self._gradient_side_streams, force=force)
+        grad_ready.set_callback(self.reducer.on_tag)
+        self._marker_hooks = grad_ready.install_text_tower_markers(self.module.transformer.text_encoder, TEXT_TOWER_SPLIT)
+        return entries
+
+    def _gradient_side_streams(self):
+        """side streams (never the main one) that backward nodes writing parameter gradients may have been queued on"""
+        from .criterion import _BRANCH_STREAMS
+        streams = list(dense.pending_param_grad_streams())
+        for m in self.module.modules():
+            for attr in ("_lang_stream", "_value_stream"):
+                st = getattr(m, attr, None)
+                if st is not None:
+                    streams.append(st)
+        streams += _BRANCH_STREAMS.get(str(self.device), [])
+        return streams
+
+    def uninstall_early_reducer(self):
+        from . import grad_ready
+        if self.reducer is not None:
+            grad_ready.set_callback(None)
+            for h in self._marker_hooks:
+                h.remove()
+            self.reducer = None
 
     def _adamw_step(self, grad_scale=None):
         from . import fused_abi
@@ -359,6 +425,10 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
             self.h_gather = torch.zeros(rows, 3, dtype=torch.int64).pin_memory()
             self.d_gather = torch.zeros(rows, 3, dtype=torch.int64, device=dev)
         self.optimizer = None                       # replaced by the flat AdamW kernel (fused_ops.cu)
+        if self.overlap_allreduce and self.fused_clip and (self.world > 1 or self.overlap_force):
+            other = [n for n, _ in named if "backbone" not in n and "text_encoder" not in n]
+            self._install_early_reducer(other + [n for n, _ in named if "backbone" in n]
+                                        + [n for n, _ in named if "text_encoder" in n], force=self.overlap_force)
         if self.world > 1:                      # identical replicas (same seed), made certain
             dist.broadcast(self.flat_param, 0)
             for p in self.module.parameters():

@@ -3,6 +3,8 @@
 * `FlatParams` (the flat-gradient data-parallel scheme of the graphed step): after the single all-reduce the flat
   gradient equals the gradient of the global-batch loss, `clip_` equals `clip_grad_norm_`, and the replicas stay
   bit-identical after an optimizer step on the views.
+* `EarlyReducer` + `grad_ready` markers (the overlapped all-reduce): ranges reduced from inside the backward plus the
+  remainder after it leave exactly what the single whole-buffer all-reduce leaves.
 * `SetCriterionHOI`: `num_interactions` is all-reduced over ranks (/root/reference/models/hoi.py:4737-4740), so the
   rank-mean of the box losses equals the single-process loss over the union of the ranks' images.
 """
@@ -58,6 +60,22 @@ def _worker(rank, port, q):
         flat.flat_grad.copy_(local)
         flat.allreduce_sum_()
         g_scaled = flat.flat_grad * flat.clip_scale(0.1)
+        g_sum = flat.flat_grad.clone()
+        # the overlapped variant: ranges all-reduced from gradient-readiness markers inside the backward, the rest after it
+        from rlipv2_b200 import grad_ready
+        from rlipv2_b200.flat_dp import EarlyReducer
+        (s0, e0, _), (s1, e1, _) = flat.group_ranges
+        reducer = EarlyReducer(flat, [({"after_first"}, s1, e1)])          # second Linear's range: final once its input's
+        assert reducer.active                                              # gradient has been formed
+        grad_ready.set_callback(reducer.on_tag)
+        flat.zero_grad()
+        reducer.begin()
+        h = grad_ready.mark(model[1](model[0](x[lo:lo + 4])), "after_first")
+        torch.nn.functional.mse_loss(model[2](h), y[lo:lo + 4]).backward()
+        assert reducer.launched == [(s1, e1)] and reducer.remaining()[0] == (0, s1)
+        reducer.finish()
+        grad_ready.set_callback(None)
+        g_early = flat.flat_grad.clone()
         flat.flat_grad.copy_(g_after_clip)
         opt = torch.optim.AdamW([{"params": pl, "lr": lr} for pl, lr in _groups(model)], weight_decay=1e-4)
         opt.step()                                     # updates the views == the flat buffer
@@ -69,7 +87,8 @@ def _worker(rank, port, q):
         keys = ["loss_sub_bbox", "loss_sub_giou", "loss_sub_bbox_0", "loss_sub_giou_1"]
         vec = torch.stack([losses[k].detach().reshape(()) for k in keys])
         dist.all_reduce(vec)
-        q.put((rank, g_after_reduce, g_after_clip, flat.flat_param.clone(), flat.group_ranges, vec / WORLD, g_scaled))
+        q.put((rank, g_after_reduce, g_after_clip, flat.flat_param.clone(), flat.group_ranges, vec / WORLD, g_scaled,
+               g_sum, g_early))
     finally:
         dist.destroy_process_group()
 
@@ -129,6 +148,7 @@ def test_two_gloo_ranks():
     for r in res:
         torch.testing.assert_close(r[2], g_clip, rtol=1e-5, atol=1e-7)
         torch.testing.assert_close(r[6], g_clip, rtol=1e-5, atol=1e-7)      # sum + clip_scale == mean + clip_
+        assert torch.equal(r[7], r[8])                   # marker-driven partial all-reduces == the one whole all-reduce
     opt = torch.optim.AdamW([{"params": pl, "lr": lr} for pl, lr in _groups(ref)], weight_decay=1e-4)
     opt.step()
     p_ref = flatten([p.data for p in ref.parameters()], ranges)

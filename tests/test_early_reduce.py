@@ -6,7 +6,11 @@ import pytest
 import torch
 
 
-def test_gradients_are_final_when_their_markers_fire(msda_cpu_stub):
+@pytest.mark.parametrize("text_first", [False, True])
+def test_gradients_are_final_when_their_markers_fire(msda_cpu_stub, monkeypatch, text_first):
+    """text_first=True reproduces the autograd-node creation order of the GPU path on CPU: there the text tower is started
+    on a side stream BEFORE the backbone (parseda.py `encode_text_async`), so its nodes are older than the backbone's and the
+    'text' marker fires after the backbone's backward has been queued."""
     from oracle.gen_golden_model import OBJ_NAMES, VERB_NAMES, make_step_inputs
     from rlipv2_b200 import dense, grad_ready, models
     from rlipv2_b200.train_step import TEXT_TOWER_SPLIT
@@ -40,6 +44,10 @@ def test_gradients_are_final_when_their_markers_fire(msda_cpu_stub):
     hooks = grad_ready.install_text_tower_markers(model.transformer.text_encoder, TEXT_TOWER_SPLIT)
     try:
         imgs, targets, text = make_step_inputs()
+        if text_first:
+            tr = type(model.transformer)
+            monkeypatch.setattr(tr, "_join_text", staticmethod(lambda handle, device: handle["_async_text"]))
+            text = {"_async_text": model.transformer.encode_text(text, torch.device("cpu")), "_stream": None}
         cache = model(imgs, encode_and_save=True, text=text, targets=targets)
         out = model(imgs, encode_and_save=False, memory_cache=cache, text=text, targets=targets)
         assert grad_ready.applied_tags() == {"image0", "image1", "image2", "text", "text_mid", "text_emb"}
@@ -51,6 +59,8 @@ def test_gradients_are_final_when_their_markers_fire(msda_cpu_stub):
             h.remove()
     assert set(order) == {"image0", "image1", "image2", "text", "text_mid", "text_emb"} and len(order) == 6
     assert order.index("text_mid") < order.index("text_emb")
+    if text_first:
+        assert order.index("text") > max(order.index(f"image{i}") for i in range(3))     # the GPU path's order
     assert set(snaps) == set(needs)
     n_checked = 0
     for key, snap in snaps.items():

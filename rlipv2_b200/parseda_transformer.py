@@ -288,6 +288,9 @@ class RLIPv2_DeformableTransformerEncoder(nn.Module):
         return vis["src"], multi_lay_lang
 
 
+_SDPA_QUERY_ATTN = os.environ.get("RLIPV2_SDPA_QUERY_ATTN", "0") == "1"
+
+
 class QuerySelfAttention(nn.Module):
     """8x32 self-attention among the queries with nn.MultiheadAttention's parameter layout
     (`in_proj_weight [3C, C]`, `in_proj_bias`, `out_proj`), batch-first."""
@@ -310,6 +313,12 @@ class QuerySelfAttention(nn.Module):
         q = q.view(b, t, h, d).transpose(1, 2)
         k = k.view(b, t, h, d).transpose(1, 2)
         v = v.view(b, t, h, d).transpose(1, 2)
+        if _SDPA_QUERY_ATTN and q.is_cuda and dense.matmul_precision() == "tf32":
+            # one fused-attention call each way instead of scale / bmm / softmax / bmm (+ their ~12 backward kernels) on the
+            # decoders' launch-bound chain; library kernel like the batched GEMMs it replaces.  Opt-in until measured.
+            o = F.scaled_dot_product_attention(q, k, v, dropout_p=self.dropout if self.training else 0.0, scale=d ** -0.5)
+            o = o.transpose(1, 2).reshape(b, t, c)
+            return dense.linear(o, self.out_proj.weight, self.out_proj.bias)
         p = torch.softmax(torch.matmul(q * (d ** -0.5), k.transpose(-1, -2)), dim=-1)
         if self.training and self.dropout > 0:
             p = F.dropout(p, self.dropout)

@@ -18,7 +18,8 @@ timeout 400 $B > gpurun_out/${TAG}_base.json 2> gpurun_out/${TAG}_base.err
 RLIPV2_DEVICE_LSAP=1 timeout 400 $B > gpurun_out/${TAG}_device_lsap.json 2> gpurun_out/${TAG}_device_lsap.err
 RLIPV2_GN_TOKENS=1 timeout 400 $B > gpurun_out/${TAG}_gn_tokens.json 2> gpurun_out/${TAG}_gn_tokens.err
 RLIPV2_DEVICE_LSAP=1 RLIPV2_GN_TOKENS=1 timeout 400 $B > gpurun_out/${TAG}_both.json 2> gpurun_out/${TAG}_both.err
-for f in base device_lsap gn_tokens both; do python - <<PY
+RLIPV2_SDPA_QUERY_ATTN=1 timeout 400 $B > gpurun_out/${TAG}_sdpa_query.json 2> gpurun_out/${TAG}_sdpa_query.err
+for f in base device_lsap gn_tokens both sdpa_query; do python - <<PY
 import json
 try:
     j = json.loads(open("gpurun_out/${TAG}_$f.json").read().strip().splitlines()[-1])

@@ -175,8 +175,9 @@ class RLIP_ParSeDA(nn.Module):
         # two 3-layer MLPs + inverse_sigmoid per level a second time.
         refined = getattr(self.transformer.ho_decoder, "refined_boxes", None)
         self.transformer.ho_decoder.refined_boxes = None
-        if not (self.with_box_refine and refined is not None and len(refined) == hs_h.shape[0]):
-            refined = None
+        if not (self.with_box_refine and refined is not None and len(refined) == hs_h.shape[0]
+                and getattr(self.transformer, "fusion_type", "GLIP_attn") != "MDETR_attn"):
+            refined = None                 # (late fusion returns re-encoded states: the heads must see those)
         n_lvl = hs_h.shape[0]
         for lvl in range(n_lvl):
             if refined is not None:

@@ -288,6 +288,27 @@ class RLIPv2_DeformableTransformerEncoder(nn.Module):
         return vis["src"], multi_lay_lang
 
 
+class DeformableTransformerEncoder(nn.Module):
+    """the plain deformable encoder (no early fusion) of the `--fusion_type MDETR_attn / no_fusion` ablations
+    (dab_deformable/deformable_transformer.py:1303-1343)"""
+
+    def __init__(self, encoder_layer, num_layers):
+        super().__init__()
+        self.layers = _get_clones(encoder_layer, num_layers)
+        self.num_layers = num_layers
+
+    def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None,
+                spatial_shapes_host=None):
+        if spatial_shapes_host is None:
+            spatial_shapes_host = [tuple(int(v) for v in hw) for hw in spatial_shapes.tolist()]
+        reference_points = RLIPv2_DeformableTransformerEncoder.get_reference_points(spatial_shapes_host, valid_ratios,
+                                                                                    src.device)
+        for layer in self.layers:
+            src = layer(src, pos, reference_points, spatial_shapes, level_start_index, padding_mask,
+                        spatial_shapes_host=spatial_shapes_host)
+        return src
+
+
 _SDPA_QUERY_ATTN = os.environ.get("RLIPV2_SDPA_QUERY_ATTN", "0") == "1"
 
 
@@ -471,8 +492,14 @@ class RLIP_ParSeDABDeformableTransformer_v2(nn.Module):
         self.two_stage_num_proposals = two_stage_num_proposals
         self.use_dab = use_dab
         self.fusion_type = args.fusion_type
+        if self.fusion_type not in ("GLIP_attn", "MDETR_attn", "no_fusion"):
+            raise ValueError(f"unknown --fusion_type {self.fusion_type}")
         if self.fusion_type != "GLIP_attn":
-            raise NotImplementedError("only --fusion_type GLIP_attn (ALIF) is on the hot path")
+            # ablations of the paper (scripts/RLIP_ParSeDA/*_MDETR.sh): plain deformable encoder (:252-256); module creation
+            # order follows the reference so that seeded initialisations agree
+            self.encoder = DeformableTransformerEncoder(
+                DeformableTransformerEncoderLayer(d_model, dim_feedforward, dropout, activation, num_feature_levels, nhead,
+                                                  enc_n_points), num_encoder_layers)
 
         ho_layer = DeformableTransformerDecoderLayer(d_model, dim_feedforward, dropout, activation,
                                                      num_feature_levels, nhead, dec_n_points)
@@ -486,12 +513,22 @@ class RLIP_ParSeDABDeformableTransformer_v2(nn.Module):
         self.level_embed = nn.Parameter(torch.Tensor(num_feature_levels, d_model))
 
         from .text_encoder import roberta_base_config
-        enc_layer = DeformableTransformerEncoderLayer(d_model, dim_feedforward, dropout, activation,
-                                                      num_feature_levels, nhead, enc_n_points)
-        self.encoder = RLIPv2_DeformableTransformerEncoder(
-            enc_layer, RobertaLayer(roberta_base_config()), RLIPv2_VLFuse(args), num_encoder_layers,
-            fusion_interval=args.fusion_interval, fusion_last_vis=args.fusion_last_vis,
-            lang_aux_loss=args.lang_aux_loss)
+        if self.fusion_type == "MDETR_attn":
+            # late fusion: two pre-norm encoder stacks over (decoder states ; label embeddings) (:278-291)
+            from .parse_detr import CrossModelTransformerEncoder, TransformerEncoderLayer
+            self.obj_fusion = CrossModelTransformerEncoder(
+                TransformerEncoderLayer(d_model, 8, dim_feedforward, dropout, activation, normalize_before=True),
+                num_decoder_layers, nn.LayerNorm(d_model), return_intermediate=True)
+            self.verb_fusion = CrossModelTransformerEncoder(
+                TransformerEncoderLayer(d_model, 8, dim_feedforward, dropout, activation, normalize_before=True),
+                num_decoder_layers, nn.LayerNorm(d_model), return_intermediate=True)
+        elif self.fusion_type == "GLIP_attn":
+            enc_layer = DeformableTransformerEncoderLayer(d_model, dim_feedforward, dropout, activation,
+                                                          num_feature_levels, nhead, enc_n_points)
+            self.encoder = RLIPv2_DeformableTransformerEncoder(
+                enc_layer, RobertaLayer(roberta_base_config()), RLIPv2_VLFuse(args), num_encoder_layers,
+                fusion_interval=args.fusion_interval, fusion_last_vis=args.fusion_last_vis,
+                lang_aux_loss=args.lang_aux_loss)
 
         self._reset_parameters()
 
@@ -597,7 +634,7 @@ class RLIP_ParSeDABDeformableTransformer_v2(nn.Module):
         if encode_and_save:
             return self._encode(srcs, masks, pos_embeds, query_embed, text)
         return self._decode(masks, query_embed, text_memory, img_memory, spatial_shapes, level_start_index,
-                            valid_ratios, spatial_shapes_host)
+                            valid_ratios, spatial_shapes_host, text_attention_mask, obj_pred_names_sums)
 
     def _encode(self, srcs, masks, pos_embeds, query_embed, text):
         src_flatten, mask_flatten, lvl_pos_flatten, shapes_host = [], [], [], []
@@ -622,6 +659,21 @@ class RLIP_ParSeDABDeformableTransformer_v2(nn.Module):
         elif self._is_label_text(text):                                     # training: label strings
             text_memory, text_attention_mask, obj_pred_names_sums = self.encode_text(text, device)
             text = None
+        if self.fusion_type != "GLIP_attn":
+            # no early fusion (:552-562, :588-595): image tokens through the plain encoder, labels resized as they are
+            img_memory = self.encoder(src_flatten, spatial_shapes, level_start_index, valid_ratios, lvl_pos_flatten,
+                                      mask_flatten, spatial_shapes_host=shapes_host)
+            if text is None:
+                text_memory_resized = self.resizer(text_memory)
+                if text_memory_resized.shape[1] != bs:
+                    text_memory_resized = text_memory_resized.repeat(1, bs, 1)
+                    text_attention_mask = text_attention_mask.repeat(1, bs)
+            else:                                                           # eval: already resized by the caller
+                text_attention_mask, text_memory_resized, obj_pred_names_sums = text
+                text_memory = text_memory_resized
+            return self._memory_cache(text_memory, text_memory_resized, img_memory, mask_flatten, text_attention_mask,
+                                      lvl_pos_flatten, query_embed, obj_pred_names_sums, spatial_shapes,
+                                      level_start_index, valid_ratios, shapes_host)
         if text is None:
             lang = text_memory
             if lang.shape[1] != bs:
@@ -638,6 +690,14 @@ class RLIP_ParSeDABDeformableTransformer_v2(nn.Module):
             text_memory_resized = self.resizer(lang_out.transpose(0, 1))
         else:                                                               # [3, bs, Tl, 768] with lang_aux_loss
             text_memory_resized = self.resizer(lang_out.transpose(1, 2))
+        return self._memory_cache(text_memory, text_memory_resized, img_memory, mask_flatten, text_attention_mask,
+                                  lvl_pos_flatten, query_embed, obj_pred_names_sums, spatial_shapes, level_start_index,
+                                  valid_ratios, shapes_host)
+
+    @staticmethod
+    def _memory_cache(text_memory, text_memory_resized, img_memory, mask_flatten, text_attention_mask, lvl_pos_flatten,
+                      query_embed, obj_pred_names_sums, spatial_shapes, level_start_index, valid_ratios, shapes_host):
+        """the phase-A dictionary (:598-613)"""
         return {
             "text_memory_bf_resize": text_memory,
             "text_memory_resized": text_memory_resized,
@@ -654,8 +714,20 @@ class RLIP_ParSeDABDeformableTransformer_v2(nn.Module):
             "spatial_shapes_host": shapes_host,        # extra key: lets phase B skip the shape syncs
         }
 
+    def _late_fusion(self, fusion, hs_last, text, text_mask):
+        """`--fusion_type MDETR_attn` (:703-733): the last decoder level's states and the label embeddings as ONE sequence
+        through a pre-norm encoder stack (labels padded per `text_mask`); every layer's output is split back into
+        (states [layers, bs, nq, C], labels [layers, n_text, bs, C])"""
+        n_text = text.shape[0]
+        seq = torch.cat((hs_last.permute(1, 0, 2), text), dim=0)
+        pad = torch.cat((torch.zeros(hs_last.shape[:2], dtype=torch.bool, device=hs_last.device), text_mask.permute(1, 0)),
+                        dim=1)
+        out = fusion(seq, src_key_padding_mask=pad)                      # [layers, nq + n_text, bs, C]
+        nq = out.shape[1] - n_text
+        return out[:, :nq].permute(0, 2, 1, 3), out[:, nq:]
+
     def _decode(self, mask_flatten, query_embed, text_memory, img_memory, spatial_shapes, level_start_index,
-                valid_ratios, spatial_shapes_host):
+                valid_ratios, spatial_shapes_host, text_attention_mask=None, obj_pred_names_sums=None):
         bs = img_memory.shape[0]
         c = self.d_model
         nq = query_embed.shape[0]
@@ -679,6 +751,15 @@ class RLIP_ParSeDABDeformableTransformer_v2(nn.Module):
         hs_verb, _ = self.verb_decoder(merge_verb_tgt, inter_refs[-1], img_memory, spatial_shapes,
                                        level_start_index, valid_ratios, query_pos=None,
                                        src_padding_mask=mask_flatten, spatial_shapes_host=spatial_shapes_host)
+        if self.fusion_type == "MDETR_attn":
+            n_obj, n_pred = int(obj_pred_names_sums[:, 0].max()), int(obj_pred_names_sums[:, 1].max())
+            assert n_obj + n_pred == text_memory.shape[0] == text_attention_mask.shape[0]
+            hs_ho_dec, obj_text_dec = self._late_fusion(self.obj_fusion, hs_ho[-1], text_memory[:n_obj],
+                                                        text_attention_mask[:n_obj])
+            hs_verb_dec, pred_text_dec = self._late_fusion(self.verb_fusion, hs_verb[-1], text_memory[n_obj:],
+                                                           text_attention_mask[n_obj:])
+            text_dec = torch.cat((obj_text_dec, pred_text_dec), dim=1)
+            return hs_ho_dec, hs_verb_dec, text_dec, init_reference_out, inter_refs, hs_ho, hs_verb, None, None
         hs_layer = hs_ho.shape[0]
         if text_memory.dim() == 4 and text_memory.shape[0] == hs_layer:
             text_dec = text_memory

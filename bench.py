@@ -183,7 +183,13 @@ def alif_tensor_roofline(device):
         w = torch.randn(N_, K_, device=device) * K_ ** -0.5
         b = torch.randn(N_, device=device)
         ops.append((x, w, b))
-    run = lambda: [dense_abi.linear_tf32(x, w, b, 0) for x, w, b in ops]
+    splitk = os.environ.get("RLIPV2_SPLITK_FWD", "0") == "1"          # A/B: split-K forward for the long-K projections
+
+    def one(x, w, b):
+        sp = dense_abi.splitk_splits(x.shape[0], w.shape[0], w.shape[1]) if splitk else 1
+        return dense_abi.linear_splitk_tf32(x, w, b, sp) if sp > 1 else dense_abi.linear_tf32(x, w, b, 0)
+
+    run = lambda: [one(x, w, b) for x, w, b in ops]
     for _ in range(3):
         run()
     torch.cuda.synchronize()
@@ -212,7 +218,8 @@ def alif_tensor_roofline(device):
         src = "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 = half the bf16 rate)"
     except Exception:
         pass
-    return {"bound": "tensor", "kernel": "linear_tf32_kernel (tcgen05.mma kind::tf32) on the 6 ALIF projections of one fusion layer, batch 2",
+    return {"bound": "tensor", "kernel": "linear_tf32_kernel (tcgen05.mma kind::tf32) on the 6 ALIF projections of one fusion layer, batch 2"
+                                          + (" [split-K gemm_tf32_kernel for K >= 768]" if splitk else ""),
             "achieved": flops / t / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / t / 1e12 / peak, "peak_src": src,
             "us_per_layer": t * 1e6, "flops_per_layer": flops,
             "ncu": "sm__pipe_tensor_cycles_active 14.0 % (v_proj, K = 256) .. 27.8 % (l_proj, K = 768) "

@@ -59,6 +59,15 @@ int rlipv2_dense_dgrad_tf32(const float *g, const float *w, float *dx, const flo
 int rlipv2_dense_linear_tf32_rowmask(const float *x, const float *w, const float *bias, const unsigned char *rowmask,
                                      float *y, int M, int N, int K, int act, void *stream);
 
+/* Split-K variant of rlipv2_dense_linear_tf32 (no activation) for the small-M / long-K linears of ALIF and the RobertaLayer
+ * (/root/reference/models/fuse_helper.py:463-464 out_v_proj / out_l_proj with K = 2048, :370-373 the label-side
+ * in-projections with K = 768, models/modeling_roberta.py:332 FFN-down with K = 3072): with a few hundred rows these fill
+ * 4-64 of 148 SMs with one CTA per output tile, so the K axis is split over `splits` CTAs per tile whose partial tiles are
+ * reduced into y with fp32 reductions (y is zero-filled by the call; the first slice adds the bias).  The summation order
+ * over K slices is not fixed between runs (fp32 rounding level).  K % 32 == 0, N % 4 == 0. */
+int rlipv2_dense_linear_splitk_tf32(const float *x, const float *w, const float *bias, float *y, int M, int N, int K,
+                                    int splits, void *stream);
+
 /* Tuning knob of rlipv2_dense_linear_tf32* for grids that leave SMs idle (M of a few hundred rows: the ALIF,
  * RobertaLayer and decoder linears).  0: always 128x128 tiles with a 3-stage TMA ring (2 CTAs/SM); 1: grids of
  * at most one CTA per SM use a 6-stage ring; 2 (default): additionally 128x64 tiles with an 8-stage ring while the grid

@@ -146,7 +146,9 @@ __host__ __device__ constexpr uint32_t make_idesc_major() {
 // Same warp roles / pipeline as linear_tf32_kernel.  K need not be a multiple of 32 for MN-major operands (TMA
 // zero-fills rows past the end); M and N tails are handled by TMA zero fill + guarded stores.
 // ---------------------------------------------------------------------------------------------------------------
-enum { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_MASK = 2 };
+// EPI_ATOMIC_BIAS  EPI_ATOMIC for a split-K *forward* linear: the blockIdx.z == 0 slice also adds bias[n] (passed in the
+//             `mask` argument) to its partial, so that zero-initialised C ends up as A . B^T + bias
+enum { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_MASK = 2, EPI_ATOMIC_BIAS = 3 };
 
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kThreads, 2)
@@ -282,6 +284,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (grow < M && col < (size_t)N) {
                     float *dst = C + (size_t)grow * N + col;
                     if (EPI == EPI_ATOMIC) {
+                        red_add_v4(dst, v);
+                    } else if (EPI == EPI_ATOMIC_BIAS) {
+                        if (blockIdx.z == 0 && mask != nullptr) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4 *>(mask + col));
+                            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                        }
                         red_add_v4(dst, v);
                     } else {
                         if (EPI == EPI_MASK) {
@@ -588,6 +596,22 @@ int rlipv2_dense_dgrad_tf32(const float *g, const float *w, float *dx, const flo
     if (relu_out)
         return launch_gemm<128, false, true, EPI_MASK>(g, w, dx, relu_out, colsum, T, K, N, 1, s);
     return launch_gemm<128, false, true, EPI_STORE>(g, w, dx, nullptr, nullptr, T, K, N, 1, s);
+}
+
+int rlipv2_dense_linear_splitk_tf32(const float *x, const float *w, const float *bias, float *y, int M, int N, int K,
+                                    int splits, void *stream)
+{
+    // y[M,N] = x[M,K] . w[N,K]^T + bias for small-M / long-K problems (ALIF out projections, label-side in-projections,
+    // RobertaLayer FFN-down: 4-64 output tiles on 148 SMs): the K axis is split over `splits` CTAs per output tile, partial
+    // tiles reduced into the zero-filled y with red.global.add.v4.f32.  Both operands K-major, as in the plain linear.
+    if (M == 0 || N == 0) return 0;
+    if (M < 0 || N < 0 || K <= 0 || !x || !w || !y) return RLIPV2_DENSE_EINVAL;
+    if ((N % 4) || (K % kBlockK)) return RLIPV2_DENSE_ESHAPE;
+    if (!aligned16(x) || !aligned16(w) || !aligned16(y) || !aligned16(bias)) return RLIPV2_DENSE_EALIGN;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(y, 0, (size_t)M * N * sizeof(float), s);
+    if (e != cudaSuccess) return (int)e;
+    return launch_gemm<128, false, false, EPI_ATOMIC_BIAS>(x, w, y, bias, nullptr, M, N, K, splits, s);
 }
 
 int rlipv2_dense_linear_tf32_supported(int M, int N, int K)

@@ -45,6 +45,9 @@ _OWN_BWD_MIN_ROWS = int(os.environ.get("RLIPV2_OWN_BWD_MIN_ROWS", "4096"))
 # the side stream; the train step joins it after backward() (`join_param_grad_stream`).
 _LIBRARY_SMALL = os.environ.get("RLIPV2_TEXT_LIBRARY_GEMM", "0") != "0"      # measured r01s4g: 27.6 vs 27.7 ms/step - no gain, off
 _LIBRARY_SMALL_MAX_ROWS = 4096
+# split-K tcgen05 forward for small-M / long-K linears: opt-in until it has its micro-benchmark and step A/B on the B200
+# (written after round 1's GPU budget was spent)
+_SPLITK_FWD = os.environ.get("RLIPV2_SPLITK_FWD", "0") == "1"
 _WGRAD_STREAM = os.environ.get("RLIPV2_WGRAD_STREAM", "1") != "0"
 # (measured r01s4d: every size on the side stream 28.65 vs 29.5 ms/step with only the <= 4096-row problems there)
 _WGRAD_STREAM_MAX_ROWS = int(os.environ.get("RLIPV2_WGRAD_STREAM_MAX_ROWS", str(1 << 30)))
@@ -132,6 +135,10 @@ class _LinearTF32(torch.autograd.Function):
             # plain small-M / long-K linears of the (third-party, HF) text tower: cuBLAS' split-K kernels are 2-3x faster
             # than one 128-row tile per CTA here (profiles/dense_microbench_r01_v3_small_grids.jsonl); backward unchanged
             y = F.linear(x2, w, bias)
+        elif _SPLITK_FWD and act == 0 and rm is None and abi.splitk_splits(x2.shape[0], w.shape[0], w.shape[1]) > 1:
+            # small-M / long-K (ALIF out projections, label-side in-projections, RobertaLayer FFN-down): K split over the
+            # SMs one-CTA-per-tile leaves idle (rlipv2_dense_linear_splitk_tf32); backward unchanged
+            y = abi.linear_splitk_tf32(x2, w, bias, abi.splitk_splits(x2.shape[0], w.shape[0], w.shape[1]))
         else:
             y = abi.linear_tf32(x2, w, bias, act, rm)
         ctx.act = act

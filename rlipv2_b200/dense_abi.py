@@ -21,6 +21,8 @@ _lib.rlipv2_dense_wgrad_tf32.argtypes = [_p, _p, _p, _i, _i, _i, _i, _p]
 _lib.rlipv2_dense_wgrad_tf32.restype = _i
 _lib.rlipv2_dense_dgrad_tf32.argtypes = [_p, _p, _p, _p, _p, _i, _i, _i, _p]
 _lib.rlipv2_dense_dgrad_tf32.restype = _i
+_lib.rlipv2_dense_linear_splitk_tf32.argtypes = [_p, _p, _p, _p, _i, _i, _i, _i, _p]
+_lib.rlipv2_dense_linear_splitk_tf32.restype = _i
 _lib.rlipv2_dense_error_string.argtypes = [_i]
 _lib.rlipv2_dense_error_string.restype = ctypes.c_char_p
 _lib.rlipv2_dense_launch_count.restype = ctypes.c_ulonglong
@@ -33,7 +35,7 @@ if os.environ.get("RLIPV2_DENSE_SMALL_MODE"):                      # A/B switch 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 EXPORTS = ("rlipv2_dense_linear_tf32", "rlipv2_dense_linear_tf32_rowmask", "rlipv2_dense_linear_tf32_supported", "rlipv2_dense_wgrad_tf32",
            "rlipv2_dense_dgrad_tf32", "rlipv2_dense_error_string", "rlipv2_dense_launch_count",
-           "rlipv2_dense_set_small_mode", "rlipv2_dense_get_small_mode")
+           "rlipv2_dense_set_small_mode", "rlipv2_dense_get_small_mode", "rlipv2_dense_linear_splitk_tf32")
 
 
 def set_small_mode(mode):
@@ -75,6 +77,30 @@ def linear_tf32(x2d, weight, bias, act=ACT_NONE, rowmask=None):
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def splitk_splits(M, N, K):
+    """K slices per output tile for the split-K forward linear: fill one wave of 148 SMs with (tiles x slices) CTAs, at
+    least 4 k-blocks of 32 per slice; 1 = not worth splitting (use the plain kernel)"""
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    kb = K // 32
+    if K % 32 or N % 4 or tiles > 74 or K < 768:          # (short K: the zero-fill + reductions cost more than they buy)
+        return 1
+    return max(1, min(148 // tiles, kb // 4))
+
+
+def linear_splitk_tf32(x2d, weight, bias, splits):
+    """y [M,N] = x2d [M,K] @ weight[N,K]^T + bias, K split over `splits` CTAs per output tile (fp32 reductions into y)"""
+    M, K = x2d.shape
+    N = weight.shape[0]
+    y = torch.empty((M, N), dtype=torch.float32, device=x2d.device)
+    with torch.cuda.device(x2d.device):
+        rc = _lib.rlipv2_dense_linear_splitk_tf32(x2d.data_ptr(), weight.data_ptr(),
+                                                  bias.data_ptr() if bias is not None else None, y.data_ptr(), M, N, K,
+                                                  int(splits), _stream())
+    if rc != 0:
+        raise RuntimeError(f"rlipv2_dense_linear_splitk_tf32: {_lib.rlipv2_dense_error_string(rc).decode()} (code {rc})")
+    return y
 
 
 def grads_supported(T, N, K):

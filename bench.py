@@ -360,12 +360,12 @@ def run_msda_step(args, rank, world, device):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores, bounded sample
 # ------------------------------------------------------------------------------------------------
-def cpu_reference(workload, budget_s=25.0):
+def cpu_reference(workload, budget_s=25.0, steps=1, warmup=0):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     if workload == "train_step":
         from oracle import parseda_oracle
-        return parseda_oracle.time_train_step_sample(threads=threads, budget_s=budget_s)
+        return parseda_oracle.time_train_step_sample(threads=threads, budget_s=budget_s, steps=steps, warmup=warmup)
     from oracle import msda_oracle_bench
     return msda_oracle_bench.time_msda_step_sample(threads=threads)
 
@@ -390,9 +390,10 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cb = cpu_reference(args.workload)
+        cb = cpu_reference(args.workload, steps=args.steps, warmup=args.warmup)
         line = {"impl": "reference", "metric": METRIC if args.workload == "train_step" else "images/sec (MSDeformAttn calls)",
-                "value": cb["value"], "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "value": cb["value"], "unit": "images/s", "n_gpus": world, "steps": cb.get("timed_steps", args.steps),
+                "warmup": args.warmup,
                 "ms_per_step": BATCH / cb["value"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": args.workload + " (CPU oracle port, bounded sample)", "per_gpu_batch": BATCH},

@@ -426,11 +426,13 @@ def synthetic_weights(num_queries, seed=0):
     return W
 
 
-def time_train_step_sample(threads, budget_s=25.0, batch=2):
+def time_train_step_sample(threads, budget_s=25.0, batch=2, steps=1, warmup=0, total_budget_s=150.0):
     """Forward + losses + backward of the oracle on the host cores for ONE image, at the largest of
     (200x333, 400x667, 800x1333) that fits the time budget; cost is ~linear in pixels, so the
     800x1333 batch-`batch` step time is extrapolated by the pixel ratio.  Optimizer step excluded
-    (it is <2 % of a CPU step)."""
+    (it is <2 % of a CPU step).  `steps` / `warmup`: after the size has been chosen the sample is repeated `warmup`
+    times untimed and up to `steps` times timed (fewer if `total_budget_s` would be exceeded; the number actually
+    timed is reported as `timed_steps`) and the mean is reported."""
     from rlipv2_b200.text_encoder import HashTokenizer
     from rlipv2_b200.train_step import synthetic_batch, synthetic_text
     torch.set_num_threads(threads)
@@ -441,8 +443,8 @@ def time_train_step_sample(threads, budget_s=25.0, batch=2):
     third = build_third_party(W)
     text = synthetic_text(170, 85)
     full = 800 * 1333
-    result = None
-    for (h, w) in ((200, 333), (400, 667), (800, 1333)):
+
+    def one(h, w):
         images, targets = synthetic_batch(1, h, w, pin=False)
         t0 = time.perf_counter()
         out, _ = forward_step(W, third, images, torch.zeros(1, h, w, dtype=torch.bool), text, HashTokenizer(), drop=0.1)
@@ -451,10 +453,22 @@ def time_train_step_sample(threads, budget_s=25.0, batch=2):
         dt = time.perf_counter() - t0
         for k in train:
             W[k].grad = None
-        per_step = dt * (full / (h * w)) * batch
-        result = {"value": batch / per_step, "unit": "images/s", "cores": threads, "kind": "port",
-                  "sample": f"oracle/parseda_oracle.py fwd+loss+bwd, 1 image {h}x{w}, 300 queries, 256 labels: {dt:.2f} s; "
-                            f"scaled by pixel ratio x batch {batch} to the 800x1333 step"}
+        return dt
+
+    for (h, w) in ((200, 333), (400, 667), (800, 1333)):
+        dt = one(h, w)                                   # the size ladder doubles as the first warm-up pass
         if dt * 4.5 > budget_s:
             break
-    return result
+    times = [dt]
+    if steps > 1 or warmup > 0:
+        for _ in range(max(0, warmup - 1)):
+            one(h, w)
+        times, spent = [], 0.0
+        while len(times) < steps and (not times or spent + times[-1] <= total_budget_s):
+            times.append(one(h, w))
+            spent += times[-1]
+    dt = sum(times) / len(times)
+    per_step = dt * (full / (h * w)) * batch
+    return {"value": batch / per_step, "unit": "images/s", "cores": threads, "kind": "port", "timed_steps": len(times),
+            "sample": f"oracle/parseda_oracle.py fwd+loss+bwd, 1 image {h}x{w}, 300 queries, 256 labels: {dt:.2f} s "
+                      f"(mean of {len(times)}); scaled by pixel ratio x batch {batch} to the 800x1333 step"}

@@ -2,7 +2,7 @@
 CPU: equals running the text encoding of engine.py:367-391, the two model phases and PostProcessHOI by hand (the pre-encoded
 `text` tuple with an all-False label mask - NOT the training-style label strings, whose mask follows SURVEY quirk 4).  The
 reference's own loop is checked against the same model in tests/test_reference_engine_dropin.py; the CUDA-graph variant in
-tests/test_zz2_infer_gpu.py."""
+tests/test_zz3_infer_gpu.py."""
 import torch
 
 OBJ = ["person", "cup", "bench", "dining table"]

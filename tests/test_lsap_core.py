@@ -1,7 +1,7 @@
 """CPU: the arithmetic core of the on-device matcher (rlipv2_b200/csrc/lsap_core.h, the header lsap.cu compiles for
 sm_100a) built for the host with g++ (tests/lsap_host_shim.cpp) and checked against the installed scipy - the call the
 reference makes (/root/reference/models/matcher.py:193).  Index outputs must be identical, ties included, for every
-number of emulated lanes (the kernel uses 32).  The GPU test of the kernel itself is tests/test_zz4_lsap_gpu.py."""
+number of emulated lanes (the kernel uses 32).  The GPU test of the kernel itself is tests/test_zz1_lsap_gpu.py."""
 import ctypes
 import os
 import subprocess

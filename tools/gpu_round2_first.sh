@@ -5,12 +5,12 @@ TAG=${1:-r02a}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
 # 1. the verified suite first (no -x: see every failure), then the unverified files on their own
-timeout -s KILL 900 python -m pytest tests -m gpu -q --deselect tests/test_zz4_lsap_gpu.py --deselect tests/test_zz1_swin_backbone.py \
-    --deselect tests/test_zz3_overlap_gpu.py --deselect tests/test_zz2_infer_gpu.py --deselect tests/test_zz5_splitk_gpu.py \
+timeout -s KILL 900 python -m pytest tests -m gpu -q --deselect tests/test_zz1_lsap_gpu.py --deselect tests/test_zz4_swin_backbone.py \
+    --deselect tests/test_zz2_overlap_gpu.py --deselect tests/test_zz3_infer_gpu.py --deselect tests/test_zz5_splitk_gpu.py \
     > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/${TAG}_pytest_gpu.log
-timeout -s KILL 300 python -m pytest tests/test_zz4_lsap_gpu.py -m gpu -q > gpurun_out/${TAG}_pytest_lsap.log 2>&1; echo "pytest exit $?" >> gpurun_out/${TAG}_pytest_lsap.log
-timeout -s KILL 300 python -m pytest tests/test_zz3_overlap_gpu.py tests/test_zz2_infer_gpu.py tests/test_zz5_splitk_gpu.py -m gpu -q > gpurun_out/${TAG}_pytest_overlap_infer.log 2>&1; echo "pytest exit $?" >> gpurun_out/${TAG}_pytest_overlap_infer.log
-timeout -s KILL 600 python -m pytest tests/test_zz1_swin_backbone.py -m gpu -q > gpurun_out/${TAG}_pytest_swin.log 2>&1; echo "pytest exit $?" >> gpurun_out/${TAG}_pytest_swin.log
+timeout -s KILL 300 python -m pytest tests/test_zz1_lsap_gpu.py -m gpu -q > gpurun_out/${TAG}_pytest_lsap.log 2>&1; echo "pytest exit $?" >> gpurun_out/${TAG}_pytest_lsap.log
+timeout -s KILL 300 python -m pytest tests/test_zz2_overlap_gpu.py tests/test_zz3_infer_gpu.py tests/test_zz5_splitk_gpu.py -m gpu -q > gpurun_out/${TAG}_pytest_overlap_infer.log 2>&1; echo "pytest exit $?" >> gpurun_out/${TAG}_pytest_overlap_infer.log
+timeout -s KILL 600 python -m pytest tests/test_zz4_swin_backbone.py -m gpu -q > gpurun_out/${TAG}_pytest_swin.log 2>&1; echo "pytest exit $?" >> gpurun_out/${TAG}_pytest_swin.log
 tail -3 gpurun_out/${TAG}_pytest_gpu.log gpurun_out/${TAG}_pytest_lsap.log gpurun_out/${TAG}_pytest_overlap_infer.log gpurun_out/${TAG}_pytest_swin.log
 # 2. A/B on one box: base, assignment on the device, token-major GroupNorm input projections, both
 B="python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-roofline"

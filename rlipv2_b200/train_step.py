@@ -217,6 +217,7 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         if self.device_lsap:
             from . import lsap_abi
             lsap_abi.solve(C, self.lsap_plan, self.s_I, self.s_J)
+            self.last_cost = C                  # (static graph memory: readable after a replay, e.g. by the tests)
         else:
             self.h_cost.copy_(C, non_blocking=True)
         self._stamp(1)

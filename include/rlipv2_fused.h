@@ -73,6 +73,15 @@ int rlipv2_adamw_scaled_f32(float *param, const float *grad, float *exp_avg, flo
                             double lr, double beta1, double beta2, double eps, double weight_decay,
                             const float *step, const float *grad_scale, void *stream);
 
+/* The same step with the learning rate read from device memory (`lr_dev`, or NULL = the host value `lr`): inside a captured
+ * CUDA graph a host scalar is frozen at capture time, so the reference's `StepLR(optimizer, lr_drop)` (main.py:554, 724)
+ * would have no effect; a device scalar follows `GraphedParSeDATrainStep.set_lr()`.  `skip_flag` (or NULL): a device word
+ * that makes the update a no-op when non-zero - the error word of rlipv2_wait_host_flag, so that a replay whose host
+ * assignment timed out cannot train on the previous step's indices. */
+int rlipv2_adamw_dev_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, double lr,
+                         const float *lr_dev, double beta1, double beta2, double eps, double weight_decay,
+                         const float *step, const float *grad_scale, const unsigned *skip_flag, void *stream);
+
 /* Gather scattered fp32 arrays into one flat buffer: for chunk c, copy table[3c+2] elements from the device
  * address table[3c] to dst + table[3c+1] (`table` is a device array of n_chunks x 3 int64; one CTA per chunk,
  * keep chunks <= 64K elements).  Used once per step to collect the gradient tensors autograd produced

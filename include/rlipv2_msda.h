@@ -44,6 +44,8 @@ extern "C" {
 #define RLIPV2_MSDA_EINVAL   (-1) /* negative / zero dimension where not allowed, null pointer */
 #define RLIPV2_MSDA_ETOOBIG  (-2) /* an index would overflow the 64-bit-safe limits we support  */
 #define RLIPV2_MSDA_ESHAPE   (-3) /* fused-prologue entry points: shape outside fp32, D=32, L=4, P=4 */
+#define RLIPV2_MSDA_EALIGN   (-4) /* fused-prologue entry points: a pointer is not 16-byte aligned (the plain entry
+                                     points fall back to the generic kernel instead, like the reference's scalar one) */
 
 /* ms_deform_attn_cuda_forward (ms_deform_attn_cuda.cu:20-80), scalar_t = float.
  * Writes every element of `out` (no pre-zeroing needed). */

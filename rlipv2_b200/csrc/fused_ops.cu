@@ -176,8 +176,14 @@ relu_bwd_colsum_kernel(const float *__restrict__ g, const float *__restrict__ y,
 __global__ void __launch_bounds__(256)
 adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
              long long n4, long long n, float lr, float b1, float b2, float omb1, float omb2, float eps, float wd,
-             const float *__restrict__ step, const float *__restrict__ grad_scale)
+             const float *__restrict__ step, const float *__restrict__ grad_scale, const float *__restrict__ lr_dev,
+             const unsigned *__restrict__ skip_flag)
 {
+    // skip_flag: the error word of the backward graph's host-flag wait - a replay whose assignment never arrived must
+    // not update the parameters from the previous step's indices (the update becomes a no-op; check() raises later)
+    if (skip_flag && *skip_flag != 0u) return;
+    // lr_dev: the learning rate as a device scalar, so that a captured graph follows the scheduler (main.py:554 StepLR)
+    if (lr_dev) lr = *lr_dev;
     // omb1 / omb2 = 1 - beta computed in double on the host (1.f - 0.999f is 1.3e-5 off)
     const float t = *step;
     // grad_scale: the clip_grad_norm_ coefficient (and 1 / world for the rank mean) applied to the gradient as it is
@@ -725,6 +731,14 @@ int rlipv2_adamw_scaled_f32(float *param, const float *grad, float *exp_avg, flo
                             double beta1, double beta2, double eps, double weight_decay, const float *step,
                             const float *grad_scale, void *stream)
 {
+    return rlipv2_adamw_dev_f32(param, grad, exp_avg, exp_avg_sq, n, lr, nullptr, beta1, beta2, eps, weight_decay, step,
+                                grad_scale, nullptr, stream);
+}
+
+int rlipv2_adamw_dev_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, double lr,
+                         const float *lr_dev, double beta1, double beta2, double eps, double weight_decay,
+                         const float *step, const float *grad_scale, const unsigned *skip_flag, void *stream)
+{
     if (n == 0) return 0;
     if (!param || !grad || !exp_avg || !exp_avg_sq || !step || n < 0) return RLIPV2_FUSED_EINVAL;
     if (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) return RLIPV2_FUSED_EINVAL;
@@ -735,7 +749,7 @@ int rlipv2_adamw_scaled_f32(float *param, const float *grad, float *exp_avg, flo
     adamw_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n4, n, (float)lr,
                                                                 (float)beta1, (float)beta2, (float)(1.0 - beta1),
                                                                 (float)(1.0 - beta2), (float)eps, (float)weight_decay, step,
-                                                                grad_scale);
+                                                                grad_scale, lr_dev, skip_flag);
     return done();
 }
 

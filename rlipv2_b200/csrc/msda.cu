@@ -587,6 +587,15 @@ inline bool fast_ok(int batch, int spatial_size, int num_heads, int channels, in
     return velems < (1ll << 32) && nq < (1ll << 31) - kQueriesPerCta;
 }
 
+// the fast kernels use 128-bit ld.global / red.global.add.v4 on value, sampling_loc, out and grad_value and 64-bit loads
+// on attn / ref: a contiguous tensor whose storage offset is not 16-byte aligned (a slice / view - the reference's
+// scalar kernel accepts it) must take the generic kernel instead of faulting with a misaligned address
+inline bool aligned16(const void *a, const void *b = nullptr, const void *c = nullptr, const void *d = nullptr,
+                      const void *e = nullptr, const void *f = nullptr, const void *g = nullptr) {
+    return ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)c) | ((uintptr_t)d) | ((uintptr_t)e) | ((uintptr_t)f) |
+             ((uintptr_t)g)) & 15) == 0;
+}
+
 // CTAs along x walk 32 consecutive queries; heads are sliced over grid.y only when the query
 // dimension alone leaves SMs idle (decoder-shaped calls: a few hundred queries).
 inline dim3 fast_grid(int NQ, int num_heads) {
@@ -685,6 +694,7 @@ int proj_forward_impl(const float *value, const int64_t *shapes, const int64_t *
     const int NQ = batch * num_query;
     if (NQ == 0) return 0;
     if (!value || !shapes || !lsi || !ref || !proj || !out) return RLIPV2_MSDA_EINVAL;
+    if (!aligned16(value, ref, proj, out)) return RLIPV2_MSDA_EALIGN;
     const dim3 grid = fast_grid(NQ, num_heads);
     if (ref_dim == 4) {
         if (NQ >= 8192)
@@ -722,6 +732,7 @@ int proj_backward_impl(const float *value, const int64_t *shapes, const int64_t 
     const int NQ = batch * num_query;
     if (NQ == 0) return 0;
     if (!value || !shapes || !lsi || !ref || !proj || !grad_out || !grad_proj) return RLIPV2_MSDA_EINVAL;
+    if (!aligned16(value, ref, proj, grad_out, grad_value, grad_proj)) return RLIPV2_MSDA_EALIGN;
     const dim3 grid = fast_grid(NQ, num_heads);
     if (ref_dim == 4)
         msda_bwd_d32_l4p4<2, 2><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, grad_out, NQ, num_query,
@@ -789,7 +800,8 @@ int rlipv2_msda_forward_f32(const float *value, const int64_t *spatial_shapes,
                                batch, spatial_size, num_heads, channels, num_levels, num_query,
                                num_point, out, (cudaStream_t)stream,
                                fast_ok(batch, spatial_size, num_heads, channels, num_levels,
-                                       num_query, num_point));
+                                       num_query, num_point) &&
+                                   aligned16(value, sampling_loc, attn_weight, out));
 }
 
 int rlipv2_msda_forward_f64(const double *value, const int64_t *spatial_shapes,
@@ -815,7 +827,9 @@ int rlipv2_msda_backward_f32(const float *value, const int64_t *spatial_shapes,
                                 num_query, num_point, grad_value, grad_sampling_loc,
                                 grad_attn_weight, (cudaStream_t)stream,
                                 fast_ok(batch, spatial_size, num_heads, channels, num_levels,
-                                        num_query, num_point));
+                                        num_query, num_point) &&
+                                    aligned16(value, sampling_loc, attn_weight, grad_out, grad_value,
+                                              grad_sampling_loc, grad_attn_weight));
 }
 
 int rlipv2_msda_backward_f64(const double *value, const int64_t *spatial_shapes,
@@ -837,6 +851,7 @@ const char *rlipv2_msda_error_string(int code)
     if (code == RLIPV2_MSDA_EINVAL) return "rlipv2_msda: invalid argument (dimension or null pointer)";
     if (code == RLIPV2_MSDA_ETOOBIG) return "rlipv2_msda: problem too large";
     if (code == RLIPV2_MSDA_ESHAPE) return "rlipv2_msda: fused-prologue entry points need fp32, D=32, L=4, P=4";
+    if (code == RLIPV2_MSDA_EALIGN) return "rlipv2_msda: fused-prologue entry points need 16-byte aligned pointers";
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
     return "rlipv2_msda: unknown error";
 }

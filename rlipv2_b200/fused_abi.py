@@ -18,6 +18,8 @@ _d = ctypes.c_double
 _lib.rlipv2_adamw_f32.argtypes = [_p, _p, _p, _p, _ll, _d, _d, _d, _d, _d, _p, _p]
 _lib.rlipv2_adamw_scaled_f32.argtypes = [_p, _p, _p, _p, _ll, _d, _d, _d, _d, _d, _p, _p, _p]
 _lib.rlipv2_adamw_scaled_f32.restype = _i
+_lib.rlipv2_adamw_dev_f32.argtypes = [_p, _p, _p, _p, _ll, _d, _p, _d, _d, _d, _d, _p, _p, _p, _p]
+_lib.rlipv2_adamw_dev_f32.restype = _i
 _lib.rlipv2_gather_chunks_f32.argtypes = [_p, _i, _p, _p]
 _lib.rlipv2_rowmask_bwd_colsum_f32.argtypes = [_p, _p, _p, _p, _i, _i, _p]
 _ull, _u64p = ctypes.c_ulonglong, ctypes.c_void_p
@@ -51,7 +53,7 @@ _lib.rlipv2_fused_error_string.restype = ctypes.c_char_p
 _lib.rlipv2_fused_launch_count.restype = ctypes.c_ulonglong
 
 EXPORTS = ("rlipv2_add_layernorm_fwd_f32", "rlipv2_layernorm_bwd_f32", "rlipv2_relu_bwd_colsum_f32",
-           "rlipv2_adamw_f32", "rlipv2_adamw_scaled_f32", "rlipv2_gather_chunks_f32", "rlipv2_rowmask_bwd_colsum_f32", "rlipv2_wait_host_flag",
+           "rlipv2_adamw_f32", "rlipv2_adamw_scaled_f32", "rlipv2_adamw_dev_f32", "rlipv2_gather_chunks_f32", "rlipv2_rowmask_bwd_colsum_f32", "rlipv2_wait_host_flag",
            "rlipv2_box_refine_f32", "rlipv2_sine_embed_f32", "rlipv2_box_pair_loss_f32", "rlipv2_groupnorm_tokens_fwd_f32", "rlipv2_groupnorm_tokens_bwd_f32",
            "rlipv2_short_attention_fwd_f32", "rlipv2_short_attention_bwd_f32", "rlipv2_stamp_globaltimer", "rlipv2_layernorm_bwd_acc_f32",
            "rlipv2_relu_bwd_colsum_acc_f32", "rlipv2_rowmask_bwd_colsum_acc_f32", "rlipv2_fused_error_string", "rlipv2_fused_launch_count")
@@ -129,14 +131,19 @@ def relu_bwd_colsum(g2, y2=None, acc=None):
     return gm, (None if into else colsum)
 
 
-def adamw(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=None):
+def adamw(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=None, lr_dev=None,
+          skip_flag=None):
     """In-place AdamW over flat contiguous fp32 buffers; `step` = 0-dim device float (1-based count); `grad_scale` =
-    optional 0-dim / 1-element device float the gradient is multiplied by as it is read (clip coefficient, 1 / world)."""
+    optional 0-dim / 1-element device float the gradient is multiplied by as it is read (clip coefficient, 1 / world);
+    `lr_dev` = optional 1-element device float that overrides `lr` (a captured graph then follows the scheduler);
+    `skip_flag` = optional 1-element device int32: non-zero makes the update a no-op."""
     with torch.cuda.device(param.device):
-        rc = _lib.rlipv2_adamw_scaled_f32(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
-                                          param.numel(), lr, beta1, beta2, eps, weight_decay, step.data_ptr(),
-                                          grad_scale.data_ptr() if grad_scale is not None else None, _stream())
-    _check(rc, "rlipv2_adamw_scaled_f32")
+        rc = _lib.rlipv2_adamw_dev_f32(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                       param.numel(), lr, lr_dev.data_ptr() if lr_dev is not None else None, beta1, beta2,
+                                       eps, weight_decay, step.data_ptr(),
+                                       grad_scale.data_ptr() if grad_scale is not None else None,
+                                       skip_flag.data_ptr() if skip_flag is not None else None, _stream())
+    _check(rc, "rlipv2_adamw_dev_f32")
 
 
 GATHER_CHUNK = 32768

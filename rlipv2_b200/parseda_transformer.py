@@ -265,8 +265,14 @@ class RLIPv2_DeformableTransformerEncoder(nn.Module):
                     # deformable layers instead of in front of them
                     cur = torch.cuda.current_stream(src.device)
                     side.wait_stream(cur)
+                    lang_in = lang["hidden"]
                     with torch.cuda.stream(side):
-                        lang["hidden"] = self.roberta_layers[k](lang["hidden"], attention_mask=lang["masks"])
+                        lang["hidden"] = self.roberta_layers[k](lang_in, attention_mask=lang["masks"])
+                    # the fused label stream was allocated on `cur` and is read on `side`: without autograd holding it
+                    # (torch.no_grad inference) it is freed right here and `cur`'s next allocation would reuse the block
+                    # while the RobertaLayer still reads it (round 1's graphed-inference test failure)
+                    lang_in.record_stream(side)
+                    lang["masks"].record_stream(side)
                     pending = True
                 else:
                     lang["hidden"] = self.roberta_layers[k](lang["hidden"], attention_mask=lang["masks"])

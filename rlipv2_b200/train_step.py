@@ -312,10 +312,12 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
     def _adamw_step(self, grad_scale=None):
         from . import fused_abi
         self.step_t.add_(1.0)
-        for start, end, lr in self.group_ranges:
+        skip = self.d_err if (self.flag_wait and not self.device_lsap) else None
+        for gi, (start, end, lr) in enumerate(self.group_ranges):
+            # lr comes from the device vector (set_lr): a host scalar would be frozen into the captured graph
             fused_abi.adamw(self.flat_param[start:end], self.flat_grad[start:end], self.exp_avg[start:end],
                             self.exp_avg_sq[start:end], lr, 0.9, 0.999, 1e-8, self.weight_decay, self.step_t,
-                            grad_scale=grad_scale)
+                            grad_scale=grad_scale, lr_dev=self.lr_dev[gi:gi + 1], skip_flag=skip)
 
     def _solve_assignment(self):
         """host: LSAP on the pinned cost tensor [layers, bs, nq, T] -> the static device index buffers
@@ -414,6 +416,10 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         self.step_t = torch.zeros((), device=dev)
         self.param_offsets = self.flat.param_offsets
         self.group_ranges = self.flat.group_ranges
+        # per-group learning rates as device scalars (read by the AdamW kernel): `set_lr` / an lr scheduler keeps working
+        # after the capture (a host lr is frozen into the graph, StepLR of main.py:554 would never drop)
+        self.lr_dev = torch.tensor([g[2] for g in self.group_ranges], dtype=torch.float32, device=dev)
+        self.group_lrs = [float(g[2]) for g in self.group_ranges]
         self.params = self.flat.params
         if not self.gather_grads and os.environ.get("RLIPV2_FUSE_GRAD_ACC", "1") != "0":
             # dense.py's backward functions add weight / bias / LayerNorm gradients straight into these views
@@ -505,8 +511,77 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
             self.np_flag[0] = self.flag_seq
         return self.s_loss
 
+    # ---- optimizer surface the reference's main.py touches (lr scheduler, checkpoint save / resume) ----------------
+    def set_lr(self, lrs):
+        """lrs: one value (scales nothing, sets every group) or one per group in the order of main.py:525-537
+        (transformer + heads | backbone | text encoder).  Takes effect at the next replay."""
+        lrs = [float(lrs)] * len(self.group_lrs) if not isinstance(lrs, (list, tuple)) else [float(x) for x in lrs]
+        assert len(lrs) == len(self.group_lrs)
+        self.group_lrs = lrs
+        self.lr_dev.copy_(torch.tensor(lrs, dtype=torch.float32), non_blocking=False)
+
+    def step_lr(self, epoch, lr_drop, gamma=0.1, base_lrs=None):
+        """torch.optim.lr_scheduler.StepLR(optimizer, lr_drop) of main.py:554, called once per epoch (main.py:724)"""
+        base = base_lrs if base_lrs is not None else getattr(self, "_base_lrs", None)
+        if base is None:
+            base = self._base_lrs = list(self.group_lrs)
+        self.set_lr([b * gamma ** (epoch // lr_drop) for b in base])
+
+    def optimizer_state_dict(self):
+        """what `optimizer.state_dict()` carries in the reference's checkpoints (main.py:609-611, 746), for the flat AdamW"""
+        return {"exp_avg": self.exp_avg.detach().clone(), "exp_avg_sq": self.exp_avg_sq.detach().clone(),
+                "step": float(self.step_t.item()), "lrs": list(self.group_lrs),
+                "param_names": [n for n, p in self.module.named_parameters() if any(p is q for q in self.params)]}
+
+    def load_optimizer_state_dict(self, sd):
+        assert sd["exp_avg"].numel() == self.exp_avg.numel(), "optimizer state of a different parameter set"
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.step_t.fill_(float(sd["step"]))
+        self.set_lr(sd["lrs"])
+
+    def update_text(self, text):
+        """New label strings for the next replay (the reference builds the label set per batch: engine.py:92-98
+        `merge_batch_data` / negative sampling, and tokenises it every step, dab_deformable/deformable_transformer.py:497).
+        The captured graph holds the token ids in static buffers: same tuple sizes and a token width of at most the captured
+        one are copied in (shorter rows padded with the pad id, attention 0 - the tower masks them); anything else needs a
+        re-capture and raises."""
+        tr = self.module.transformer
+        if isinstance(text, dict):
+            ids, am, sums = text["input_ids"], text["attention_mask"], text["sums"]
+        else:
+            sums, flat = [], []
+            for obj_names, pred_names in text:
+                sums.append((len(obj_names), len(pred_names)))
+                flat += list(obj_names) + list(pred_names)
+            tok = tr.tokenizer.batch_encode_plus(flat, padding="longest", return_tensors="pt")
+            ids, am = tok["input_ids"], tok["attention_mask"]
+        s_ids, s_am = self.s_tok["input_ids"], self.s_tok["attention_mask"]
+        if [tuple(x) for x in sums] != [tuple(x) for x in self.s_tok["sums"]]:
+            raise ValueError(f"label-set sizes {sums} differ from the captured {self.s_tok['sums']}: re-capture")
+        if ids.shape[0] != s_ids.shape[0] or ids.shape[1] > s_ids.shape[1]:
+            raise ValueError(f"token matrix {tuple(ids.shape)} does not fit the captured {tuple(s_ids.shape)}: re-capture")
+        if getattr(self, "h_ids", None) is None:
+            pad = getattr(getattr(tr, "tokenizer", None), "pad_token_id", None)
+            self._pad_id = 1 if pad is None else int(pad)
+            self.h_ids = torch.empty(s_ids.shape, dtype=s_ids.dtype).pin_memory()
+            self.h_am = torch.empty(s_am.shape, dtype=s_am.dtype).pin_memory()
+        if getattr(self, "_tok_copied", None) is not None:
+            self._tok_copied.synchronize()           # the previous step's H2D of these pinned buffers has been consumed
+        self.h_ids.fill_(self._pad_id)
+        self.h_am.zero_()
+        self.h_ids[:, :ids.shape[1]].copy_(ids)
+        self.h_am[:, :am.shape[1]].copy_(am)
+        s_ids.copy_(self.h_ids, non_blocking=True)
+        s_am.copy_(self.h_am, non_blocking=True)
+        self._tok_copied = torch.cuda.Event()
+        self._tok_copied.record()
+
     def step(self, images_host, targets_host, text=None):
-        """H2D of a new batch (same shapes as at capture) + one replayed step."""
+        """H2D of a new batch (same shapes as at capture) + one replayed step.  `text`: the batch's label strings (or a
+        `tokenize()` dict); None keeps the label set of the previous step."""
+        if text is not None:
+            self.update_text(text)
         self.s_samples.tensors.copy_(images_host, non_blocking=True)
         for st, ht in zip(self.s_targets, targets_host):
             for k in st:

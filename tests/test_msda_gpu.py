@@ -177,3 +177,51 @@ def test_against_reference_cuda_kernel():
         torch.testing.assert_close(ga, rga, rtol=1e-4, atol=1e-4)
         torch.testing.assert_close(gl, rgl, rtol=1e-3, atol=1e-2)
         torch.testing.assert_close(gv, rgv, rtol=1e-3, atol=1e-3)
+
+
+def test_full_size_against_reference_cuda_kernel():
+    """the reference's own CUDA op at the BASELINE size - the encoder call of a 800x1333 image,
+    N = 2, S = Lq = 22223 (models/ops/src/cuda/ms_deform_im2col_cuda.cuh:238-403) - not only at Lq = 300."""
+    from oracle import build_ref
+    ref = build_ref.load()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    from rlipv2_b200 import synth
+    value, sh, lsi, loc, attn, gout = synth.encoder_inputs(2, synth.LEVELS_800x1333, seed=7)
+    out = _msda().ms_deform_attn_forward(value, sh, lsi, loc, attn, 64)
+    rout = ref.ms_deform_attn_forward(value, sh, lsi, loc, attn, 64)
+    torch.testing.assert_close(out, rout, rtol=1e-4, atol=2e-5)
+    gv, gl, ga = _msda().ms_deform_attn_backward(value, sh, lsi, loc, attn, gout, 64)
+    rgv, rgl, rga = ref.ms_deform_attn_backward(value, sh, lsi, loc, attn, gout, 64)
+    torch.testing.assert_close(ga, rga, rtol=1e-4, atol=1e-4)
+    # grad_value / grad_loc are sums of up to hundreds of fp32 atomics in a different order on each side
+    assert float((gv - rgv).abs().max()) <= 1e-3 * float(rgv.abs().max())
+    assert float((gl - rgl).abs().max()) <= 1e-3 * float(rgl.abs().max())
+
+
+def test_misaligned_views_take_the_generic_kernel():
+    """a contiguous tensor whose storage offset is not 16-byte aligned (the reference's scalar kernel accepts
+    it: only is_contiguous() is checked, ms_deform_attn_cuda.cu:28-33) must not reach the 128-bit fast path."""
+    from rlipv2_b200 import synth
+    shapes = [(12, 15), (6, 8), (3, 4), (2, 2)]
+    value, sh, lsi, loc, attn, gout = synth.random_inputs(2, 37, shapes, seed=5)
+
+    def shifted(t):
+        buf = torch.empty(t.numel() + 1, device=t.device, dtype=t.dtype)
+        v = buf[1:].view(t.shape)
+        v.copy_(t)
+        assert v.is_contiguous() and v.data_ptr() % 16 != 0
+        return v
+
+    out = _msda().ms_deform_attn_forward(value, sh, lsi, loc, attn, 64)
+    gv, gl, ga = _msda().ms_deform_attn_backward(value, sh, lsi, loc, attn, gout, 64)
+    for which in range(4):
+        args = [value, loc, attn, gout]
+        args[which] = shifted(args[which])
+        v, l, a, g = args
+        o2 = _msda().ms_deform_attn_forward(v, sh, lsi, l, a, 64)
+        torch.testing.assert_close(o2, out, rtol=1e-5, atol=1e-7)
+        gv2, gl2, ga2 = _msda().ms_deform_attn_backward(v, sh, lsi, l, a, g, 64)
+        torch.testing.assert_close(gv2, gv, rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(gl2, gl, rtol=1e-3, atol=1e-5)
+        torch.testing.assert_close(ga2, ga, rtol=1e-4, atol=1e-6)

@@ -45,3 +45,51 @@ def test_graphed_step_matches_eager_step():
         assert graphed.flag_wait and int(graphed.d_seq.item()) == 4 == graphed.flag_seq   # priming replay + 3
     finally:
         dense.set_matmul_precision("fp32")
+
+
+def test_graphed_step_follows_lr_text_and_checkpoint():
+    """ADVICE r1: (a) the learning rate is a device scalar the captured AdamW reads (`set_lr`, StepLR of main.py:554);
+    (b) `step(text=...)` puts the batch's label strings into the static token buffers (engine.py:92-98 builds a label set per
+    batch) and refuses a label set of another shape; (c) the flat AdamW state round-trips (main.py:609-611, 746)."""
+    from rlipv2_b200 import dense, train_step
+    try:
+        ts, imgs, tg, text = _make(train_step.GraphedParSeDATrainStep)
+        ts.capture(imgs, tg, text, warmup=2)
+        names = ("transformer.level_embed", "transformer.encoder.layers.3.linear1.weight")
+        params = dict(ts.module.named_parameters())
+        # (a) lr = 0: a replay leaves the parameters where they are (weight decay is lr * wd, also 0)
+        before = {k: params[k].detach().clone() for k in names}
+        ts.set_lr(0.0)
+        ts.replay()
+        torch.cuda.synchronize()
+        for k in names:
+            assert torch.equal(params[k].detach(), before[k]), k
+        ts.set_lr([1.41e-4, 1.41e-5, 1.41e-5])
+        ts.replay()
+        torch.cuda.synchronize()
+        assert not torch.equal(params[names[1]].detach(), before[names[1]])
+        ts.step_lr(epoch=3, lr_drop=2)                       # StepLR: one drop by 0.1 after 2 epochs
+        assert abs(ts.group_lrs[0] - 1.41e-5) < 1e-12 and abs(float(ts.lr_dev[0]) - 1.41e-5) < 1e-10
+        # (b) other label strings of the same shape: token buffers change, the loss moves; another shape raises
+        ids0 = ts.s_tok["input_ids"].clone()
+        l_same = float(ts.step(imgs, tg, text))
+        objs = [f"thing number {i}" for i in range(6)] + ["no objects"]
+        verbs = [f"touching {i} at" for i in range(4)]
+        l_new = float(ts.step(imgs, tg, [(objs, verbs)]))
+        assert not torch.equal(ts.s_tok["input_ids"], ids0)
+        assert l_new == l_new and l_new != l_same
+        with pytest.raises(ValueError, match="re-capture"):
+            ts.step(imgs, tg, [(objs[:-1], verbs)])
+        with pytest.raises(ValueError, match="re-capture"):
+            ts.step(imgs, tg, [(["a very long label with many many words in it"] + objs[1:], verbs)])
+        ts.check()
+        # (c) optimizer state round trip
+        sd = ts.optimizer_state_dict()
+        ts.replay()
+        torch.cuda.synchronize()
+        assert not torch.equal(ts.exp_avg, sd["exp_avg"])
+        ts.load_optimizer_state_dict(sd)
+        assert torch.equal(ts.exp_avg, sd["exp_avg"]) and float(ts.step_t) == sd["step"]
+        assert len(sd["param_names"]) == len(ts.params)
+    finally:
+        dense.set_matmul_precision("fp32")

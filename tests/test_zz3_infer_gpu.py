@@ -1,14 +1,25 @@
-"""GPU: the CUDA-graph inference step equals the eager one (rlipv2_b200/infer_step.py).  Runs last: written after round
-1's GPU budget was spent."""
+"""GPU: the CUDA-graph inference step equals the eager one (rlipv2_b200/infer_step.py).
+
+Round 1's version compared arg-max labels only and failed on the driver's box; the round-2 diagnosis
+(tools/debug_infer_graph.py, profiles/infer_graph_r02.md) showed a real race, not a near-tie: under torch.no_grad the fused
+label stream handed to the side-stream RobertaLayer was freed while that stream still read it.  The test now compares the
+raw model outputs (logits, boxes) of the replay with the eager forward, checks that two replays are bit-identical
+(no race left), and compares labels wherever the eager top-2 margin exceeds the output tolerance."""
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
 
 
+def _raw(infer, samples):
+    with torch.no_grad():
+        return {k: v.clone() for k, v in infer._forward(samples).items() if torch.is_tensor(v)}
+
+
 def test_graphed_inference_equals_eager():
     from rlipv2_b200 import dense
     from rlipv2_b200.infer_step import ParSeDAInference
+    from rlipv2_b200.nested import nested_tensor_from_tensor_list
     from tests.test_infer_step import OBJ, VERB, _build
     try:
         model, post = _build("cuda")
@@ -16,14 +27,31 @@ def test_graphed_inference_equals_eager():
         imgs = [torch.randn(3, 160, 192, generator=g).cuda(), torch.randn(3, 160, 192, generator=g).cuda()]
         sizes = torch.tensor([[480, 576], [320, 384]], device="cuda")
         infer = ParSeDAInference(model, post, OBJ, VERB, batch_size=2)
+        samples = nested_tensor_from_tensor_list(imgs)
+        eager_raw = _raw(infer, samples)
         eager = infer(imgs, sizes)
         infer.capture(160, 192)
         graphed = infer(imgs, sizes)
         assert infer.graph is not None
-        for a, b in zip(graphed, eager):
-            assert torch.equal(a["labels"], b["labels"])
-            torch.testing.assert_close(a["boxes"], b["boxes"], rtol=1e-4, atol=1e-2)
-            torch.testing.assert_close(a["verb_scores"], b["verb_scores"], rtol=1e-4, atol=1e-6)
+        torch.cuda.synchronize()
+        first = {k: v.clone() for k, v in infer.s_out.items()}
+        graphed2 = infer(imgs, sizes)
+        torch.cuda.synchronize()
+        for k, v in infer.s_out.items():                                   # same inputs, same graph: bit-identical
+            assert torch.equal(v, first[k]), f"{k}: two replays differ by {float((v - first[k]).abs().max())}"
+        tol = 2e-4                                                         # cuBLAS may pick other kernels under capture
+        for k in ("pred_sub_logits", "pred_obj_logits", "pred_verb_logits", "pred_sub_boxes", "pred_obj_boxes"):
+            torch.testing.assert_close(first[k], eager_raw[k], rtol=tol, atol=tol, msg=lambda m, k=k: f"{k}: {m}")
+        top2 = eager_raw["pred_obj_logits"][..., :-1].topk(2).values
+        decided = (top2[..., 0] - top2[..., 1] > 10 * tol).cpu()
+        assert decided.any()
+        for b, (a, e) in enumerate(zip(graphed, eager)):
+            nq = decided.shape[1]
+            assert torch.equal(a["labels"][nq:][decided[b]], e["labels"][nq:][decided[b]])     # [subjects ; objects]
+            assert torch.equal(a["labels"][:nq], e["labels"][:nq])
+            torch.testing.assert_close(a["boxes"], e["boxes"], rtol=1e-4, atol=0.5)          # pixels of a 480x576 image
+            torch.testing.assert_close(a["verb_scores"], e["verb_scores"], rtol=1e-3, atol=2e-4)
+        assert all(torch.equal(a["verb_scores"], b["verb_scores"]) for a, b in zip(graphed, graphed2))
         other = infer([torch.randn(3, 160, 192, device="cuda") for _ in range(2)], sizes)      # new inputs, same graph
         assert not torch.equal(other[0]["verb_scores"], graphed[0]["verb_scores"])
     finally:

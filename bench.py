@@ -251,7 +251,7 @@ def alif_tensor_roofline(device):
 # workload: full train step
 # ------------------------------------------------------------------------------------------------
 def run_train_step(args, rank, world, device):
-    from rlipv2_b200 import dense, dense_abi, fused_abi, lsap_abi, msda_abi, train_step
+    from rlipv2_b200 import attn_abi, dense, dense_abi, fused_abi, lsap_abi, msda_abi, train_step
     text = train_step.synthetic_text(170, 85)
     batch = args.per_gpu_batch or BATCH
     images_h, targets_h = train_step.synthetic_batch(batch, 800, 1333, seed=rank)
@@ -265,7 +265,7 @@ def run_train_step(args, rank, world, device):
                                          backbone=args.backbone, drop_path_rate=0.5 if "swin" in args.backbone else 0.2,
                                          **extra)
     own = lambda: (msda_abi.launch_count() + dense_abi.launch_count() + fused_abi.launch_count()
-                   + lsap_abi.launch_count())
+                   + lsap_abi.launch_count() + attn_abi.launch_count())
     loss = None
     if args.graphs:
         ts = train_step.GraphedParSeDATrainStep(args=model_args, device=str(device), precision=args.precision, seed=0)

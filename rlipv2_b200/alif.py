@@ -26,7 +26,6 @@ Reference quirks reproduced on purpose:
     `--dropout` (fuse_helper.py:438-439, 1011).
 """
 import torch
-import torch.nn.functional as F
 from torch import nn
 
 from . import dense
@@ -82,30 +81,21 @@ class RLIPv2_BiMultiHeadAttention(nn.Module):
             lin.bias.data.fill_(0)
 
     def forward(self, v, l, v_pos=None, attention_mask_l=None, attention_mask_v=None):
-        bsz, tgt_len, _ = v.shape
-        src_len = l.shape[1]
-        H, Dh = self.num_heads, self.head_dim
         # the reference's bool-mask handling is a no-op (module docstring); masks are accepted and ignored
         for m in (attention_mask_l, attention_mask_v):
             if m is not None and m.dtype != torch.bool:
                 raise NotImplementedError("non-bool ALIF masks are not on the reference's call path")
         q_in = v if v_pos is None else v + v_pos
-        q = dense.linear(q_in, self.v_proj.weight, self.v_proj.bias) * self.scale
+        # (the reference scales q before the product, `v_proj(...) * scale`; scale = 256^-0.5 is a power of two, so
+        # folding it into the score is bit-identical)
+        q = dense.linear(q_in, self.v_proj.weight, self.v_proj.bias)
         k = dense.linear(l, self.l_proj.weight, self.l_proj.bias)
         vv = dense.linear(v, self.values_v_proj.weight, self.values_v_proj.bias)
         vl = dense.linear(l, self.values_l_proj.weight, self.values_l_proj.bias)
-        q = q.view(bsz, tgt_len, H, Dh).transpose(1, 2)       # [b, h, Tv, Dh]
-        k = k.view(bsz, src_len, H, Dh).transpose(1, 2)       # [b, h, Tl, Dh]
-        vv = vv.view(bsz, tgt_len, H, Dh).transpose(1, 2)
-        vl = vl.view(bsz, src_len, H, Dh).transpose(1, 2)
-        scores = torch.matmul(q, k.transpose(-1, -2))         # [b, h, Tv, Tl]
-        p_v = torch.softmax(scores, dim=-1)                   # vision -> language
-        p_l = torch.softmax(scores.transpose(-1, -2), dim=-1)  # language -> vision (rows of S^T)
-        if self.training and self.dropout > 0:
-            p_v = F.dropout(p_v, p=self.dropout, training=True)
-            p_l = F.dropout(p_l, p=self.dropout, training=True)
-        out_v = torch.matmul(p_v, vl).transpose(1, 2).reshape(bsz, tgt_len, self.embed_dim)
-        out_l = torch.matmul(p_l, vv).transpose(1, 2).reshape(bsz, src_len, self.embed_dim)
+        # one score matrix S = scale * q k^T per head, softmax over its rows (vision -> language) and over its columns
+        # (language -> vision), dropout on both maps, two probability x value products: dense.bi_attention
+        out_v, out_l = dense.bi_attention(q, k, vv, vl, self.num_heads, self.scale, self.dropout, self.training,
+                                          salt=getattr(self, "_rlipv2_salt", 0))
         out_v = dense.linear(out_v, self.out_v_proj.weight, self.out_v_proj.bias)
         out_l = dense.linear(out_l, self.out_l_proj.weight, self.out_l_proj.bias)
         return out_v, out_l

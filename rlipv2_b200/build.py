@@ -27,6 +27,7 @@ TARGETS = {
     "librlipv2_dense.so": (["dense_tf32.cu"], []),
     "librlipv2_fused.so": (["fused_ops.cu"], []),
     "librlipv2_lsap.so": (["lsap.cu"], []),
+    "librlipv2_attn.so": (["attn_tf32.cu"], []),
 }
 
 

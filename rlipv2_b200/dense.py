@@ -364,6 +364,96 @@ def add_layer_norm(x, residual, weight, bias, eps):
     return F.layer_norm(x + residual, (x.shape[-1],), weight, bias, eps)
 
 
+# ---- softmax-attention cores (csrc/attn_tf32.cu, include/rlipv2_attn.h) ---------------------------------------------
+# ALIF's bidirectional cross-attention (fuse_helper.py:395-445), the RobertaLayer's 12 x 64 self-attention
+# (modeling_roberta.py:185-241) and the decoders' query self-attention (dab_deformable/deformable_transformer.py:1383-1390)
+# are the same bmm -> softmax -> dropout -> bmm chain; in 'tf32' mode on a GPU it is ONE fused tcgen05 kernel forward and
+# one dS kernel + three batched tcgen05 GEMMs backward, on [B, T, H*D] tensors as the projections produce them.
+_ATTN = os.environ.get("RLIPV2_FUSED_ATTN", "1") != "0"
+_dropout_seeds = {}
+
+
+def dropout_seed(device):
+    """device-resident int64 counter the fused attention kernels hash their dropout masks from"""
+    s = _dropout_seeds.get(device)
+    if s is None:
+        s = _dropout_seeds[device] = torch.zeros(1, dtype=torch.int64, device=device) + (torch.initial_seed() % (2 ** 62))
+    return s
+
+
+def advance_dropout_seed(device):
+    """fresh dropout masks for the next forward (one tiny kernel; safe inside a CUDA-graph capture)"""
+    dropout_seed(device).add_(1)
+
+
+def _attn_abi():
+    from . import attn_abi
+    return attn_abi
+
+
+class _Attention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, key_bias, heads, scale, dropout_p, salt):
+        abi = _attn_abi()
+        q_, k_, v_ = (t if abi.usable(t) else t.contiguous() for t in (q, k, v))
+        kb = None
+        if key_bias is not None:
+            kb = key_bias if key_bias.is_contiguous() else key_bias.contiguous()
+        seed = dropout_seed(q.device) if dropout_p > 0 else None
+        out, stats, seed_used = abi.forward(q_, k_, v_, heads, kb, scale, dropout_p, seed, salt)
+        ctx.save_for_backward(q_, k_, v_, kb, out, stats, seed_used)
+        ctx.conf = (heads, scale, dropout_p, salt)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q_, k_, v_, kb, out, stats, seed_used = ctx.saved_tensors
+        heads, scale, dropout_p, salt = ctx.conf
+        g = dout if dout.is_contiguous() else dout.contiguous()
+        dq, dk, dv = _attn_abi().backward(q_, k_, v_, heads, kb, out, g, stats, scale, dropout_p, seed_used, salt)
+        return dq, dk, dv, None, None, None, None, None
+
+
+def _attn_ok(q, k, v, heads):
+    if not (_ATTN and _USE_TCGEN05 and _PRECISION == "tf32" and q.is_cuda and q.dtype == torch.float32 and q.dim() == 3):
+        return False
+    B, Tq, C = q.shape
+    return (k.shape[0] == B and v.shape == k.shape and k.shape[2] == C and C % heads == 0
+            and _attn_abi().supported(B, heads, Tq, k.shape[1], C // heads))
+
+
+def attention(q, k, v, heads, scale, key_bias=None, dropout_p=0.0, training=False, salt=0):
+    """softmax_j(scale * <q_i, k_j> + key_bias_j) -> dropout -> . v, per head.
+    q [B, Tq, H*D], k / v [B, Nk, H*D] (head h = columns [h*D, (h+1)*D)), key_bias [B, Nk] additive or None
+    -> [B, Tq, H*D]"""
+    p = float(dropout_p) if training else 0.0
+    if _attn_ok(q, k, v, heads):
+        return _Attention.apply(q, k, v, key_bias, heads, float(scale), p, int(salt))
+    # torch path: CPU host-logic tests, the IEEE-fp32 parity mode and problems beyond the kernel's 480 keys - the
+    # reference's own op chain
+    B, Tq, C = q.shape
+    D = C // heads
+    qh = q.reshape(B, Tq, heads, D).transpose(1, 2)
+    kh = k.reshape(B, -1, heads, D).transpose(1, 2)
+    vh = v.reshape(B, -1, heads, D).transpose(1, 2)
+    scores = torch.matmul(qh * scale, kh.transpose(-1, -2))
+    if key_bias is not None:
+        scores = scores + key_bias[:, None, None, :]
+    probs = torch.softmax(scores, dim=-1)
+    if p > 0:
+        probs = F.dropout(probs, p=p, training=True)
+    return torch.matmul(probs, vh).transpose(1, 2).reshape(B, Tq, C)
+
+
+def bi_attention(q, k, vv, vl, heads, scale, dropout_p=0.0, training=False, salt=0):
+    """ALIF's two directions over one score matrix S = scale * q k^T (fuse_helper.py:395-445):
+    out_v = dropout(softmax_rows(S)) vl  (image tokens attend to labels),
+    out_l = dropout(softmax_rows(S^T)) vv (labels attend to image tokens) - i.e. attention(q, k, vl) and attention(k, q, vv)."""
+    out_v = attention(q, k, vl, heads, scale, None, dropout_p, training, 2 * salt)
+    out_l = attention(k, q, vv, heads, scale, None, dropout_p, training, 2 * salt + 1)
+    return out_v, out_l
+
+
 # ---- input projections: GroupNorm on token-major activations, all feature levels into one token buffer -------------
 # Off by default: the kernels are parity-checked on the GPU (tests/test_fused_gpu.py) and the model plumbing on CPU
 # (tests/test_flat_levels_cpu.py), but the path has not had its A/B run inside the train step yet (in r01s4f a shape check

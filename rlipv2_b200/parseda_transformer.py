@@ -214,6 +214,11 @@ class RLIPv2_DeformableTransformerEncoder(nn.Module):
         self.VLFuse_layers = _get_clones(VLFuse_layer, num_layers // fusion_interval)
         self.fusion_last_vis = fusion_last_vis
         self.lang_aux_loss = lang_aux_loss
+        # call-site ids of the fused attention kernels' hashed dropout (one stream of masks per attention map)
+        for i, m in enumerate(self.VLFuse_layers):
+            m.b_attn.attn._rlipv2_salt = 0x100 + i
+        for i, m in enumerate(self.roberta_layers):
+            m.attention.self._rlipv2_salt = 0x400 + i
 
     @staticmethod
     def get_reference_points(spatial_shapes_host, valid_ratios, device):
@@ -243,6 +248,8 @@ class RLIPv2_DeformableTransformerEncoder(nn.Module):
             vis = {"src": src, "padding_mask": inv_padding_mask, "pos": pos}
         lang = {"hidden": lang_hidden, "masks": inv_lang_masks}
         multi_lay_lang = []
+        if self.training and src.is_cuda:
+            dense.advance_dropout_seed(src.device)          # fresh masks for the fused attention kernels' hashed dropout
         side, pending = None, False
         if _LANG_STREAM and src.is_cuda:
             if getattr(self, "_lang_stream", None) is None:
@@ -315,9 +322,6 @@ class DeformableTransformerEncoder(nn.Module):
         return src
 
 
-_SDPA_QUERY_ATTN = os.environ.get("RLIPV2_SDPA_QUERY_ATTN", "0") == "1"
-
-
 class QuerySelfAttention(nn.Module):
     """8x32 self-attention among the queries with nn.MultiheadAttention's parameter layout
     (`in_proj_weight [3C, C]`, `in_proj_bias`, `out_proj`), batch-first."""
@@ -336,20 +340,9 @@ class QuerySelfAttention(nn.Module):
         h, d = self.num_heads, c // self.num_heads
         qk = dense.linear(qk_input, self.in_proj_weight[:2 * c], self.in_proj_bias[:2 * c])
         v = dense.linear(v_input, self.in_proj_weight[2 * c:], self.in_proj_bias[2 * c:])
-        q, k = qk[..., :c], qk[..., c:]
-        q = q.view(b, t, h, d).transpose(1, 2)
-        k = k.view(b, t, h, d).transpose(1, 2)
-        v = v.view(b, t, h, d).transpose(1, 2)
-        if _SDPA_QUERY_ATTN and q.is_cuda and dense.matmul_precision() == "tf32":
-            # one fused-attention call each way instead of scale / bmm / softmax / bmm (+ their ~12 backward kernels) on the
-            # decoders' launch-bound chain; library kernel like the batched GEMMs it replaces.  Opt-in until measured.
-            o = F.scaled_dot_product_attention(q, k, v, dropout_p=self.dropout if self.training else 0.0, scale=d ** -0.5)
-            o = o.transpose(1, 2).reshape(b, t, c)
-            return dense.linear(o, self.out_proj.weight, self.out_proj.bias)
-        p = torch.softmax(torch.matmul(q * (d ** -0.5), k.transpose(-1, -2)), dim=-1)
-        if self.training and self.dropout > 0:
-            p = F.dropout(p, self.dropout)
-        o = torch.matmul(p, v).transpose(1, 2).reshape(b, t, c)
+        q, k = qk[..., :c], qk[..., c:]                       # column slices of the fused projection, used in place
+        # softmax(q k^T / sqrt(d)) -> dropout -> . v, 8 heads x 32 (nn.MultiheadAttention, :1383-1390): dense.attention
+        o = dense.attention(q, k, v, h, d ** -0.5, None, self.dropout, self.training, salt=getattr(self, "_rlipv2_salt", 0))
         return dense.linear(o, self.out_proj.weight, self.out_proj.bias)
 
 

@@ -13,8 +13,6 @@ Dropouts (p = 0.1 from the HF config) are active in training mode, as in the ref
 """
 import math
 
-import torch
-import torch.nn.functional as F
 from torch import nn
 
 from . import dense
@@ -32,17 +30,15 @@ class RobertaSelfAttention(nn.Module):
         self.dropout = nn.Dropout(config.attention_probs_dropout_prob)
 
     def forward(self, hidden_states, extended_mask):
-        b, t, _ = hidden_states.shape
+        """extended_mask: [b, 1, 1, t] additive (0 / -10000) or None"""
         h, d = self.num_attention_heads, self.attention_head_size
-        q = dense.linear(hidden_states, self.query.weight, self.query.bias).view(b, t, h, d).transpose(1, 2)
-        k = dense.linear(hidden_states, self.key.weight, self.key.bias).view(b, t, h, d).transpose(1, 2)
-        v = dense.linear(hidden_states, self.value.weight, self.value.bias).view(b, t, h, d).transpose(1, 2)
-        scores = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(d)
-        if extended_mask is not None:
-            scores = scores + extended_mask
-        probs = self.dropout(torch.softmax(scores, dim=-1))
-        ctx = torch.matmul(probs, v).transpose(1, 2).reshape(b, t, self.all_head_size)
-        return ctx
+        q = dense.linear(hidden_states, self.query.weight, self.query.bias)
+        k = dense.linear(hidden_states, self.key.weight, self.key.bias)
+        v = dense.linear(hidden_states, self.value.weight, self.value.bias)
+        key_bias = extended_mask.reshape(extended_mask.shape[0], -1) if extended_mask is not None else None
+        # softmax(q k^T / sqrt(d) + mask) -> dropout -> . v  (modeling_roberta.py:185-241): dense.attention
+        return dense.attention(q, k, v, h, 1.0 / math.sqrt(d), key_bias, self.dropout.p, self.training,
+                               salt=getattr(self, "_rlipv2_salt", 0))
 
 
 class RobertaSelfOutput(nn.Module):

@@ -452,9 +452,9 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
                 self._loss_backward_step(outputs, giou)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        from . import dense_abi, fused_abi, lsap_abi, msda_abi
+        from . import attn_abi, dense_abi, fused_abi, lsap_abi, msda_abi
         own = lambda: (msda_abi.launch_count() + dense_abi.launch_count() + fused_abi.launch_count()
-                       + lsap_abi.launch_count())
+                       + lsap_abi.launch_count() + attn_abi.launch_count())
         l0 = own()
         self.graph_a = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_a, stream=self.cap_stream):

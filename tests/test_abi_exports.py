@@ -39,8 +39,8 @@ def test_binding_matches_abi_version():
     assert os.path.exists(msda_abi.library_path())
     for sym in msda_abi.EXPORTS:
         assert sym in declared_symbols()
-    from rlipv2_b200 import dense_abi, fused_abi, lsap_abi
-    for abi in (dense_abi, fused_abi, lsap_abi):
+    from rlipv2_b200 import attn_abi, dense_abi, fused_abi, lsap_abi
+    for abi in (attn_abi, dense_abi, fused_abi, lsap_abi):
         assert os.path.exists(abi.library_path())
         for sym in abi.EXPORTS:
             assert sym in declared_symbols()

@@ -3,8 +3,12 @@
 Every GEMM-shaped op of ALIF, the RobertaLayer stack, the text tower and the deformable encoder/decoder goes through
 these functions, so the module code stays independent of how the contraction is executed.
 
-Two execution modes (`set_matmul_precision`):
+Three execution modes (`set_matmul_precision`):
   'fp32'  IEEE fp32 products through cuBLAS - used by the parity tests against the reference fixtures;
+  '3xtf32' the tcgen05 kernels with error-compensated operands: x = hi + lo with `hi` the TF32
+          truncation, x w ~ hi(x) hi(w) + hi(x) lo(w) + lo(x) hi(w) evaluated as ONE tcgen05 GEMM over the three-fold
+          contraction axis.  fp32-class accuracy (error ~2^-20), so the 1e-3 model-level parity tests run through the same
+          linear / weight-gradient / input-gradient kernels the benchmark uses; everything else as in 'fp32';
   'tf32'  TF32 tensor-core products, fp32 accumulation - what the reference's pinned torch 1.10 does by default on
           tensor-core GPUs, and what bench.py measures.  Forward linears whose shape the hand-written tcgen05 kernel
           supports (N % 128 == 0, K % 32 == 0; csrc/dense_tf32.cu, include/rlipv2_dense.h) run on it with bias / ReLU /
@@ -98,9 +102,43 @@ def join_param_grad_stream(device=None):
             _param_grad_pending.discard(dev)
 
 
+def _split_tf32(t):
+    """t = hi + lo, hi = t with the 13 low mantissa bits cleared (exactly what a TF32 tensor-core operand keeps)"""
+    hi = (t.view(torch.int32) & -8192).view(torch.float32)
+    return hi, t - hi
+
+
+def _linear_kernel(x2, w, bias, act, rm):
+    """act(x2 w^T + bias) on the tcgen05 kernel; '3xtf32': one GEMM over [hi | hi | lo] x [hi | lo | hi]"""
+    abi = _abi()
+    if _PRECISION == "3xtf32":
+        xh, xl = _split_tf32(x2)
+        wh, wl = _split_tf32(w)
+        return abi.linear_tf32(torch.cat((xh, xh, xl), 1), torch.cat((wh, wl, wh), 1), bias, act, rm)
+    return abi.linear_tf32(x2, w, bias, act, rm)
+
+
+def _wgrad_kernel(g, x2, acc=None):
+    """dw[N,K] (+)= g[T,N]^T x2[T,K] on the split-K tcgen05 kernel (contraction over the rows)"""
+    if _PRECISION == "3xtf32":
+        gh, gl = _split_tf32(g)
+        xh, xl = _split_tf32(x2)
+        return _abi().wgrad_tf32(torch.cat((gh, gh, gl), 0), torch.cat((xh, xl, xh), 0), acc=acc)
+    return _abi().wgrad_tf32(g, x2, acc=acc)
+
+
+def _dgrad_kernel(g, w):
+    """dx[T,K] = g[T,N] w[N,K] on the tcgen05 kernel (contraction over N)"""
+    if _PRECISION == "3xtf32":
+        gh, gl = _split_tf32(g)
+        wh, wl = _split_tf32(w)
+        return _abi().dgrad_tf32(torch.cat((gh, gh, gl), 1), torch.cat((wh, wl, wh), 0))[0]
+    return _abi().dgrad_tf32(g, w)[0]
+
+
 def set_matmul_precision(mode: str, tcgen05: bool = True, fused: bool = True):
     global _PRECISION, _USE_TCGEN05, _USE_FUSED
-    assert mode in ("fp32", "tf32")
+    assert mode in ("fp32", "tf32", "3xtf32")
     _PRECISION = mode
     _USE_TCGEN05 = tcgen05
     _USE_FUSED = fused
@@ -131,16 +169,19 @@ class _LinearTF32(torch.autograd.Function):
         if row_mask is not None:
             rm = row_mask.reshape(-1)
             rm = rm if rm.is_contiguous() else rm.contiguous()
-        if library_small and act == 0 and rm is None and x2.shape[0] <= _LIBRARY_SMALL_MAX_ROWS and w.shape[1] >= 512:
+        if (library_small and act == 0 and rm is None and x2.shape[0] <= _LIBRARY_SMALL_MAX_ROWS and w.shape[1] >= 512
+                and _PRECISION == "tf32"):
             # plain small-M / long-K linears of the (third-party, HF) text tower: cuBLAS' split-K kernels are 2-3x faster
             # than one 128-row tile per CTA here (profiles/dense_microbench_r01_v3_small_grids.jsonl); backward unchanged
             y = F.linear(x2, w, bias)
+        elif _PRECISION == "3xtf32":
+            y = _linear_kernel(x2, w, bias, act, rm)
         elif _SPLITK_FWD and act == 0 and rm is None and abi.splitk_splits(x2.shape[0], w.shape[0], w.shape[1]) > 1:
             # small-M / long-K (ALIF out projections, label-side in-projections, RobertaLayer FFN-down): K split over the
             # SMs one-CTA-per-tile leaves idle (rlipv2_dense_linear_splitk_tf32); backward unchanged
             y = abi.linear_splitk_tf32(x2, w, bias, abi.splitk_splits(x2.shape[0], w.shape[0], w.shape[1]))
         else:
-            y = abi.linear_tf32(x2, w, bias, act, rm)
+            y = _linear_kernel(x2, w, bias, act, rm)
         ctx.act = act
         ctx.has_bias = bias is not None
         # parameters whose .grad is a view of the step's flat gradient buffer (train_step marks them `_fuse_grad`):
@@ -187,19 +228,19 @@ class _LinearTF32(torch.autograd.Function):
                 if plain_bias and ctx.has_bias and ctx.needs_input_grad[2]:
                     _fused().relu_bwd_colsum(g, None, acc=b_acc)
                 if big and _OWN_WGRAD and (_OWN_BWD or N * K <= 384 * 256):
-                    _abi().wgrad_tf32(g, x2, acc=w_acc)  # split-K tcgen05 kernel, reduces straight into the view
+                    _wgrad_kernel(g, x2, acc=w_acc)      # split-K tcgen05 kernel, reduces straight into the view
                 else:
                     w_acc.addmm_(g.t(), x2)              # cuBLAS with beta = 1: grad view += g^T x
             if ctx.needs_input_grad[0]:
-                gx = (_abi().dgrad_tf32(g, w)[0] if _OWN_BWD and big else g @ w).view(*grad_out.shape[:-1], K)
+                gx = (_dgrad_kernel(g, w) if (_OWN_BWD or _PRECISION == "3xtf32") and big else g @ w).view(*grad_out.shape[:-1], K)
             return gx, None, None, None, None, None
         if ctx.needs_input_grad[0]:
-            gx = (_abi().dgrad_tf32(g, w)[0] if _OWN_BWD and big else g @ w).view(*grad_out.shape[:-1], K)
+            gx = (_dgrad_kernel(g, w) if (_OWN_BWD or _PRECISION == "3xtf32") and big else g @ w).view(*grad_out.shape[:-1], K)
         if ctx.needs_input_grad[1]:
             # tall-skinny weight gradients (44k tokens -> a 256x256 .. 384x256 weight): cuBLAS falls back to an
             # sm_80 64x64 kernel at 65-72 us; the split-K tcgen05 kernel takes 28-40 us (measured, B200)
             if big and _OWN_WGRAD and (_OWN_BWD or N * K <= 384 * 256):
-                gw = _abi().wgrad_tf32(g, x2, acc=w_acc)
+                gw = _wgrad_kernel(g, x2, acc=w_acc)
                 gw = None if w_acc is not None else gw
             elif w_acc is not None:
                 w_acc.addmm_(g.t(), x2)                  # cuBLAS with beta = 1: grad view += g^T x
@@ -272,7 +313,7 @@ class _FFNReLU(torch.autograd.Function):
 def ffn_relu(x, w1, b1, w2, b2):
     """relu(x W1^T + b1) W2^T + b2"""
     M = x.numel() // x.shape[-1]
-    if ((_OWN_BWD or _FFN_BWD == "hybrid") and _tcgen05_ok(x, w1) and _abi().supported(M, w2.shape[0], w2.shape[1]) and M >= _OWN_BWD_MIN_ROWS
+    if (_PRECISION == "tf32" and (_OWN_BWD or _FFN_BWD == "hybrid") and _tcgen05_ok(x, w1) and _abi().supported(M, w2.shape[0], w2.shape[1]) and M >= _OWN_BWD_MIN_ROWS
             and b1 is not None and b2 is not None and w2.shape[0] % 32 == 0):
         return _FFNReLU.apply(x, w1, b1, w2, b2)
     return linear(linear_relu(x, w1, b1), w2, b2)
@@ -322,7 +363,7 @@ def _fused_ln_ok(x):
 
 
 def _tcgen05_ok(x, weight):
-    if not (_USE_TCGEN05 and _PRECISION == "tf32" and x.is_cuda and x.dtype == torch.float32):
+    if not (_USE_TCGEN05 and _PRECISION in ("tf32", "3xtf32") and x.is_cuda and x.dtype == torch.float32):
         return False
     M = x.numel() // x.shape[-1]
     return M > 0 and _abi().supported(M, weight.shape[0], weight.shape[1])

@@ -98,14 +98,9 @@ def _run_step(device):
     return g, model, criterion, cache, out, loss_dict, total, targets, GRAD_KEYS
 
 
-@pytest.mark.parametrize("device", DEVICES)
-def test_full_step_golden(device, request):
-    _fp32()
-    if device == "cpu":
-        request.getfixturevalue("msda_cpu_stub")
-    g, model, criterion, cache, out, loss_dict, total, targets, GRAD_KEYS = _run_step(device)
+def _assert_step(res, tol, loss_rtol, grad_tol, exact_indices=True):
+    g, model, criterion, cache, out, loss_dict, total, targets, GRAD_KEYS = res
     c = lambda t: t.detach().cpu().numpy()
-    tol = dict(rtol=1e-3, atol=2e-4)
     # phase A
     np.testing.assert_array_equal(c(cache["text_attention_mask"]), g["text_attention_mask"])
     np.testing.assert_allclose(c(cache["valid_ratios"]), g["valid_ratios"], rtol=1e-6)
@@ -116,19 +111,30 @@ def test_full_step_golden(device, request):
         np.testing.assert_allclose(c(out[k]), g["out_" + k], **tol)
         for i, a in enumerate(out["aux_outputs"]):
             np.testing.assert_allclose(c(a[k]), g[f"aux{i}_" + k], **tol)
-    # matcher indices: bit-exact
+    # matcher indices: bit-exact (IEEE-class arithmetic), or - under TF32 products - optimal up to the perturbation of the costs
     layers = [{k: v for k, v in out.items() if k != "aux_outputs"}] + list(out["aux_outputs"])
     for li, o in enumerate(layers):
-        for b, (i, j) in enumerate(criterion.matcher(o, targets)):
+        C, _ = criterion.matcher.compute_costs(o, targets)
+        sizes = [len(t["obj_labels"]) for t in targets]
+        for b, ((i, j), cb) in enumerate(zip(criterion.matcher(o, targets), C.cpu().split(sizes, -1))):
             assert i.dtype == torch.int64 and j.dtype == torch.int64 and i.device.type == "cpu"
-            np.testing.assert_array_equal(i.numpy(), g[f"match{li}_{b}_i"])
-            np.testing.assert_array_equal(j.numpy(), g[f"match{li}_{b}_j"])
+            gi, gj = g[f"match{li}_{b}_i"], g[f"match{li}_{b}_j"]
+            if exact_indices:
+                np.testing.assert_array_equal(i.numpy(), gi)
+                np.testing.assert_array_equal(j.numpy(), gj)
+            else:
+                # the reference's assignment, priced with THIS run's costs, may beat this run's optimum only by the cost
+                # perturbation (2 k delta): indices agree wherever the reference's margin exceeds the TF32 error
+                mine, theirs = float(cb[b][i, j].sum()), float(cb[b][torch.from_numpy(gi), torch.from_numpy(gj)].sum())
+                assert mine <= theirs + 1e-6
+                assert theirs - mine <= 2 * len(gi) * 2e-2, (li, b, mine, theirs)
+                assert sorted(j.tolist()) == sorted(gj.tolist())
     # losses: same keys, same values
     gold_keys = sorted(k[len("loss_"):] for k in g if k.startswith("loss_"))
     assert sorted(loss_dict.keys()) == gold_keys
     for k, v in loss_dict.items():
-        np.testing.assert_allclose(float(v), float(g["loss_" + k]), rtol=1e-3, atol=1e-4, err_msg=k)
-    np.testing.assert_allclose(float(total), float(g["total_loss"]), rtol=1e-3)
+        np.testing.assert_allclose(float(v), float(g["loss_" + k]), rtol=loss_rtol, atol=loss_rtol / 10, err_msg=k)
+    np.testing.assert_allclose(float(total), float(g["total_loss"]), rtol=loss_rtol)
     # backward: gradient norms and strided samples of selected parameters (vector-relative error: the
     # samples contain near-zero entries, where an element-wise relative test is meaningless)
     params = model.state_dict(keep_vars=True)
@@ -142,8 +148,48 @@ def test_full_step_golden(device, request):
         ref = g["grad_" + k].astype(np.float64)
         worst[k] = (abs(float(gk.norm()) - ref_norm) / (ref_norm + 1e-12),
                     float(np.linalg.norm(sample - ref) / (np.linalg.norm(ref) + 1e-12)))
-    bad = {k: v for k, v in worst.items() if v[0] > 2e-3 or v[1] > 5e-3}
+    bad = {k: v for k, v in worst.items() if v[0] > grad_tol[0] or v[1] > grad_tol[1]}
     assert not bad, f"gradient mismatch (norm rel err, sample rel err): {bad}"
+
+
+@pytest.mark.parametrize("device", DEVICES)
+def test_full_step_golden(device, request):
+    _fp32()
+    if device == "cpu":
+        request.getfixturevalue("msda_cpu_stub")
+    _assert_step(_run_step(device), dict(rtol=1e-3, atol=2e-4), 1e-3, (2e-3, 5e-3))
+
+
+@pytest.mark.gpu
+def test_full_step_golden_3xtf32():
+    """The same fixture at the same 1e-3 tolerances with every supported linear / weight gradient / input gradient on the
+    tcgen05 kernels, operands split into TF32 hi + lo parts (dense.py '3xtf32'; SURVEY.md section 7's error-compensated
+    switch): model-level parity that DOES run through the hand-written contraction kernels."""
+    from rlipv2_b200 import dense, dense_abi
+    try:
+        dense.set_matmul_precision("3xtf32")
+        n0 = dense_abi.launch_count()
+        res = _run_step("cuda")
+        assert dense_abi.launch_count() - n0 > 100          # the step really went through the tcgen05 kernels
+        _assert_step(res, dict(rtol=1e-3, atol=2e-4), 1e-3, (2e-3, 5e-3))
+    finally:
+        _fp32()
+
+
+@pytest.mark.gpu
+def test_full_step_golden_tf32():
+    """The benchmark's arithmetic (TF32 tensor-core products: tcgen05 linears, fused attention cores, cuBLAS / cuDNN TF32)
+    against the fp32 fixture: every output of every decoder level, every loss, gradient norms and samples, and matcher
+    indices wherever the assignment is decided by more than the TF32 perturbation of the costs."""
+    from rlipv2_b200 import attn_abi, dense, dense_abi
+    try:
+        dense.set_matmul_precision("tf32")
+        n0, a0 = dense_abi.launch_count(), attn_abi.launch_count()
+        res = _run_step("cuda")
+        assert dense_abi.launch_count() - n0 > 100 and attn_abi.launch_count() - a0 >= 3 * 3 + 6
+        _assert_step(res, dict(rtol=2e-2, atol=2e-2), 5e-3, (1e-2, 3e-2), exact_indices=False)
+    finally:
+        _fp32()
 
 
 @pytest.mark.parametrize("device", DEVICES)

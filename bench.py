@@ -42,6 +42,22 @@ M, D, L, P = 8, 32, 4, 4
 METRIC = "images/sec RLIPv2-ParSeDA R50 800px train step"
 
 
+TRAINABLE_PARAMS_R50 = 212737454          # parameters that receive a gradient in the BASELINE config-2 step (flat buffer)
+
+
+def train_config(batch, world, nparams, graphs=True, backbone=None, pretrain=False):
+    """the `config` object of a train_step line; the reference arm prints the SAME object for the same workload"""
+    return {"workload": ("train_step: RLIPv2-ParSeDA R50 HICO-DET fine-tune step (BASELINE config 2), batch 2 x 3x800x1333 "
+                         "per GPU, 300 queries, 256 label strings, AdamW, clip 0.1, random-init weights") if backbone is None else
+                        (f"train_step: RLIPv2-ParSeDA {backbone}, {'relational pre-train' if pretrain else 'HICO-DET fine-tune'} "
+                         f"flags, batch {batch} x 3x800x1333 per GPU, 300 queries, 256 label strings, AdamW, clip 0.1, random-init weights"),
+            "per_gpu_batch": batch, "global_batch": batch * world, "trainable_params": nparams,
+            "l2": "working set >> L2 (activations > 2 GB per image)",
+            "execution": "2 CUDA graphs per step + host LSAP" if graphs else "eager",
+            "parallelism": (f"dp{world} (flat-gradient NCCL all-reduce in graph)" if graphs else
+                            f"dp{world} (DDP static_graph, NCCL)") if world > 1 else "dp1"}
+
+
 def peaks():
     p = {"hbm_gbs": 6650.0, "src": "fallback (B200_PROFILING.md)"}
     try:
@@ -311,15 +327,8 @@ def run_train_step(args, rank, world, device):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 storage, " + ("tf32 tensor-core products" if dense.matmul_precision() == "tf32" else "fp32 products"),
         "data": "synthetic",
-        "config": {"workload": ("train_step: RLIPv2-ParSeDA R50 HICO-DET fine-tune step (BASELINE config 2), batch 2 x 3x800x1333 "
-                                "per GPU, 300 queries, 256 label strings, AdamW, clip 0.1, random-init weights") if model_args is None else
-                               (f"train_step: RLIPv2-ParSeDA {args.backbone}, {'relational pre-train' if args.pretrain else 'HICO-DET fine-tune'} "
-                                f"flags, batch {batch} x 3x800x1333 per GPU, 300 queries, 256 label strings, AdamW, clip 0.1, random-init weights"),
-                   "per_gpu_batch": batch, "global_batch": batch * world, "trainable_params": nparams,
-                   "l2": "working set >> L2 (activations > 2 GB per image)",
-                   "execution": "2 CUDA graphs per step + host LSAP" if args.graphs else "eager",
-                   "parallelism": (f"dp{world} (flat-gradient NCCL all-reduce in graph)" if args.graphs else
-                                   f"dp{world} (DDP static_graph, NCCL)") if world > 1 else "dp1"},
+        "config": train_config(batch, world, nparams, args.graphs, args.backbone if model_args is not None else None,
+                               args.pretrain),
         "clocks": clk.summary(), "gpu_launches": int(launches), "final_loss": final_loss,
         "e2e": {"value": batch * world / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
@@ -410,13 +419,19 @@ def main():
         if rank != 0:
             return
         cb = cpu_reference(args.workload, steps=args.steps, warmup=args.warmup)
-        line = {"impl": "reference", "metric": METRIC if args.workload == "train_step" else "images/sec (MSDeformAttn calls)",
+        if args.workload == "train_step":
+            # whole optimisation steps of the CPU port on the host cores (oracle/parseda_oracle.py time_train_step_sample):
+            # `steps` = the steps really timed, ms_per_step = the measured time of one of them, value = images / second
+            ms = cb["step_s"] * 1e3
+            cfg = train_config(BATCH, 1, TRAINABLE_PARAMS_R50)
+        else:
+            ms = BATCH / cb["value"] * 1e3
+            cfg = {"workload": "msda_step: 12 MSDeformAttn fwd+bwd calls (6x Lq=S=22223, 3x Lq=300, 3x Lq=150), batch 2",
+                   "per_gpu_batch": BATCH, "l2": "inputs>L2 (rotating input sets)", "parallelism": f"replicas x{world}"}
+        line = {"impl": "reference", "metric": METRIC if args.workload == "train_step" else "images/sec (MSDeformAttn fwd+bwd calls of one RLIPv2-ParSeDA R50 train step)",
                 "value": cb["value"], "unit": "images/s", "n_gpus": world, "steps": cb.get("timed_steps", args.steps),
-                "warmup": args.warmup,
-                "ms_per_step": BATCH / cb["value"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": {"workload": args.workload + " (CPU oracle port, bounded sample)", "per_gpu_batch": BATCH},
-                "cpu_baseline": cb,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": cfg, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return

@@ -426,49 +426,67 @@ def synthetic_weights(num_queries, seed=0):
     return W
 
 
-def time_train_step_sample(threads, budget_s=25.0, batch=2, steps=1, warmup=0, total_budget_s=150.0):
-    """Forward + losses + backward of the oracle on the host cores for ONE image, at the largest of
-    (200x333, 400x667, 800x1333) that fits the time budget; cost is ~linear in pixels, so the
-    800x1333 batch-`batch` step time is extrapolated by the pixel ratio.  Optimizer step excluded
-    (it is <2 % of a CPU step).  `steps` / `warmup`: after the size has been chosen the sample is repeated `warmup`
-    times untimed and up to `steps` times timed (fewer if `total_budget_s` would be exceeded; the number actually
-    timed is reported as `timed_steps`) and the mean is reported."""
+def time_train_step_sample(threads, budget_s=25.0, batch=2, steps=1, warmup=0, total_budget_s=240.0):
+    """REAL optimisation steps of the oracle on the host cores: forward + losses + backward + clip_grad_norm_(0.1) + AdamW
+    (the three learning-rate groups of main.py:523-539) on `batch` synthetic 3x800x1333 images, 300 queries, 256 labels -
+    BASELINE config 2, the configuration bench.py's GPU arm times.  `warmup` untimed and `steps` timed steps, each one whole
+    step; when the whole run would not fit `total_budget_s` (the box is slower than expected) the sample shrinks to
+    ONE image per step - still a full-resolution step, reported per image - and, failing that, fewer timed steps
+    (`timed_steps` says how many).  Called with steps = 1, warmup = 0 (bench.py's `cpu_baseline` leg) it times one
+    single-image step within `budget_s`.  value = images processed / time, never extrapolated across resolutions."""
+    from rlipv2_b200.synth import synthetic_batch, synthetic_text          # (module without any C-ABI library)
     from rlipv2_b200.text_encoder import HashTokenizer
-    from rlipv2_b200.train_step import synthetic_batch, synthetic_text
     torch.set_num_threads(threads)
     W = synthetic_weights(300)
-    train = [k for k in W if not k.startswith("backbone.") and not k.startswith("transformer.text_encoder.")]
-    for k in train:
-        W[k].requires_grad_(True)
     third = build_third_party(W)
+    resnet, text_model = third
+    for k in W:
+        if not k.startswith("backbone.") and not k.startswith("transformer.text_encoder."):
+            W[k].requires_grad_(True)
+    groups = [[v for k, v in W.items() if v.requires_grad and not k.startswith("transformer.text_encoder.")],
+              [p for p in resnet.parameters() if p.requires_grad],
+              [p for p in text_model.parameters() if p.requires_grad]]
+    seen, uniq = set(), []
+    for g in groups:                                        # bbox-head aliases share storage: one optimizer slot each
+        u = []
+        for p in g:
+            if id(p) not in seen:
+                seen.add(id(p))
+                u.append(p)
+        uniq.append(u)
+    opt = torch.optim.AdamW([{"params": uniq[0]}, {"params": uniq[1], "lr": 1.41e-5}, {"params": uniq[2], "lr": 1.41e-5}],
+                            lr=1.41e-4, weight_decay=1e-4)
+    params = [p for g in uniq for p in g]
     text = synthetic_text(170, 85)
-    full = 800 * 1333
+    h, w = 800, 1333
 
-    def one(h, w):
-        images, targets = synthetic_batch(1, h, w, pin=False)
+    def one(nimg):
+        images, targets = synthetic_batch(nimg, h, w, pin=False)
         t0 = time.perf_counter()
-        out, _ = forward_step(W, third, images, torch.zeros(1, h, w, dtype=torch.bool), text, HashTokenizer(), drop=0.1)
+        out, _ = forward_step(W, third, images, torch.zeros(nimg, h, w, dtype=torch.bool), text, HashTokenizer(), drop=0.1)
         _, total, _ = criterion(out, targets)
+        opt.zero_grad(set_to_none=True)
         total.backward()
-        dt = time.perf_counter() - t0
-        for k in train:
-            W[k].grad = None
-        return dt
+        torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 0.1)
+        opt.step()
+        return time.perf_counter() - t0
 
-    for (h, w) in ((200, 333), (400, 667), (800, 1333)):
-        dt = one(h, w)                                   # the size ladder doubles as the first warm-up pass
-        if dt * 4.5 > budget_s:
-            break
-    times = [dt]
-    if steps > 1 or warmup > 0:
-        for _ in range(max(0, warmup - 1)):
-            one(h, w)
-        times, spent = [], 0.0
+    nimg = 1 if (steps <= 1 and warmup <= 0) else batch
+    first = one(nimg)                                      # first pass: doubles as warm-up and as the cost probe
+    if nimg > 1 and first * (steps + max(0, warmup - 1)) > total_budget_s:
+        nimg = 1                                            # bounded sample: one full-resolution image per step
+        first = one(nimg)
+    for _ in range(max(0, warmup - 1) if steps > 1 or warmup > 0 else 0):
+        one(nimg)
+    times, spent = [], 0.0
+    if steps <= 1 and warmup <= 0:
+        times = [first]
+    else:
         while len(times) < steps and (not times or spent + times[-1] <= total_budget_s):
-            times.append(one(h, w))
+            times.append(one(nimg))
             spent += times[-1]
     dt = sum(times) / len(times)
-    per_step = dt * (full / (h * w)) * batch
-    return {"value": batch / per_step, "unit": "images/s", "cores": threads, "kind": "port", "timed_steps": len(times),
-            "sample": f"oracle/parseda_oracle.py fwd+loss+bwd, 1 image {h}x{w}, 300 queries, 256 labels: {dt:.2f} s "
-                      f"(mean of {len(times)}); scaled by pixel ratio x batch {batch} to the 800x1333 step"}
+    return {"value": nimg / dt, "unit": "images/s", "cores": threads, "kind": "port", "timed_steps": len(times),
+            "images_per_step": nimg, "step_s": dt,
+            "sample": f"oracle/parseda_oracle.py: whole optimisation steps (fwd + loss + bwd + clip + AdamW) on {nimg} "
+                      f"image(s) 800x1333, 300 queries, 256 labels: {dt:.2f} s per step (mean of {len(times)})"}

@@ -137,14 +137,26 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
 }
 
-// the same dropout rule as the text tower's short-sequence kernel (csrc/fused_ops.cu sa_keep)
-__device__ __forceinline__ bool keep_element(unsigned long long seed, unsigned salt, unsigned idx, unsigned thresh) {
+// Dropout: one splitmix64 hash of (seed, salt, group index) decides FOUR consecutive keys of a row (16 bits each against a
+// 16-bit threshold), so the mask costs ~6 integer instructions per element instead of ~25.  Group index =
+// (batch x head x query row) * (Nk_pad / 4) + key / 4: the forward and the backward regenerate the same bits.
+__device__ __forceinline__ unsigned long long hash4(unsigned long long seed, unsigned salt, unsigned idx) {
     unsigned long long z = seed * 0x9E3779B97F4A7C15ull + ((unsigned long long)salt << 32 | idx) + 0xD1B54A32D192ED03ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    return (unsigned)(z >> 32) >= thresh;
+    return z ^ (z >> 31);
 }
+__device__ __forceinline__ bool keep_of(unsigned long long z, int u, unsigned thresh16) {
+    return ((unsigned)(z >> (16 * u)) & 0xFFFFu) >= thresh16;
+}
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+constexpr int kSoftmaxWarps = 8;                          // 2 per TMEM lane quadrant: each takes half of the columns
+constexpr int kThreadsAttn = 64 + 32 * kSoftmaxWarps;     // + TMA warp + MMA warp
 
 struct FwdArgs {
     int B, H, Tq, Nk, D, dv_tile, Nk_pad, nbox, box_rows, stages, stage_bytes;
@@ -158,7 +170,7 @@ struct FwdArgs {
     long long *seed_used;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsAttn, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const FwdArgs a)
 {
@@ -168,7 +180,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     uint64_t *empty_bar = full_bar + a.stages;
     uint64_t *s_full = empty_bar + a.stages, *p_ready = s_full + 1, *o_full = s_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(s_full + 3);
-    float *kb = reinterpret_cast<float *>(tmem_slot + 4);                 // [Nk_pad]: additive key bias, -inf past Nk
+    float *red = reinterpret_cast<float *>(tmem_slot + 4);               // [2][128]: per-half row max, then row sum
+    float *kb = red + 2 * kTile;                                          // [Nk_pad]: log2e * key bias, -inf past Nk
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, bh = blockIdx.y;
@@ -183,7 +196,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tm_v) : "memory");
         for (int s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(s_full, 1);
-        mbar_init(p_ready, 128);
+        mbar_init(p_ready, 32 * kSoftmaxWarps);
         mbar_init(o_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && a.seed_used) *a.seed_used = a.seed ? *a.seed : 0ll;
@@ -193,8 +206,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp >= 2) {
-        for (int c = threadIdx.x - 64; c < a.Nk_pad; c += 128)
-            kb[c] = c < a.Nk ? (a.key_bias ? __ldg(a.key_bias + (size_t)b * a.Nk + c) : 0.f) : -INFINITY;
+        for (int c = threadIdx.x - 64; c < a.Nk_pad; c += 32 * kSoftmaxWarps)
+            kb[c] = c < a.Nk ? (a.key_bias ? kLog2e * __ldg(a.key_bias + (size_t)b * a.Nk + c) : 0.f) : -INFINITY;
     }
     fence_before();
     __syncthreads();
@@ -258,54 +271,71 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
             umma_commit(o_full);
         }
-    } else {                                                             // ---- softmax + epilogue warps 2..5
+    } else {                                                             // ---- softmax + epilogue warps 2..9
         const int q4 = warp & 3;                                         // TMEM lane quadrant this warp may touch
-        const int grow = qt * kTile + q4 * 32 + lane;                    // query row of this thread
+        const int half = (warp - 2) >> 2;                                // which half of the key / output columns
+        const int rloc = q4 * 32 + lane;
+        const int grow = qt * kTile + rloc;                              // query row of this thread
         const uint32_t lane_s = tmem_s + ((uint32_t)(q4 * 32) << 16);
         const unsigned long long seed = (a.thresh && a.seed) ? (unsigned long long)*a.seed : 0ull;
+        const float scale2 = a.scale * kLog2e;
+        const int c_lo = half ? (nkc + 1) / 2 : 0, c_hi = half ? nkc : (nkc + 1) / 2;
         mbar_wait(s_full, 0);
         fence_after();
         uint32_t r[32];
         float m = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < nkc; ++c) {
+        for (int c = c_lo; c < c_hi; ++c) {
             tmem_ld32(lane_s + (uint32_t)(c * 32), r);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) m = fmaxf(m, fmaf(__uint_as_float(r[j]), a.scale, kb[c * 32 + j]));
+            for (int j = 0; j < 32; ++j) m = fmaxf(m, fmaf(__uint_as_float(r[j]), scale2, kb[c * 32 + j]));
         }
+        red[half * kTile + rloc] = m;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        m = fmaxf(red[rloc], red[kTile + rloc]);                         // finite: the first half always holds a real key
+        asm volatile("bar.sync 1, 256;" ::: "memory");                   // both halves have read before `red` is reused
         float sum = 0.f;
-        const unsigned idx_row = (unsigned)(((size_t)bh * a.Tq + grow) * (size_t)a.Nk);
+        const unsigned grp_row = (unsigned)((size_t)bh * a.Tq + grow) * (unsigned)(a.Nk_pad / 4);
 #pragma unroll 1
-        for (int c = 0; c < nkc; ++c) {
+        for (int c = c_lo; c < c_hi; ++c) {
             tmem_ld32(lane_s + (uint32_t)(c * 32), r);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float e = expf(fmaf(__uint_as_float(r[j]), a.scale, kb[c * 32 + j]) - m);
-                sum += e;
-                bool keep = true;
-                if (a.thresh) keep = keep_element(seed, a.salt, idx_row + (unsigned)(c * 32 + j), a.thresh);
-                r[j] = keep ? __float_as_uint(e) : 0u;
+            for (int j = 0; j < 32; j += 4) {
+                unsigned long long z = 0ull;
+                if (a.thresh) z = hash4(seed, a.salt, grp_row + (unsigned)(c * 8 + (j >> 2)));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float e = ex2(fmaf(__uint_as_float(r[j + u]), scale2, kb[c * 32 + j + u]) - m);
+                    sum += e;
+                    const bool keep = a.thresh ? keep_of(z, u, a.thresh) : true;
+                    r[j + u] = keep ? __float_as_uint(e) : 0u;
+                }
             }
             tmem_st32(lane_s + (uint32_t)(c * 32), r);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         fence_before();
         mbar_arrive(p_ready);
-        if (blockIdx.z == 0 && grow < a.Tq && a.stats) {
+        red[half * kTile + rloc] = sum;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        sum = red[rloc] + red[kTile + rloc];
+        if (half == 0 && blockIdx.z == 0 && grow < a.Tq && a.stats) {
             float2 *st = reinterpret_cast<float2 *>(a.stats) + ((size_t)bh * a.Tq + grow);
-            *st = make_float2(m, sum);
+            *st = make_float2(m * kLn2, sum);                            // natural-log units: max of scale * s + bias
         }
         const float inv = a.inv_keep / sum;
         mbar_wait(o_full, 0);
         fence_after();
-        // staging for coalesced stores: 32 rows x 36 floats per warp, aliasing pipeline stage 0 (every MMA - hence every
-        // shared-memory read - has retired when o_full fires and the producer has nothing left to load)
+        // staging for coalesced stores: 32 rows x 36 floats per warp, aliasing the head of the pipeline ring (every MMA -
+        // hence every shared-memory read - has retired when o_full fires and the producer has nothing left to load)
         float *stage_out = reinterpret_cast<float *>(smem) + (warp - 2) * (32 * 36);
         const int sub = lane & 7, rgrp = lane >> 3;
         const uint32_t lane_o = tmem_o + ((uint32_t)(q4 * 32) << 16);
         float *obase = a.out + (size_t)b * a.o_bs + col_base + dv0;
+        const int noc = a.dv_tile / 32;
+        const int o_lo = half ? (noc + 1) / 2 : 0, o_hi = half ? noc : (noc + 1) / 2;
 #pragma unroll 1
-        for (int c = 0; c < a.dv_tile / 32; ++c) {
+        for (int c = o_lo; c < o_hi; ++c) {
             tmem_ld32(lane_o + (uint32_t)(c * 32), r);
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -344,7 +374,7 @@ struct DsArgs {
     const long long *seed_used;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsAttn, 1)
 attn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_v, const DsArgs a)
 {
@@ -355,7 +385,7 @@ attn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     uint64_t *empty_bar = full_bar + a.stages;
     uint64_t *acc_full = empty_bar + a.stages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
-    float *kb = reinterpret_cast<float *>(tmem_slot + 4);                 // [128]
+    float *kb = reinterpret_cast<float *>(tmem_slot + 4);                 // [128]: log2e * key bias of this key chunk
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, bh = blockIdx.y, kc = blockIdx.z;
@@ -377,9 +407,9 @@ attn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp >= 2) {
+    if (warp >= 2 && warp < 6) {
         const int c = threadIdx.x - 64, key = key0 + c;
-        kb[c] = key < a.Nk ? (a.key_bias ? __ldg(a.key_bias + (size_t)b * a.Nk + key) : 0.f) : -INFINITY;
+        kb[c] = key < a.Nk ? (a.key_bias ? kLog2e * __ldg(a.key_bias + (size_t)b * a.Nk + key) : 0.f) : -INFINITY;
     }
     fence_before();
     __syncthreads();
@@ -421,6 +451,7 @@ attn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
     } else {
         const int q4 = warp & 3;
+        const int half = (warp - 2) >> 2;                                // key columns [64 * half, 64 * half + 64) of the chunk
         const int row0 = qt * kTile + q4 * 32;
         const int grow = row0 + lane;
         // delta[row] = <dO[row], O[row]> over the head's D columns (= sum_j P~ dP~): one coalesced pass per row
@@ -437,34 +468,35 @@ attn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == rr) delta = acc;
         }
-        float m = 0.f, inv_l = 1.f;
+        float m2 = 0.f, inv_l = 1.f;
         if (grow < a.Tq) {
             const float2 st = __ldg(reinterpret_cast<const float2 *>(a.stats) + ((size_t)bh * a.Tq + grow));
-            m = st.x;
+            m2 = st.x * kLog2e;
             inv_l = 1.f / st.y;
         }
         const unsigned long long seed = (a.thresh && a.seed_used) ? (unsigned long long)*a.seed_used : 0ull;
-        const unsigned idx_row = (unsigned)(((size_t)bh * a.Tq + grow) * (size_t)a.Nk);
+        const unsigned grp_row = (unsigned)((size_t)bh * a.Tq + grow) * (unsigned)(a.Nk_pad / 4);
+        const float scale2 = a.scale * kLog2e;
         mbar_wait(acc_full, 0);
         fence_after();
-        float *stage_ds = reinterpret_cast<float *>(smem) + (warp - 2) * (2 * 32 * 36);      // aliases stage 0 (idle now)
+        float *stage_ds = reinterpret_cast<float *>(smem) + (warp - 2) * (2 * 32 * 36);      // aliases the idle ring
         float *stage_p = stage_ds + 32 * 36;
         const int sub = lane & 7, rgrp = lane >> 3;
         const uint32_t lane_s = tmem_s + ((uint32_t)(q4 * 32) << 16), lane_dp = tmem_dp + ((uint32_t)(q4 * 32) << 16);
         uint32_t rs[32], rd[32];
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 2 * half; c < 2 * half + 2; ++c) {
             tmem_ld32(lane_s + (uint32_t)(c * 32), rs);
             tmem_ld32(lane_dp + (uint32_t)(c * 32), rd);
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 float ds4[4], p4[4];
+                unsigned long long z = 0ull;
+                if (a.thresh) z = hash4(seed, a.salt, grp_row + (unsigned)((key0 + c * 32 + j) >> 2));
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int cl = c * 32 + j + u;
-                    const float p = expf(fmaf(__uint_as_float(rs[j + u]), a.scale, kb[cl]) - m) * inv_l;
-                    bool keep = true;
-                    if (a.thresh) keep = keep_element(seed, a.salt, idx_row + (unsigned)(key0 + cl), a.thresh);
+                    const float p = ex2(fmaf(__uint_as_float(rs[j + u]), scale2, kb[c * 32 + j + u]) - m2) * inv_l;
+                    const bool keep = a.thresh ? keep_of(z, u, a.thresh) : true;
                     const float dp = keep ? __uint_as_float(rd[j + u]) * a.inv_keep : 0.f;
                     ds4[u] = a.scale * p * (dp - delta);
                     p4[u] = keep ? p * a.inv_keep : 0.f;
@@ -496,24 +528,35 @@ attn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// batched C[z] (+)= A[z] . B[z]^T, logical A [M, K], B [N, K]; X_MN: the operand is stored [K rows, M|N columns].
-// z = batch x head.  Operand X lives in a 3-D tensor [batches, rows, cols]: batch coordinate z / x_zdiv, column offset
-// (z % H) * x_hcols (head-sliced [B, T, H*D] tensors: zdiv = H, hcols = D; per-(batch, head) workspaces: zdiv 1, hcols 0).
-struct BgemmArgs {
-    int M, N, H, num_kb;
-    int a_zdiv, a_hcols, b_zdiv, b_hcols, c_zdiv, c_hcols;
-    float *C;
-    long long c_ld, c_bs;
+// The three gradient contractions of one attention call in ONE launch, operands read as stored (3-D TMA boxes):
+//   problem 0   dQ[b, :, h] (+)= dS[bh] . K[b, :, h]       A = dS  K-major (contraction = keys),       B = K  MN-major
+//   problem 1   dK[b, :, h] (+)= dS[bh]^T . Q[b, :, h]     A = dS  MN-major (contraction = query rows), B = Q  MN-major
+//   problem 2   dV[b, :, h] (+)= P~[bh]^T . dO[b, :, h]    A = P~  MN-major,                            B = dO MN-major
+// grid = (D / BLOCK_N, max row tiles, 3 * B * H); the A operands are the per-(batch, head) workspaces [B*H, Tq, Nk_pad],
+// the B operands and the results head-sliced [B, T, H*D] tensors.
+struct Bgemm3Args {
+    int H, N, Z;
+    int M[3], num_kb[3];
+    float *C[3];
+    long long c_ld[3], c_bs[3];
     int accumulate;
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 2)
-attn_bgemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const BgemmArgs g)
+attn_bgemm3_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_b0,
+                   const __grid_constant__ CUtensorMap tm_a1, const __grid_constant__ CUtensorMap tm_b1,
+                   const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_b2, const Bgemm3Args g)
 {
     constexpr int STAGES = 3;
     constexpr int kBBytes = BLOCK_N * kChunk * 4;
     constexpr int kStage = kTileBytes + kBBytes;
+    const int prob = blockIdx.z / g.Z, z = blockIdx.z - prob * g.Z;
+    const int n_blk = blockIdx.x, m_blk = blockIdx.y;
+    // (selected with constant indices: a dynamically indexed kernel-parameter array would be copied to local memory)
+    const int M = prob == 0 ? g.M[0] : (prob == 1 ? g.M[1] : g.M[2]);
+    const int num_kb = prob == 0 ? g.num_kb[0] : (prob == 1 ? g.num_kb[1] : g.num_kb[2]);
+    if (m_blk * kTile >= M) return;                                      // uniform per CTA, before any barrier / allocation
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * kStage);
@@ -522,14 +565,15 @@ attn_bgemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_blk = blockIdx.x, m_blk = blockIdx.y, z = blockIdx.z;
-    const int hz = z % g.H;
-    const int za = z / g.a_zdiv, zb = z / g.b_zdiv;
-    const int a_off = hz * g.a_hcols, b_off = hz * g.b_hcols;
+    const int hz = z % g.H, zb = z / g.H;
+    const int b_off = hz * g.N;
+    const bool a_mn = prob != 0;
+    const CUtensorMap *ta = prob == 0 ? &tm_a0 : (prob == 1 ? &tm_a1 : &tm_a2);
+    const CUtensorMap *tb = prob == 0 ? &tm_b0 : (prob == 1 ? &tm_b1 : &tm_b2);
 
     if (threadIdx.x == 0) {
-        asm volatile("prefetch.tensormap [%0];" :: "l"(&tm_a) : "memory");
-        asm volatile("prefetch.tensormap [%0];" :: "l"(&tm_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(ta) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(tb) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -545,32 +589,27 @@ attn_bgemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < g.num_kb; ++kb) {
+            for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
                 mbar_expect_tx(&full_bar[s], kStage);
                 uint8_t *sa = smem + s * kStage;
-                if (A_MN) {
+                if (a_mn) {
 #pragma unroll
                     for (int j = 0; j < kTile / 32; ++j)
-                        tma_load_3d(sa + j * 4096, &tm_a, &full_bar[s], a_off + m_blk * kTile + j * 32, kb * kChunk, za);
+                        tma_load_3d(sa + j * 4096, ta, &full_bar[s], m_blk * kTile + j * 32, kb * kChunk, z);
                 } else {
-                    tma_load_3d(sa, &tm_a, &full_bar[s], a_off + kb * kChunk, m_blk * kTile, za);
+                    tma_load_3d(sa, ta, &full_bar[s], kb * kChunk, m_blk * kTile, z);
                 }
-                if (B_MN) {
 #pragma unroll
-                    for (int j = 0; j < BLOCK_N / 32; ++j)
-                        tma_load_3d(sa + kTileBytes + j * 4096, &tm_b, &full_bar[s], b_off + n_blk * BLOCK_N + j * 32,
-                                    kb * kChunk, zb);
-                } else {
-                    tma_load_3d(sa + kTileBytes, &tm_b, &full_bar[s], b_off + kb * kChunk, n_blk * BLOCK_N, zb);
-                }
+                for (int j = 0; j < BLOCK_N / 32; ++j)
+                    tma_load_3d(sa + kTileBytes + j * 4096, tb, &full_bar[s], b_off + n_blk * BLOCK_N + j * 32, kb * kChunk, zb);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BLOCK_N, A_MN, B_MN);
-            for (int kb = 0; kb < g.num_kb; ++kb) {
+            const uint32_t idesc = make_idesc(BLOCK_N, a_mn, true);
+            for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 mbar_wait(&full_bar[s], (kb / STAGES) & 1);
                 fence_after();
@@ -578,9 +617,8 @@ attn_bgemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 const uint32_t sb = sa + kTileBytes;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint64_t da = A_MN ? desc_mn_sw128(sa + k * 1024) : desc_k_sw128(sa + k * 32);
-                    const uint64_t db = B_MN ? desc_mn_sw128(sb + k * 1024) : desc_k_sw128(sb + k * 32);
-                    umma_ss(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    const uint64_t da = a_mn ? desc_mn_sw128(sa + k * 1024) : desc_k_sw128(sa + k * 32);
+                    umma_ss(tmem_base, da, desc_mn_sw128(sb + k * 1024), idesc, (kb | k) != 0 ? 1u : 0u);
                 }
                 umma_commit(&empty_bar[s]);
             }
@@ -592,7 +630,10 @@ attn_bgemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         fence_after();
         float *stage_out = reinterpret_cast<float *>(smem) + (warp - 2) * (32 * 36);
         const int sub = lane & 7, rgrp = lane >> 3;
-        float *cbase = g.C + (size_t)(z / g.c_zdiv) * g.c_bs + hz * g.c_hcols;
+        float *cptr = prob == 0 ? g.C[0] : (prob == 1 ? g.C[1] : g.C[2]);
+        const long long c_bs = prob == 0 ? g.c_bs[0] : (prob == 1 ? g.c_bs[1] : g.c_bs[2]);
+        const long long c_ld = prob == 0 ? g.c_ld[0] : (prob == 1 ? g.c_ld[1] : g.c_ld[2]);
+        float *cbase = cptr + (size_t)zb * c_bs + hz * g.N;
         uint32_t r[32];
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
@@ -608,9 +649,9 @@ attn_bgemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             for (int it8 = 0; it8 < 8; ++it8) {
                 const int rr = it8 * 4 + rgrp;
                 const int grow = m_blk * kTile + q4 * 32 + rr;
-                if (grow < g.M && col < g.N) {
+                if (grow < M && col < g.N) {
                     const float4 v = *reinterpret_cast<const float4 *>(stage_out + rr * 36 + sub * 4);
-                    float *dst = cbase + (size_t)grow * g.c_ld + col;
+                    float *dst = cbase + (size_t)grow * c_ld + col;
                     if (g.accumulate) red_add_v4(dst, v);
                     else *reinterpret_cast<float4 *>(dst) = v;
                 }
@@ -665,6 +706,13 @@ inline bool mult4(long long v) { return (v & 3) == 0; }
 
 inline int key_pitch(int Nk) { return (Nk + 31) & ~31; }
 
+// 16-bit dropout threshold (an element is kept when its 16 hash bits are >= it); 0 = no dropout
+inline unsigned thresh16(double p) {
+    if (p <= 0.0) return 0u;
+    unsigned t = (unsigned)(p * 65536.0 + 0.5);
+    return t < 1u ? 1u : (t > 65535u ? 65535u : t);
+}
+
 bool shape_ok(int B, int H, int Tq, int Nk, int D) {
     if (B <= 0 || H <= 0 || Tq <= 0 || Nk <= 0) return false;
     if (!(D == 32 || D == 64 || D == 128 || D == 256)) return false;
@@ -677,29 +725,22 @@ int set_smem(K kern, int bytes) {
     return e == cudaSuccess ? 0 : (int)e;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
-int launch_bgemm(const CUtensorMap &ta, const CUtensorMap &tb, const BgemmArgs &g, int Z, cudaStream_t stream) {
+template <int BLOCK_N>
+int launch_bgemm3(const CUtensorMap *t, const Bgemm3Args &g, cudaStream_t stream) {
     constexpr int smem = 3 * (kTileBytes + BLOCK_N * kChunk * 4) + 7 * 8 + 16 + 1024;
-    auto kern = attn_bgemm_kernel<BLOCK_N, A_MN, B_MN>;
+    auto kern = attn_bgemm3_kernel<BLOCK_N>;
     static bool configured = false;
     if (!configured) {
         int rc = set_smem(kern, smem);
         if (rc) return rc;
         configured = true;
     }
-    dim3 grid((g.N + BLOCK_N - 1) / BLOCK_N, (g.M + kTile - 1) / kTile, Z);
-    kern<<<grid, kThreads, smem, stream>>>(ta, tb, g);
+    int mt = 0;
+    for (int p = 0; p < 3; ++p) mt = (g.M[p] + kTile - 1) / kTile > mt ? (g.M[p] + kTile - 1) / kTile : mt;
+    dim3 grid((g.N + BLOCK_N - 1) / BLOCK_N, mt, 3 * g.Z);
+    kern<<<grid, kThreads, smem, stream>>>(t[0], t[1], t[2], t[3], t[4], t[5], g);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
-}
-
-template <bool A_MN, bool B_MN>
-int dispatch_bgemm(int block_n, const CUtensorMap &ta, const CUtensorMap &tb, const BgemmArgs &g, int Z, cudaStream_t s) {
-    switch (block_n) {
-        case 32: return launch_bgemm<32, A_MN, B_MN>(ta, tb, g, Z, s);
-        case 64: return launch_bgemm<64, A_MN, B_MN>(ta, tb, g, Z, s);
-        default: return launch_bgemm<128, A_MN, B_MN>(ta, tb, g, Z, s);
-    }
 }
 
 }  // namespace
@@ -736,7 +777,7 @@ int rlipv2_attn_forward_tf32(const float *q, long long q_ld, long long q_bs, con
     if (a.stages > total) a.stages = total;
     if (a.stages < 2) return RLIPV2_ATTN_ESHAPE;
     a.scale = scale;
-    a.thresh = dropout_p > 0.0 ? (unsigned)(dropout_p * 4294967296.0) : 0u;
+    a.thresh = thresh16(dropout_p);
     a.inv_keep = dropout_p > 0.0 ? (float)(1.0 / (1.0 - dropout_p)) : 1.f;
     a.salt = salt;
     a.key_bias = key_bias;
@@ -750,7 +791,7 @@ int rlipv2_attn_forward_tf32(const float *q, long long q_ld, long long q_bs, con
     if (rc) return rc;
     rc = make_map3(&tv, v, (uint64_t)H * D, (uint64_t)Nk, (uint64_t)B, (uint64_t)v_ld, (uint64_t)v_bs, 32, true);
     if (rc) return rc;
-    const int smem = a.stages * a.stage_bytes + (2 * a.stages + 3) * 8 + 16 + a.Nk_pad * 4 + 1024;
+    const int smem = a.stages * a.stage_bytes + (2 * a.stages + 3) * 8 + 16 + (2 * kTile + a.Nk_pad) * 4 + 1024;
     static int configured = 0;
     if (smem > configured) {
         rc = set_smem(attn_fwd_kernel, smem);
@@ -758,7 +799,7 @@ int rlipv2_attn_forward_tf32(const float *q, long long q_ld, long long q_bs, con
         configured = smem;
     }
     dim3 grid((Tq + kTile - 1) / kTile, B * H, D / a.dv_tile);
-    attn_fwd_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tq, tk, tv, a);
+    attn_fwd_kernel<<<grid, kThreadsAttn, smem, (cudaStream_t)stream>>>(tq, tk, tv, a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
 }
@@ -788,9 +829,9 @@ int rlipv2_attn_backward_tf32(const float *q, long long q_ld, long long q_bs, co
     {
         DsArgs a;
         a.B = B; a.H = H; a.Tq = Tq; a.Nk = Nk; a.D = D; a.Nk_pad = Nk_pad;
-        a.stages = D / kChunk < 3 ? D / kChunk : 3;
+        a.stages = D / kChunk < 3 ? (D / kChunk < 2 ? 2 : D / kChunk) : 3;     // >= 2: the epilogue stages through the ring
         a.scale = scale;
-        a.thresh = dropout_p > 0.0 ? (unsigned)(dropout_p * 4294967296.0) : 0u;
+        a.thresh = thresh16(dropout_p);
         a.inv_keep = dropout_p > 0.0 ? (float)(1.0 / (1.0 - dropout_p)) : 1.f;
         a.salt = salt;
         a.key_bias = key_bias; a.out = out; a.dout = dout; a.stats = stats;
@@ -814,39 +855,36 @@ int rlipv2_attn_backward_tf32(const float *q, long long q_ld, long long q_bs, co
             configured = smem;
         }
         dim3 grid((Tq + kTile - 1) / kTile, Z, (Nk + kTile - 1) / kTile);
-        attn_bwd_ds_kernel<<<grid, kThreads, smem, s>>>(tq, tk, tg, tv, a);
+        attn_bwd_ds_kernel<<<grid, kThreadsAttn, smem, s>>>(tq, tk, tg, tv, a);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }
     const int block_n = D >= 128 ? 128 : D;
-    CUtensorMap t_ds_k, t_ds_mn, t_p_mn, t_k_mn, t_q_mn, t_do_mn;
-    int rc = make_map3(&t_ds_k, ws_ds, (uint64_t)Nk_pad, (uint64_t)Tq, (uint64_t)Z, (uint64_t)Nk_pad, (uint64_t)Tq * Nk_pad, kTile, false);
+    CUtensorMap t[6];
+    // problem 0: dS K-major, K as stored;  1: dS MN-major, Q as stored;  2: P~ MN-major, dO as stored
+    int rc = make_map3(&t[0], ws_ds, (uint64_t)Nk_pad, (uint64_t)Tq, (uint64_t)Z, (uint64_t)Nk_pad, (uint64_t)Tq * Nk_pad, kTile, false);
     if (rc) return rc;
-    rc = make_map3(&t_ds_mn, ws_ds, (uint64_t)Nk_pad, (uint64_t)Tq, (uint64_t)Z, (uint64_t)Nk_pad, (uint64_t)Tq * Nk_pad, 32, true);
+    rc = make_map3(&t[1], k, HD, (uint64_t)Nk, (uint64_t)B, (uint64_t)k_ld, (uint64_t)k_bs, 32, true);
     if (rc) return rc;
-    rc = make_map3(&t_p_mn, ws_p, (uint64_t)Nk_pad, (uint64_t)Tq, (uint64_t)Z, (uint64_t)Nk_pad, (uint64_t)Tq * Nk_pad, 32, true);
+    rc = make_map3(&t[2], ws_ds, (uint64_t)Nk_pad, (uint64_t)Tq, (uint64_t)Z, (uint64_t)Nk_pad, (uint64_t)Tq * Nk_pad, 32, true);
     if (rc) return rc;
-    rc = make_map3(&t_k_mn, k, HD, (uint64_t)Nk, (uint64_t)B, (uint64_t)k_ld, (uint64_t)k_bs, 32, true);
+    rc = make_map3(&t[3], q, HD, (uint64_t)Tq, (uint64_t)B, (uint64_t)q_ld, (uint64_t)q_bs, 32, true);
     if (rc) return rc;
-    rc = make_map3(&t_q_mn, q, HD, (uint64_t)Tq, (uint64_t)B, (uint64_t)q_ld, (uint64_t)q_bs, 32, true);
+    rc = make_map3(&t[4], ws_p, (uint64_t)Nk_pad, (uint64_t)Tq, (uint64_t)Z, (uint64_t)Nk_pad, (uint64_t)Tq * Nk_pad, 32, true);
     if (rc) return rc;
-    rc = make_map3(&t_do_mn, dout, HD, (uint64_t)Tq, (uint64_t)B, (uint64_t)o_ld, (uint64_t)o_bs, 32, true);
+    rc = make_map3(&t[5], dout, HD, (uint64_t)Tq, (uint64_t)B, (uint64_t)o_ld, (uint64_t)o_bs, 32, true);
     if (rc) return rc;
-    BgemmArgs g;
-    g.H = H; g.N = D; g.accumulate = accumulate;
-    g.a_zdiv = 1; g.a_hcols = 0; g.b_zdiv = H; g.b_hcols = D; g.c_zdiv = H; g.c_hcols = D;
-    // 2. dQ[b, :, h] (+)= dS[bh] . K[b, :, h]          A = dS K-major (contraction = keys), B = K as stored (MN-major)
-    g.M = Tq; g.num_kb = Nk_pad / kChunk; g.C = dq; g.c_ld = dq_ld; g.c_bs = dq_bs;
-    rc = dispatch_bgemm<false, true>(block_n, t_ds_k, t_k_mn, g, Z, s);
-    if (rc) return rc;
-    // 3. dK[b, :, h] (+)= dS[bh]^T . Q[b, :, h]        both operands as stored (contraction = query rows)
-    g.M = Nk; g.num_kb = (Tq + kChunk - 1) / kChunk; g.C = dk; g.c_ld = dk_ld; g.c_bs = dk_bs;
-    rc = dispatch_bgemm<true, true>(block_n, t_ds_mn, t_q_mn, g, Z, s);
-    if (rc) return rc;
-    // 4. dV[b, :, h] (+)= P~[bh]^T . dO[b, :, h]
-    g.C = dv; g.c_ld = dv_ld; g.c_bs = dv_bs;
-    return dispatch_bgemm<true, true>(block_n, t_p_mn, t_do_mn, g, Z, s);
+    Bgemm3Args g;
+    g.H = H; g.N = D; g.Z = Z; g.accumulate = accumulate;
+    g.M[0] = Tq; g.num_kb[0] = Nk_pad / kChunk; g.C[0] = dq; g.c_ld[0] = dq_ld; g.c_bs[0] = dq_bs;
+    g.M[1] = Nk; g.num_kb[1] = (Tq + kChunk - 1) / kChunk; g.C[1] = dk; g.c_ld[1] = dk_ld; g.c_bs[1] = dk_bs;
+    g.M[2] = Nk; g.num_kb[2] = (Tq + kChunk - 1) / kChunk; g.C[2] = dv; g.c_ld[2] = dv_ld; g.c_bs[2] = dv_bs;
+    switch (block_n) {
+        case 32: return launch_bgemm3<32>(t, g, s);
+        case 64: return launch_bgemm3<64>(t, g, s);
+        default: return launch_bgemm3<128>(t, g, s);
+    }
 }
 
 const char *rlipv2_attn_error_string(int code)

@@ -65,3 +65,32 @@ def encoder_inputs(N, shapes, M=8, D=32, P=4, seed=3, noise_px=1.0, device="cuda
     gout = torch.randn(N, S, M * D, generator=g, device=device, dtype=dtype)
     sh, lsi = level_tensors(shapes, device)
     return value, sh, lsi, loc.contiguous(), attn.contiguous(), gout
+
+
+# ---- synthetic train-step inputs (SURVEY.md section 8d recipe).  This module loads none of the C-ABI libraries, so the CPU
+# reference arm of bench.py (oracle/parseda_oracle.py) can build the same batch without touching the product's kernels.
+def synthetic_text(n_obj=170, n_verb=85):
+    """256 label strings: n_obj object names + 'no objects' + n_verb relation names."""
+    objs = [f"object kind {i}" for i in range(n_obj)] + ["no objects"]
+    verbs = [f"relation {i} with" for i in range(n_verb)]
+    return [(objs, verbs)]
+
+
+def synthetic_batch(batch, height=800, width=1333, n_obj=170, n_verb=85, triplets=5, seed=0, pin=True):
+    """Host-side batch: images [B,3,H,W] fp32 + per-image targets (SURVEY.md section 8d recipe)."""
+    g = torch.Generator().manual_seed(seed)
+    images = torch.randn(batch, 3, height, width, generator=g)
+    targets = []
+    for _ in range(batch):
+        def boxes():
+            return torch.cat([torch.rand(triplets, 2, generator=g) * 0.4 + 0.3,
+                              torch.rand(triplets, 2, generator=g) * 0.2 + 0.1], 1)
+        verbs = torch.zeros(triplets, n_verb)
+        verbs[torch.arange(triplets), torch.randint(0, n_verb, (triplets,), generator=g)] = 1
+        targets.append({"obj_labels": torch.randint(0, n_obj, (triplets,), generator=g),
+                        "sub_labels": torch.zeros(triplets, dtype=torch.long), "verb_labels": verbs,
+                        "sub_boxes": boxes(), "obj_boxes": boxes()})
+    if pin and torch.cuda.is_available():
+        images = images.pin_memory()
+        targets = [{k: v.pin_memory() for k, v in t.items()} for t in targets]
+    return images, targets

@@ -133,6 +133,8 @@ def _assert_step(res, tol, loss_rtol, grad_tol, exact_indices=True):
     gold_keys = sorted(k[len("loss_"):] for k in g if k.startswith("loss_"))
     assert sorted(loss_dict.keys()) == gold_keys
     for k, v in loss_dict.items():
+        if not exact_indices and ("class_error" in k or "cardinality_error" in k):
+            continue            # logging metrics built on arg-max counts (hoi.py:3723, 3909-3923): steps of 1 / #targets
         np.testing.assert_allclose(float(v), float(g["loss_" + k]), rtol=loss_rtol, atol=loss_rtol / 10, err_msg=k)
     np.testing.assert_allclose(float(total), float(g["total_loss"]), rtol=loss_rtol)
     # backward: gradient norms and strided samples of selected parameters (vector-relative error: the

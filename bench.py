@@ -206,36 +206,44 @@ def msda_roofline(device):
 
 
 def alif_tensor_roofline(device):
-    """ALIF's dense contractions on the tcgen05 kernel: achieved TF32 FLOP/s of the six projections of one
-    fusion layer (batch 2: Tv = 2x273 rows, Tl = 2x256 rows, E = 2048) vs the tensor peak.  The driver's
-    MEASURED_PEAKS.json holds the dense bf16 figure; TF32 runs at half the bf16 rate on this part
-    (B200_PROFILING.md: 2.25 vs 1.1 PFLOP/s nominal), so peak_tf32 = bf16_tflops / 2."""
-    from rlipv2_b200 import dense_abi
-    shapes = [(546, 2048, 256), (546, 2048, 256), (512, 2048, 768), (512, 2048, 768), (546, 256, 2048), (512, 768, 2048)]
-    ops = []
-    for M_, N_, K_ in shapes:
-        x = torch.randn(M_, K_, device=device)
-        w = torch.randn(N_, K_, device=device) * K_ ** -0.5
-        b = torch.randn(N_, device=device)
-        ops.append((x, w, b))
-    splitk = os.environ.get("RLIPV2_SPLITK_FWD", "0") == "1"          # A/B: split-K forward for the long-K projections
+    """One whole ALIF fusion layer on the tcgen05 kernels (forward, batch 2: Tv = 273 image tokens, Tl = 256 labels,
+    E = 2048 = 8 heads x 256): the six projections (linear_tf32_kernel) AND the bidirectional attention core
+    (attn_fwd_kernel x 2: S = Q K^T in tensor memory, both softmaxes, two P V products) = SURVEY 8d's 4.13 GFLOP per image
+    and layer.  Achieved TF32 FLOP/s vs the tensor peak; the driver's MEASURED_PEAKS.json holds the dense bf16 figure and
+    TF32 runs at half the bf16 rate on this part (B200_PROFILING.md: 2.25 vs 1.1 PFLOP/s nominal): peak_tf32 = bf16 / 2."""
+    from rlipv2_b200 import attn_abi, dense_abi
+    B, Tv, Tl, E, H = BATCH, 273, 256, 2048, 8
+    g = torch.Generator(device=device).manual_seed(0)
+    mk = lambda *s: torch.randn(*s, device=device, generator=g)
+    v, l = mk(B, Tv, 256), mk(B, Tl, 768)
+    W = {n: (mk(o, i) * i ** -0.5, mk(o)) for n, o, i in (("q", E, 256), ("k", E, 768), ("vv", E, 256), ("vl", E, 768),
+                                                       ("ov", 256, E), ("ol", 768, E))}
+    splitk = os.environ.get("RLIPV2_SPLITK_FWD", "1") != "0"
 
-    def one(x, w, b):
-        sp = dense_abi.splitk_splits(x.shape[0], w.shape[0], w.shape[1]) if splitk else 1
-        return dense_abi.linear_splitk_tf32(x, w, b, sp) if sp > 1 else dense_abi.linear_tf32(x, w, b, 0)
+    def lin(x, name):
+        w, b = W[name]
+        x2 = x.reshape(-1, x.shape[-1])
+        sp = dense_abi.splitk_splits(x2.shape[0], w.shape[0], w.shape[1]) if splitk else 1
+        y = dense_abi.linear_splitk_tf32(x2, w, b, sp) if sp > 1 else dense_abi.linear_tf32(x2, w, b, 0)
+        return y.view(*x.shape[:-1], w.shape[0])
 
-    run = lambda: [one(x, w, b) for x, w, b in ops]
+    def layer():
+        q, k, vv, vl = lin(v, "q"), lin(l, "k"), lin(v, "vv"), lin(l, "vl")
+        ov, _, _ = attn_abi.forward(q, k, vl, H, None, 256 ** -0.5, 0.0, None, 0)
+        ol, _, _ = attn_abi.forward(k, q, vv, H, None, 256 ** -0.5, 0.0, None, 1)
+        return lin(ov, "ov"), lin(ol, "ol")
+
     for _ in range(3):
-        run()
+        layer()
     torch.cuda.synchronize()
-    # the kernels take a few us each - less than the python/ctypes launch path - so the six launches are timed the way
-    # the train step issues them: as nodes of a CUDA graph (10 layers' worth per replay)
+    # the kernels take a few us each - less than the python / ctypes launch path - so the layer is timed the way the train
+    # step issues it: as nodes of a CUDA graph (10 layers' worth per replay)
     st = torch.cuda.Stream()
     with torch.cuda.stream(st):
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr, stream=st):
             for _ in range(10):
-                run()
+                layer()
     gr.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -245,7 +253,10 @@ def alif_tensor_roofline(device):
     e1.record()
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1) / 50 * 1e-3
-    flops = sum(2.0 * m * n * k for m, n, k in shapes)
+    proj = sum(2.0 * m * n * k for m, n, k in ((B * Tv, E, 256), (B * Tl, E, 768), (B * Tv, E, 256), (B * Tl, E, 768),
+                                               (B * Tv, 256, E), (B * Tl, 768, E)))
+    attn = 3 * 2.0 * B * Tv * Tl * E                      # S = Q K^T once per direction is counted once + 2 P V
+    flops = proj + attn
     peak = 1590.0 / 2
     src = "fallback (B200_PROFILING.md) / 2"
     try:
@@ -253,14 +264,15 @@ def alif_tensor_roofline(device):
         src = "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 = half the bf16 rate)"
     except Exception:
         pass
-    return {"bound": "tensor", "kernel": "linear_tf32_kernel (tcgen05.mma kind::tf32) on the 6 ALIF projections of one fusion layer, batch 2"
-                                          + (" [split-K gemm_tf32_kernel for K >= 768]" if splitk else ""),
+    return {"bound": "tensor",
+            "kernel": "one ALIF fusion layer forward, batch 2: 6 x linear_tf32_kernel"
+                      + (" / split-K gemm_tf32_kernel for K >= 768" if splitk else "")
+                      + " + 2 x attn_fwd_kernel (tcgen05.mma kind::tf32; scores and probabilities in tensor memory)",
             "achieved": flops / t / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / t / 1e12 / peak, "peak_src": src,
-            "us_per_layer": t * 1e6, "flops_per_layer": flops,
-            "ncu": "sm__pipe_tensor_cycles_active 14.0 % (v_proj, K = 256) .. 27.8 % (l_proj, K = 768) "
-                   "(profiles/dense_r01_final_alif_ncu.txt, dense_r01_v1_alif_ncu.txt); "
-                   "M = 512-546 rows fill 16-64 of 148 SMs: the GEMMs are latency-bound (6-stage TMA ring for these grids)",
-            "timing": "CUDA-graph replay of the 6 launches x 10, CUDA events"}
+            "us_per_layer": t * 1e6, "flops_per_layer": flops, "flops_per_image_layer": flops / B,
+            "ncu": "profiles/attn_r02_ncu.txt, profiles/dense_r01_final_alif_ncu.txt (sm__pipe_tensor_cycles_active per kernel); "
+                   "512-546 row problems fill 16-112 of 148 SMs: latency-bound, not pipe-bound",
+            "timing": "CUDA-graph replay of the 8 launches x 10, CUDA events"}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -49,9 +49,9 @@ _OWN_BWD_MIN_ROWS = int(os.environ.get("RLIPV2_OWN_BWD_MIN_ROWS", "4096"))
 # the side stream; the train step joins it after backward() (`join_param_grad_stream`).
 _LIBRARY_SMALL = os.environ.get("RLIPV2_TEXT_LIBRARY_GEMM", "0") != "0"      # measured r01s4g: 27.6 vs 27.7 ms/step - no gain, off
 _LIBRARY_SMALL_MAX_ROWS = 4096
-# split-K tcgen05 forward for small-M / long-K linears: opt-in until it has its micro-benchmark and step A/B on the B200
-# (written after round 1's GPU budget was spent)
-_SPLITK_FWD = os.environ.get("RLIPV2_SPLITK_FWD", "0") == "1"
+# split-K tcgen05 forward for small-M / long-K linears (ALIF out projections, label-side in-projections, RobertaLayer
+# FFN-down): measured r02a 27.19 vs 27.41 ms/step on one box, tests/test_zz5_splitk_gpu.py green -> on by default
+_SPLITK_FWD = os.environ.get("RLIPV2_SPLITK_FWD", "1") != "0"
 _WGRAD_STREAM = os.environ.get("RLIPV2_WGRAD_STREAM", "1") != "0"
 # (measured r01s4d: every size on the side stream 28.65 vs 29.5 ms/step with only the <= 4096-row problems there)
 _WGRAD_STREAM_MAX_ROWS = int(os.environ.get("RLIPV2_WGRAD_STREAM_MAX_ROWS", str(1 << 30)))

@@ -78,6 +78,10 @@ for name, M, N, K, act in SHAPES:
         dense_abi.set_small_mode(mode)
         rec[f"ours_mode{mode}_us"] = timeit(ours, iters) * 1e6
     dense_abi.set_small_mode(keep)
+    sp = dense_abi.splitk_splits(M, N, K) if act == 0 else 1
+    if sp > 1:                                      # split-K forward (the default for these shapes since round 2)
+        rec["splits"] = sp
+        rec["ours_splitk_us"] = timeit([lambda x=x: dense_abi.linear_splitk_tf32(x, w, b, sp) for x in xs], iters) * 1e6
     t_o, t_r = timeit(ours, iters), timeit(ref, iters)
     rec.update({"ours_us": t_o * 1e6, "cublas_us": t_r * 1e6, "ours_TFLOPs": fl / t_o / 1e12,
                 "cublas_TFLOPs": fl / t_r / 1e12, "ours_GBs": bytes_ / t_o / 1e9, "default_mode": keep})

@@ -29,6 +29,9 @@ class FlatParams:
             off += sum(p.numel() for p in plist)
             ranges.append((start, off, lr))
             off = (off + 3) // 4 * 4
+        # equal, 16-byte aligned shards per rank (sharded optimizer step: reduce-scatter / all-gather in place)
+        unit = 4 * max(1, world_size())
+        off = (off + unit - 1) // unit * unit
         self.flat_param = torch.zeros(off, device=device)
         self.flat_grad = torch.zeros(off, device=device)
         self.exp_avg = torch.zeros(off, device=device) if moments else None
@@ -65,6 +68,50 @@ class FlatParams:
         """the rank SUM of the gradients; `clip_scale` folds the 1 / world of the mean into the optimizer's read"""
         if world_size() > 1:
             dist.all_reduce(self.flat_grad)
+
+    # ---- sharded optimizer step (ZeRO-1 style): every rank reduces, clips and updates 1 / world of the flat buffer --------
+    def shard_range(self):
+        w, n = world_size(), self.flat_grad.numel()
+        r = dist.get_rank() if w > 1 else 0
+        per = n // w
+        return r * per, (r + 1) * per
+
+    def reduce_scatter_sum_(self):
+        """this rank's shard of `flat_grad` <- the rank SUM of that shard (in place; the other shards keep local values).
+        Half the bytes of the all-reduce; the other half is the all-gather of the updated parameters."""
+        if world_size() <= 1:
+            return
+        s0, s1 = self.shard_range()
+        if dist.get_backend() == "nccl":
+            dist.reduce_scatter_tensor(self.flat_grad[s0:s1], self.flat_grad)
+        else:                                   # gloo (CPU tests) has no reduce-scatter: same result through an all-reduce
+            dist.all_reduce(self.flat_grad)
+
+    def all_gather_params_(self):
+        """every rank's updated parameter shard -> all ranks (in place): replicas leave the step bit-identical"""
+        if world_size() <= 1:
+            return
+        s0, s1 = self.shard_range()
+        if dist.get_backend() == "nccl":
+            dist.all_gather_into_tensor(self.flat_param, self.flat_param[s0:s1])
+        else:
+            per = s1 - s0
+            parts = [torch.empty(per, dtype=self.flat_param.dtype) for _ in range(world_size())]
+            dist.all_gather(parts, self.flat_param[s0:s1].clone())
+            self.flat_param.copy_(torch.cat(parts))
+
+    def clip_scale_sharded(self, max_norm):
+        """`clip_scale` when only this rank's shard holds the rank sum: squared norms of the shards are summed across ranks
+        (one scalar all-reduce) - the same global norm, hence the same coefficient on every rank"""
+        w = float(world_size())
+        s0, s1 = self.shard_range()
+        if max_norm > 0:
+            sq = self.flat_grad[s0:s1].square().sum().reshape(1)
+            if w > 1:
+                dist.all_reduce(sq)
+            coef = torch.clamp(max_norm / (sq.sqrt() / w + 1e-6), max=1.0)
+            return (coef / w).reshape(1)
+        return torch.full((1,), 1.0 / w, device=self.flat_grad.device)
 
     def clip_scale(self, max_norm):
         """1-element tensor s such that `flat_grad * s` is what `allreduce_mean_()` + `clip_(max_norm)` would have left

@@ -61,6 +61,22 @@ def _worker(rank, port, q):
         flat.allreduce_sum_()
         g_scaled = flat.flat_grad * flat.clip_scale(0.1)
         g_sum = flat.flat_grad.clone()
+        full_scale = flat.clip_scale(0.1)
+        # the sharded optimizer step: this rank's shard of the sum, the same clip coefficient from shard norms, an update of
+        # the shard only, all-gather of the parameters
+        flat.flat_grad.copy_(local)
+        flat.reduce_scatter_sum_()
+        sh0, sh1 = flat.shard_range()
+        assert (sh1 - sh0) * WORLD == flat.flat_grad.numel() and sh0 % 4 == 0
+        shard_sum_ok = torch.allclose(flat.flat_grad[sh0:sh1], g_sum[sh0:sh1], rtol=1e-6, atol=1e-7)
+        scale_sh = flat.clip_scale_sharded(0.1)
+        p_before = flat.flat_param.clone()
+        flat.flat_param[sh0:sh1] -= 0.5 * scale_sh * flat.flat_grad[sh0:sh1]
+        flat.all_gather_params_()
+        p_sharded = flat.flat_param.clone()
+        p_full = p_before - 0.5 * full_scale * g_sum
+        flat.flat_param.copy_(p_before)
+        sharded = (shard_sum_ok, scale_sh.clone(), full_scale.clone(), p_sharded, p_full)
         # the overlapped variant: ranges all-reduced from gradient-readiness markers inside the backward, the rest after it
         from rlipv2_b200 import grad_ready
         from rlipv2_b200.flat_dp import EarlyReducer
@@ -88,7 +104,7 @@ def _worker(rank, port, q):
         vec = torch.stack([losses[k].detach().reshape(()) for k in keys])
         dist.all_reduce(vec)
         q.put((rank, g_after_reduce, g_after_clip, flat.flat_param.clone(), flat.group_ranges, vec / WORLD, g_scaled,
-               g_sum, g_early))
+               g_sum, g_early, sharded))
     finally:
         dist.destroy_process_group()
 
@@ -127,7 +143,7 @@ def test_two_gloo_ranks():
     torch.nn.functional.mse_loss(ref(x), y).backward()
 
     def flatten(tensors, ranges):
-        out = torch.zeros(res[0][1].numel())
+        out = torch.zeros(res[0][1].numel())             # (includes the tail padding to 4 * world elements)
         groups = _groups(ref)
         for (plist, _), (start, _, _) in zip(groups, ranges):
             o = start
@@ -149,6 +165,11 @@ def test_two_gloo_ranks():
         torch.testing.assert_close(r[2], g_clip, rtol=1e-5, atol=1e-7)
         torch.testing.assert_close(r[6], g_clip, rtol=1e-5, atol=1e-7)      # sum + clip_scale == mean + clip_
         assert torch.equal(r[7], r[8])                   # marker-driven partial all-reduces == the one whole all-reduce
+        ok, scale_sh, scale_full, p_sharded, p_full = r[9]
+        assert ok                                        # reduce-scatter leaves the rank sum in this rank's shard
+        torch.testing.assert_close(scale_sh, scale_full, rtol=1e-6, atol=0)     # same clip coefficient from shard norms
+        torch.testing.assert_close(p_sharded, p_full, rtol=1e-6, atol=1e-7)     # shard updates + all-gather == full update
+    assert torch.equal(res[0][9][3], res[1][9][3])       # and the replicas are bit-identical after the all-gather
     opt = torch.optim.AdamW([{"params": pl, "lr": lr} for pl, lr in _groups(ref)], weight_decay=1e-4)
     opt.step()
     p_ref = flatten([p.data for p in ref.parameters()], ranges)

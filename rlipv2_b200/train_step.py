@@ -139,6 +139,7 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         super().__init__(*a, **kw)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.captured = False
+        self._prefetched = False
         # measured neutral on 1xB200 (37.2 vs 37.0 ms/step): inside a graph the ~600 accumulation kernels cost about what
         # the gather + the copies of non-stealable gradients cost.  Kept behind the switch.
         self.gather_grads = os.environ.get("RLIPV2_GATHER_GRADS", "0") == "1"
@@ -297,7 +298,7 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         """shard = (s0, s1): update only that range of the flat buffers (this rank's part of a sharded step)"""
         from . import fused_abi
         self.step_t.add_(1.0)
-        skip = self.d_err if (self.flag_wait and not self.device_lsap) else None
+        skip = self.d_err                       # non-zero: host-flag timeout, or the dry warm-up of a later shape's capture
         for gi, (start, end, lr) in enumerate(self.group_ranges):
             if shard is not None:
                 start, end = max(start, shard[0]), min(end, shard[1])
@@ -345,12 +346,44 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
             from . import lsap_abi
             lsap_abi.check(self.lsap_plan)
             return
-        if self.captured and self.flag_wait and int(self.d_err.item()) != 0:
+        if self.captured and self.flag_wait and int(self.d_err.item()) > 0:
             raise RuntimeError(f"backward graph replay {int(self.d_err.item())} timed out waiting for the host assignment")
 
-    def capture(self, images_host, targets_host, text, warmup=3):
+    # attributes that belong to ONE captured shape (image size, triplet counts, label-token shape); `capture` of another
+    # shape replaces them, `activate` swaps a saved set back in (BucketedParSeDATrainStep)
+    SHAPE_STATE = ("s_tok", "s_samples", "s_targets", "sizes", "h_cost", "ks", "h_I", "h_J", "s_I", "s_J", "np_cost", "np_I",
+                   "np_J", "lsap_plan", "h_flag", "np_flag", "d_seq", "flag_seq", "graph_a", "graph_b", "s_loss", "_keep",
+                   "done_a", "own_launches_per_step", "h_ids", "h_am", "_tok_copied", "_copy_stream", "p_images", "p_targets",
+                   "_staging_free", "_prefetch_done", "_prefetched", "last_cost")
+
+    def shape_state(self):
+        return {k: getattr(self, k) for k in self.SHAPE_STATE if hasattr(self, k)}
+
+    def activate(self, state):
+        for k in self.SHAPE_STATE:
+            if k in state:
+                setattr(self, k, state[k])
+            elif hasattr(self, k):
+                delattr(self, k)
+        self._prefetched = bool(state.get("_prefetched", False))
+
+    def capture(self, images_host, targets_host, text, warmup=3, graphs=True):
+        """Static buffers + (graphs=True) the two CUDA graphs for this batch shape.  The first call also runs the probe step
+        and moves the parameters into the flat buffers; later calls (other shapes) leave the training state untouched: their
+        warm-up and priming steps run with the optimizer update disabled.  graphs=False: buffers only - `replay()` then runs
+        the same three pieces eagerly (rare shapes that are not worth a capture)."""
         dev = self.device
-        self.s_tok = self.module.transformer.tokenize(text, dev)
+        first = getattr(self, "flat", None) is None
+        for k in ("h_ids", "h_am", "_tok_copied", "_copy_stream", "p_images", "p_targets", "_staging_free", "_prefetch_done",
+                  "graph_a", "graph_b", "lsap_plan", "last_cost"):
+            if hasattr(self, k):
+                delattr(self, k)                # staging / graphs of the previously active shape
+        self._prefetched = False
+        if isinstance(text, dict):              # already tokenised (host or device tensors)
+            self.s_tok = {"input_ids": text["input_ids"].to(dev).clone(), "attention_mask": text["attention_mask"].to(dev).clone(),
+                          "sums": [tuple(x) for x in text["sums"]]}
+        else:
+            self.s_tok = self.module.transformer.tokenize(text, dev)
         self.s_samples, self.s_targets = self.to_device(images_host, targets_host)
         self.sizes = [len(t["obj_labels"]) for t in targets_host]
         nq = self.args.num_queries // 2
@@ -369,7 +402,9 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         self.h_flag = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.np_flag = self.h_flag.numpy()
         self.d_seq = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.d_err = torch.zeros(1, dtype=torch.int32, device=dev)
+        if first:
+            # error word of the host-flag wait = "skip the update" word of the AdamW kernel (shared by every shape's graphs)
+            self.d_err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.flag_seq = 0
         if os.environ.get("RLIPV2_STAMPS", "0") == "1":
             self.stamps = torch.zeros(8, dtype=torch.int64, device=dev)
@@ -378,8 +413,31 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         # One stream for the probe, the warm-up and both captures: autograd runs every backward node
         # (AccumulateGrad included) on the stream its forward op first ran on, so all of them must be
         # the capture stream - never the legacy default stream.
-        side = self.cap_stream = torch.cuda.Stream()
+        if first:
+            self.cap_stream = torch.cuda.Stream()
+        side = self.cap_stream
         side.wait_stream(torch.cuda.current_stream())
+        if first:
+            self._setup_flat(side)
+        self.graph_a = self.graph_b = None
+        if not graphs:
+            return self
+        # warm-up / priming steps of a LATER shape must not train: the AdamW kernels see a non-zero skip word and return, the
+        # step counter is put back afterwards (gradients are re-zeroed by every step anyway)
+        dry = (not first) or getattr(self, "dry_captures", False)
+        if dry:
+            step_keep = self.step_t.clone()
+            self.d_err.fill_(-1)
+        self._capture_graphs(side, warmup)
+        if dry:
+            torch.cuda.synchronize()
+            self.d_err.zero_()
+            self.step_t.copy_(step_keep)
+        self.check()
+        return self
+
+    def _setup_flat(self, side):
+        dev = self.device
         # 1. one eager step to learn which parameters receive gradients
         for p in self.module.parameters():
             p.grad = None
@@ -430,6 +488,8 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
             for p in self.module.parameters():
                 if id(p) not in used_ids:
                     dist.broadcast(p.data, 0)
+
+    def _capture_graphs(self, side, warmup):
         # 3. warm-up on a side stream (cuBLAS/cuDNN workspaces, lazy inits), then capture
         # (with the flag wait, the last warm-up step is the priming replay below: `warmup` optimizer steps either way)
         n_eager = max(1, warmup - 1) if self.flag_wait else warmup
@@ -468,7 +528,6 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
             self.np_flag[0] = self.flag_seq
             self.graph_b.replay()
             torch.cuda.synchronize()
-            self.check()
 
     def _forward_and_costs_eager_probe(self):
         outputs, giou = self._forward_and_costs()
@@ -481,6 +540,17 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
 
     def replay(self):
         """One step on the batch currently held by the static buffers."""
+        if self.graph_a is None:                # shape without graphs (capture(graphs=False)): the same pieces, eagerly
+            cur = torch.cuda.current_stream(self.device)
+            self.cap_stream.wait_stream(cur)
+            with torch.cuda.stream(self.cap_stream):
+                outputs, giou = self._forward_and_costs()
+                if not self.device_lsap:
+                    self.cap_stream.synchronize()
+                    self._solve_assignment()
+                loss = self._loss_backward_step(outputs, giou)
+            cur.wait_stream(self.cap_stream)
+            return loss
         self.graph_a.replay()
         if self.device_lsap:
             self.graph_b.replay()               # the indices are already in s_I / s_J when graph A ends
@@ -570,13 +640,98 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         self._tok_copied = torch.cuda.Event()
         self._tok_copied.record()
 
-    def step(self, images_host, targets_host, text=None):
+    def prefetch(self, images_host, targets_host):
+        """Start the host->device copy of the NEXT batch on a copy stream, into staging buffers, while the current step still
+        runs (the reference's DataLoader + `.to(device)` pipeline, engine.py:88-90, as a double buffer).  The following
+        `step()` without a batch consumes it: a device-to-device copy into the graphs' static buffers, then the replay."""
+        dev = self.device
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+            self.p_images = torch.empty_like(self.s_samples.tensors)
+            self.p_targets = [{k: torch.empty_like(v) for k, v in t.items()} for t in self.s_targets]
+            self._staging_free = None
+        if self._staging_free is not None:
+            self._copy_stream.wait_event(self._staging_free)        # the previous consumer has read the staging buffers
+        with torch.cuda.stream(self._copy_stream):
+            self.p_images.copy_(images_host, non_blocking=True)
+            for st, ht in zip(self.p_targets, targets_host):
+                for k in st:
+                    st[k].copy_(ht[k], non_blocking=True)
+            self._prefetch_done = torch.cuda.Event()
+            self._prefetch_done.record(self._copy_stream)
+        self._prefetched = True
+
+    def step(self, images_host=None, targets_host=None, text=None):
         """H2D of a new batch (same shapes as at capture) + one replayed step.  `text`: the batch's label strings (or a
-        `tokenize()` dict); None keeps the label set of the previous step."""
+        `tokenize()` dict); None keeps the label set of the previous step.  Without a batch, the one handed to `prefetch()`
+        is used (its copy has been running beside the previous step)."""
         if text is not None:
             self.update_text(text)
+        if images_host is None:
+            assert getattr(self, "_prefetched", False), "step() without a batch needs a preceding prefetch()"
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(self._prefetch_done)
+            self.s_samples.tensors.copy_(self.p_images, non_blocking=True)
+            for st, pt in zip(self.s_targets, self.p_targets):
+                for k in st:
+                    st[k].copy_(pt[k], non_blocking=True)
+            self._staging_free = torch.cuda.Event()
+            self._staging_free.record(cur)
+            self._prefetched = False
+            return self.replay()
         self.s_samples.tensors.copy_(images_host, non_blocking=True)
         for st, ht in zip(self.s_targets, targets_host):
             for k in st:
                 st[k].copy_(ht[k], non_blocking=True)
         return self.replay()
+
+
+class BucketedParSeDATrainStep(GraphedParSeDATrainStep):
+    """The graphed step for batches whose SHAPE changes from step to step, as the reference's `train_one_epoch` produces
+    them (engine.py:68-172: multi-scale resize -> another padded image size per batch, another number of annotated triplets
+    per image, engine.py:700-757 `merge_batch_data` -> another label set).  A CUDA graph is bound to one shape, so this
+    class keeps a small set of captured shapes:
+
+      key = (padded image shape, triplets per image, label-set sizes, token-matrix width)
+      * a shape seen for the `capture_after`-th time is captured (at most `max_shapes` live captures, least recently used
+        evicted); the capture's warm-up does not train (GraphedParSeDATrainStep.capture, dry mode);
+      * any other shape runs the SAME step eagerly on static buffers of its own (no padding to a bucket: ALIF lets padded
+        image cells take part in its softmaxes - SURVEY quirk 1 - so a larger padded size would change the result).
+    Parameters, gradients and AdamW state are the one flat buffer set of the first capture; every shape's graphs update it.
+    """
+
+    def __init__(self, *a, max_shapes=8, capture_after=2, **kw):
+        super().__init__(*a, **kw)
+        self.max_shapes, self.capture_after = int(max_shapes), int(capture_after)
+        self.dry_captures = True                # no capture trains: exactly one optimizer step per step() call
+        self._shapes, self._seen, self._clock = {}, {}, 0
+        self.stats = {"graph_steps": 0, "eager_steps": 0, "captures": 0, "evictions": 0}
+
+    def _key(self, images_host, targets_host, tok):
+        return (tuple(images_host.shape), tuple(len(t["obj_labels"]) for t in targets_host),
+                tuple(tuple(x) for x in tok["sums"]), tuple(tok["input_ids"].shape))
+
+    def step(self, images_host, targets_host, text):
+        tok = text if isinstance(text, dict) else self.module.transformer.tokenize(text, "cpu")
+        key = self._key(images_host, targets_host, tok)
+        self._clock += 1
+        self._seen[key] = self._seen.get(key, 0) + 1
+        entry = self._shapes.get(key)
+        want_graphs = self._seen[key] >= self.capture_after or getattr(self, "flat", None) is None
+        if entry is None or (want_graphs and not entry["graphs"]):
+            if want_graphs:
+                live = [k for k, e in self._shapes.items() if e["graphs"] and k != key]
+                if len(live) >= self.max_shapes:
+                    victim = min(live, key=lambda k: self._shapes[k]["used"])
+                    del self._shapes[victim]                      # its graphs, pools and static buffers go with it
+                    self.stats["evictions"] += 1
+            self.capture(images_host, targets_host, tok, warmup=2, graphs=want_graphs)
+            self.stats["captures"] += int(want_graphs)
+            entry = self._shapes[key] = {"state": self.shape_state(), "graphs": want_graphs, "used": self._clock}
+        else:
+            self.activate(entry["state"])
+        entry["used"] = self._clock
+        self.stats["graph_steps" if entry["graphs"] else "eager_steps"] += 1
+        loss = GraphedParSeDATrainStep.step(self, images_host, targets_host, text=tok)
+        entry["state"] = self.shape_state()
+        return loss

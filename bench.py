@@ -323,9 +323,9 @@ def run_train_step(args, rank, world, device):
             # every step, inside the timed region); the label strings are tokenised on the host and copied every step like the
             # reference does (dab_deformable/deformable_transformer.py:497); the loss is read back (4 bytes D2H)
             if not ts._prefetched:
-                ts.prefetch(images_h, targets_h)
-            loss_dev = ts.step(text=text)
-            ts.prefetch(images_h, targets_h)                # next step's batch: copies while this step computes
+                ts.prefetch(images_h, targets_h, text)
+            loss_dev = ts.step()
+            ts.prefetch(images_h, targets_h, text)          # next step's batch + label tokens: staged while this step computes
             float(loss_dev)
     else:
         ts = train_step.ParSeDATrainStep(args=model_args, device=str(device), precision=args.precision, seed=0)
@@ -449,6 +449,9 @@ def main():
     ap.add_argument("--no-graphs", dest="graphs", action="store_false", help="eager step instead of CUDA graphs")
     args = ap.parse_args()
     rank, world, local = dist_info()
+    if os.environ.get("RLIPV2_BENCH_FAULT_S"):          # diagnostics: dump every thread's stack and exit if the run hangs
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["RLIPV2_BENCH_FAULT_S"]), exit=True)
 
     if args.impl == "reference":
         if rank != 0:

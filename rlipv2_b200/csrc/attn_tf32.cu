@@ -386,6 +386,7 @@ attn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     uint64_t *acc_full = empty_bar + a.stages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
     float *kb = reinterpret_cast<float *>(tmem_slot + 4);                 // [128]: log2e * key bias of this key chunk
+    float *dl = kb + kTile;                                               // [128]: delta of this query tile's rows
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, bh = blockIdx.y, kc = blockIdx.z;
@@ -454,20 +455,31 @@ attn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const int half = (warp - 2) >> 2;                                // key columns [64 * half, 64 * half + 64) of the chunk
         const int row0 = qt * kTile + q4 * 32;
         const int grow = row0 + lane;
-        // delta[row] = <dO[row], O[row]> over the head's D columns (= sum_j P~ dP~): one coalesced pass per row
-        float delta = 0.f;
-        for (int rr = 0; rr < 32; ++rr) {
-            const int row = row0 + rr;
-            float acc = 0.f;
-            if (row < a.Tq) {
+        // delta[row] = <dO[row], O[row]> over the head's D columns (= sum_j P~ dP~).  The two warps of a lane quadrant take 16
+        // of its 32 rows each, four rows per round with all of their (coalesced) loads in flight before the reductions; the
+        // results meet in shared memory.
+        for (int r0 = half * 16; r0 < half * 16 + 16; r0 += 4) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int row = row0 + r0 + u;
                 const float *po = a.out + (size_t)b * a.o_bs + (size_t)row * a.o_ld + col_base;
                 const float *pg = a.dout + (size_t)b * a.o_bs + (size_t)row * a.o_ld + col_base;
-                for (int d = lane; d < a.D; d += 32) acc = fmaf(__ldg(po + d), __ldg(pg + d), acc);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int d = lane + 32 * i;
+                    if (d < a.D && row < a.Tq) acc[u] = fmaf(__ldg(po + d), __ldg(pg + d), acc[u]);
+                }
             }
 #pragma unroll
-            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == rr) delta = acc;
+            for (int o = 16; o; o >>= 1) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+            }
+            if (lane < 4) dl[q4 * 32 + r0 + lane] = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
         }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float delta = dl[q4 * 32 + lane];
         float m2 = 0.f, inv_l = 1.f;
         if (grow < a.Tq) {
             const float2 st = __ldg(reinterpret_cast<const float2 *>(a.stats) + ((size_t)bh * a.Tq + grow));
@@ -847,7 +859,7 @@ int rlipv2_attn_backward_tf32(const float *q, long long q_ld, long long q_bs, co
         if (rc) return rc;
         rc = make_map3(&tv, v, HD, (uint64_t)Nk, (uint64_t)B, (uint64_t)v_ld, (uint64_t)v_bs, kTile, false);
         if (rc) return rc;
-        const int smem = a.stages * 4 * kTileBytes + (2 * a.stages + 1) * 8 + 16 + 128 * 4 + 1024;
+        const int smem = a.stages * 4 * kTileBytes + (2 * a.stages + 1) * 8 + 16 + 2 * 128 * 4 + 1024;
         static int configured = 0;
         if (smem > configured) {
             rc = set_smem(attn_bwd_ds_kernel, smem);

@@ -353,7 +353,8 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
     # shape replaces them, `activate` swaps a saved set back in (BucketedParSeDATrainStep)
     SHAPE_STATE = ("s_tok", "s_samples", "s_targets", "sizes", "h_cost", "ks", "h_I", "h_J", "s_I", "s_J", "np_cost", "np_I",
                    "np_J", "lsap_plan", "h_flag", "np_flag", "d_seq", "flag_seq", "graph_a", "graph_b", "s_loss", "_keep",
-                   "done_a", "own_launches_per_step", "h_ids", "h_am", "_tok_copied", "_copy_stream", "p_images", "p_targets",
+                   "done_a", "own_launches_per_step", "h_ids", "h_am", "_tok_copied", "_copy_stream", "p_images", "p_targets", "p_tok",
+                   "_p_has_text",
                    "_staging_free", "_prefetch_done", "_prefetched", "last_cost")
 
     def shape_state(self):
@@ -374,7 +375,7 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         the same three pieces eagerly (rare shapes that are not worth a capture)."""
         dev = self.device
         first = getattr(self, "flat", None) is None
-        for k in ("h_ids", "h_am", "_tok_copied", "_copy_stream", "p_images", "p_targets", "_staging_free", "_prefetch_done",
+        for k in ("h_ids", "h_am", "_tok_copied", "_copy_stream", "p_images", "p_targets", "p_tok", "_p_has_text", "_staging_free", "_prefetch_done",
                   "graph_a", "graph_b", "lsap_plan", "last_cost"):
             if hasattr(self, k):
                 delattr(self, k)                # staging / graphs of the previously active shape
@@ -609,16 +610,17 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         The captured graph holds the token ids in static buffers: same tuple sizes and a token width of at most the captured
         one are copied in (shorter rows padded with the pad id, attention 0 - the tower masks them); anything else needs a
         re-capture and raises."""
+        ids, am, sums = self._tokenize_host(text)
+        self._fill_token_staging(ids, am, sums)
+        s_ids, s_am = self.s_tok["input_ids"], self.s_tok["attention_mask"]
+        s_ids.copy_(self.h_ids, non_blocking=True)
+        s_am.copy_(self.h_am, non_blocking=True)
+        self._tok_copied = torch.cuda.Event()
+        self._tok_copied.record()
+
+    def _fill_token_staging(self, ids, am, sums):
+        """token ids / attention mask -> the pinned staging pair (padded to the captured width); raises when they do not fit"""
         tr = self.module.transformer
-        if isinstance(text, dict):
-            ids, am, sums = text["input_ids"], text["attention_mask"], text["sums"]
-        else:
-            sums, flat = [], []
-            for obj_names, pred_names in text:
-                sums.append((len(obj_names), len(pred_names)))
-                flat += list(obj_names) + list(pred_names)
-            tok = tr.tokenizer.batch_encode_plus(flat, padding="longest", return_tensors="pt")
-            ids, am = tok["input_ids"], tok["attention_mask"]
         s_ids, s_am = self.s_tok["input_ids"], self.s_tok["attention_mask"]
         if [tuple(x) for x in sums] != [tuple(x) for x in self.s_tok["sums"]]:
             raise ValueError(f"label-set sizes {sums} differ from the captured {self.s_tok['sums']}: re-capture")
@@ -630,26 +632,39 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
             self.h_ids = torch.empty(s_ids.shape, dtype=s_ids.dtype).pin_memory()
             self.h_am = torch.empty(s_am.shape, dtype=s_am.dtype).pin_memory()
         if getattr(self, "_tok_copied", None) is not None:
-            self._tok_copied.synchronize()           # the previous step's H2D of these pinned buffers has been consumed
+            self._tok_copied.synchronize()           # the previous H2D of these pinned buffers has been consumed
         self.h_ids.fill_(self._pad_id)
         self.h_am.zero_()
         self.h_ids[:, :ids.shape[1]].copy_(ids)
         self.h_am[:, :am.shape[1]].copy_(am)
-        s_ids.copy_(self.h_ids, non_blocking=True)
-        s_am.copy_(self.h_am, non_blocking=True)
-        self._tok_copied = torch.cuda.Event()
-        self._tok_copied.record()
 
-    def prefetch(self, images_host, targets_host):
+    def _tokenize_host(self, text):
+        if isinstance(text, dict):
+            return text["input_ids"], text["attention_mask"], text["sums"]
+        sums, flat = [], []
+        for obj_names, pred_names in text:
+            sums.append((len(obj_names), len(pred_names)))
+            flat += list(obj_names) + list(pred_names)
+        tok = self.module.transformer.tokenizer.batch_encode_plus(flat, padding="longest", return_tensors="pt")
+        return tok["input_ids"], tok["attention_mask"], sums
+
+    def prefetch(self, images_host, targets_host, text=None):
         """Start the host->device copy of the NEXT batch on a copy stream, into staging buffers, while the current step still
-        runs (the reference's DataLoader + `.to(device)` pipeline, engine.py:88-90, as a double buffer).  The following
-        `step()` without a batch consumes it: a device-to-device copy into the graphs' static buffers, then the replay."""
+        runs (the reference's DataLoader + `.to(device)` pipeline, engine.py:88-90, as a double buffer); `text`: the next
+        batch's label strings, tokenised here on the host (while the GPU works) and staged the same way.  The following
+        `step()` without a batch consumes it: device-to-device copies into the graphs' static buffers, then the replay."""
         dev = self.device
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(dev)
             self.p_images = torch.empty_like(self.s_samples.tensors)
             self.p_targets = [{k: torch.empty_like(v) for k, v in t.items()} for t in self.s_targets]
+            self.p_tok = None
             self._staging_free = None
+        self._p_has_text = text is not None
+        if text is not None:
+            self._fill_token_staging(*self._tokenize_host(text))
+            if self.p_tok is None:
+                self.p_tok = (torch.empty_like(self.s_tok["input_ids"]), torch.empty_like(self.s_tok["attention_mask"]))
         if self._staging_free is not None:
             self._copy_stream.wait_event(self._staging_free)        # the previous consumer has read the staging buffers
         with torch.cuda.stream(self._copy_stream):
@@ -657,6 +672,11 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
             for st, ht in zip(self.p_targets, targets_host):
                 for k in st:
                     st[k].copy_(ht[k], non_blocking=True)
+            if text is not None:
+                self.p_tok[0].copy_(self.h_ids, non_blocking=True)
+                self.p_tok[1].copy_(self.h_am, non_blocking=True)
+                self._tok_copied = torch.cuda.Event()
+                self._tok_copied.record(self._copy_stream)
             self._prefetch_done = torch.cuda.Event()
             self._prefetch_done.record(self._copy_stream)
         self._prefetched = True
@@ -675,6 +695,9 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
             for st, pt in zip(self.s_targets, self.p_targets):
                 for k in st:
                     st[k].copy_(pt[k], non_blocking=True)
+            if getattr(self, "_p_has_text", False):
+                self.s_tok["input_ids"].copy_(self.p_tok[0], non_blocking=True)
+                self.s_tok["attention_mask"].copy_(self.p_tok[1], non_blocking=True)
             self._staging_free = torch.cuda.Event()
             self._staging_free.record(cur)
             self._prefetched = False

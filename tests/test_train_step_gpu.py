@@ -86,8 +86,8 @@ def test_graphed_step_follows_lr_text_and_checkpoint():
         # double-buffered input: prefetch() + step() without a batch == step(batch)
         imgs3, tg3 = train_step.synthetic_batch(2, 160, 192, n_obj=6, n_verb=4, triplets=3, seed=5)
         ts.set_lr(0.0)                                        # frozen parameters: both paths see the same model
-        l_direct = float(ts.step(imgs3, tg3))
-        ts.prefetch(imgs3, tg3)
+        l_direct = float(ts.step(imgs3, tg3, [(objs, verbs)]))
+        ts.prefetch(imgs3, tg3, [(objs, verbs)])              # batch and its label strings staged on the copy stream
         l_pref = float(ts.step())
         assert abs(l_direct - l_pref) <= 1e-5 * abs(l_direct), (l_direct, l_pref)
         ts.set_lr([1.41e-4, 1.41e-5, 1.41e-5])

@@ -122,6 +122,17 @@ int rlipv2_msda_proj_ref4_backward_f32(const float *value, const int64_t *spatia
                                        float *grad_value, float *grad_proj, void *stream);
 
 /* Human-readable text for a return code of the functions above (static storage). */
+/* Experimental forward variant with north_star's literal design: the cells of the two coarsest levels of one (image, head) -
+ * the cell range [coarse_start, spatial_size), coarse_start = level_start_index[num_levels - 2] passed as a HOST integer -
+ * are staged in shared memory by TMA (cp.async.bulk.tensor 3-D boxes) and sampled from there; levels 0 / 1 are gathered from
+ * global memory.  Same arguments / result as rlipv2_msda_forward_f32 (fp32, D = 32, L = 4, P = 4 only;
+ * RLIPV2_MSDA_ESHAPE when the coarse levels exceed one SM's shared memory).  Measured slower than the default kernel
+ * (profiles/msda_r02.md); kept for the comparison. */
+int rlipv2_msda_forward_tma_f32(const float *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                                const float *sampling_loc, const float *attn_weight, int batch, int spatial_size,
+                                int num_heads, int channels, int num_levels, int num_query, int num_point,
+                                int coarse_start, float *out, void *stream);
+
 const char *rlipv2_msda_error_string(int code);
 
 /* RLIPV2_MSDA_ABI_VERSION the library was built with. */

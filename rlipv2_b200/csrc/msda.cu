@@ -31,6 +31,7 @@
 //    (forward) or one warp per pair (backward); kept for API completeness (gradcheck shapes).
 //
 // No CPU fallback exists on purpose.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -444,6 +445,123 @@ msda_bwd_d32_l4p4(const float *__restrict__ value, const int64_t *__restrict__ s
                              scaleH, prep[warp], Q, live, n, S, M, m);
 }
 
+
+// ---- experimental: coarse levels staged in shared memory by TMA (north_star's literal design) ------------------------------
+// One CTA = (block of queries, head m, image n), 1024 threads.  The cells of levels 2 and 3 of (n, m) - one contiguous
+// cell range [coarse_start, S) of `value`, 128 bytes per cell at a 1 KB stride - are fetched by 3-D TMA boxes
+// (32 channels x 1 head x 64 cells) into a dense [cells][32] shared-memory tile; the sampling loop then reads the corners of
+// levels 2 / 3 from the tile (LDS.128) and those of levels 0 / 1 from global memory as before.  Measured against the default
+// kernel in profiles/msda_r02.md: the gather is bound by L1 / shared-memory data-pipe wavefronts, which a corner read costs
+// on either path, while the 170 KB tile takes the L1 capacity away from levels 0 / 1 - kept as a documented variant.
+constexpr int kTmaThreads = 1024;
+constexpr int kTmaBoxCells = 64;
+
+__device__ __forceinline__ uint32_t smem_addr_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__global__ void __launch_bounds__(kTmaThreads, 1)
+msda_fwd_tma_d32_l4p4(const __grid_constant__ CUtensorMap tm_v, const float *__restrict__ value,
+                      const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
+                      const float *__restrict__ loc, const float *__restrict__ attn, int Lq, int S, int M, int qb,
+                      int coarse_start, int tile_cells, float *__restrict__ out)
+{
+    extern __shared__ __align__(128) uint8_t tma_smem[];
+    float *tile = reinterpret_cast<float *>(tma_smem);                               // [tile_cells][32]
+    uint4 *prep = reinterpret_cast<uint4 *>(tma_smem + (size_t)tile_cells * 128);    // [32 warps][64]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(prep + 32 * 4 * kFastLP);
+    __shared__ LevelRow lvl_tab[kFastL];
+    const int m = blockIdx.y, n = blockIdx.z;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr_u32(bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    load_level_table(lvl_tab, shapes, lsi, (uint32_t)M * kFastD);                    // (__syncthreads inside)
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                     :: "r"(smem_addr_u32(bar)), "r"((uint32_t)tile_cells * 128u) : "memory");
+        for (int i = 0; i < tile_cells / kTmaBoxCells; ++i)
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                :: "r"(smem_addr_u32(tile + (size_t)i * kTmaBoxCells * 32)), "l"(&tm_v), "r"(smem_addr_u32(bar)), "r"(0), "r"(m),
+                   "r"(n * S + coarse_start + i * kTmaBoxCells) : "memory");
+    }
+    const WarpCtx c = make_ctx(lvl_tab, M);
+    const LevelRow my = lvl_tab[c.sub >> 1];
+    const int warp = threadIdx.x >> 5;
+    uint4 *mine = prep + warp * (4 * kFastLP);
+    const bool coarse_lane = (c.sub >> 1) >= 2;                                      // this lane prepares points of level 2 / 3
+    {   // wait for the tile
+        uint32_t done = 0;
+        for (uint32_t spins = 0; !done; ++spins) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(done) : "r"(smem_addr_u32(bar)), "r"(0) : "memory");
+            if (spins > (1u << 24)) __trap();
+        }
+    }
+    const int q_end = min(Lq, (int)(blockIdx.x + 1) * qb);
+    const float *vbase = value + c.sub * 4;
+    const float *tbase = tile + c.sub * 4;
+    const uint32_t rs2s = (uint32_t)lvl_tab[2].W * kFastD, rs3s = (uint32_t)lvl_tab[3].W * kFastD;
+    for (int q0 = blockIdx.x * qb + warp * 4; q0 < q_end; q0 += (kTmaThreads / 32) * 4) {
+        const int q = q0 + c.grp;
+        const bool live = q < q_end;
+        const int Q = n * Lq + (live ? q : q0);
+        const size_t pair = (size_t)Q * M + m;
+        float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 a2 = make_float2(0.f, 0.f);
+        if (live) {
+            l4 = ldg_f4(loc + pair * (kFastLP * 2) + c.sub * 4);
+            a2 = __ldg(reinterpret_cast<const float2 *>(attn + pair * kFastLP + c.sub * 2));
+        }
+        // global element offset (levels 0 / 1) or tile element offset (levels 2 / 3) of the level's first cell
+        const uint32_t cell0 = coarse_lane ? (my.start - (uint32_t)coarse_start) * kFastD
+                                           : ((uint32_t)n * (uint32_t)S + my.start) * c.MD + (uint32_t)m * kFastD;
+        const uint32_t md = coarse_lane ? (uint32_t)kFastD : c.MD;
+        mine[c.grp * kFastLP + c.sub * 2 + 0] = pack_point(l4.x, l4.y, a2.x, my.H, my.W, cell0, md);
+        mine[c.grp * kFastLP + c.sub * 2 + 1] = pack_point(l4.z, l4.w, a2.y, my.H, my.W, cell0, md);
+        __syncwarp();
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < kFastLP; ++p) {
+            const uint4 pt = mine[c.grp * kFastLP + p];
+            const bool sm = p >= 8;                                                  // compile-time after unrolling
+            const uint32_t rs = (p < 4) ? c.rs0 : (p < 8) ? c.rs1 : (p < 12) ? rs2s : rs3s;
+            const uint32_t bits = pt.x & 15u, base = pt.x & ~31u;
+            const uint32_t dx = ((bits & 12u) == 12u) ? (sm ? (uint32_t)kFastD : c.MD) : 0u;
+            const uint32_t dy = ((bits & 3u) == 3u) ? rs : 0u;
+            float4 v1, v2, v3, v4;
+            if (sm) {
+                v1 = *reinterpret_cast<const float4 *>(tbase + base);
+                v2 = *reinterpret_cast<const float4 *>(tbase + base + dx);
+                v3 = *reinterpret_cast<const float4 *>(tbase + base + dy);
+                v4 = *reinterpret_cast<const float4 *>(tbase + base + dy + dx);
+            } else {
+                v1 = ldg_f4(vbase + base);
+                v2 = ldg_f4(vbase + base + dx);
+                v3 = ldg_f4(vbase + base + dy);
+                v4 = ldg_f4(vbase + base + dy + dx);
+            }
+            const float lh = __uint_as_float(pt.y), lw = __uint_as_float(pt.z);
+            const float a = __uint_as_float(pt.w);
+            const float ha = (bits & 1u) ? (1.f - lh) * a : 0.f;
+            const float la = (bits & 2u) ? lh * a : 0.f;
+            const float hw = (bits & 4u) ? 1.f - lw : 0.f;
+            const float lwv = (bits & 8u) ? lw : 0.f;
+            const float w1 = ha * hw, w2 = ha * lwv, w3 = la * hw, w4 = la * lwv;
+            acc.x = fmaf(w1, v1.x, acc.x); acc.y = fmaf(w1, v1.y, acc.y);
+            acc.z = fmaf(w1, v1.z, acc.z); acc.w = fmaf(w1, v1.w, acc.w);
+            acc.x = fmaf(w2, v2.x, acc.x); acc.y = fmaf(w2, v2.y, acc.y);
+            acc.z = fmaf(w2, v2.z, acc.z); acc.w = fmaf(w2, v2.w, acc.w);
+            acc.x = fmaf(w3, v3.x, acc.x); acc.y = fmaf(w3, v3.y, acc.y);
+            acc.z = fmaf(w3, v3.z, acc.z); acc.w = fmaf(w3, v3.w, acc.w);
+            acc.x = fmaf(w4, v4.x, acc.x); acc.y = fmaf(w4, v4.y, acc.y);
+            acc.z = fmaf(w4, v4.z, acc.z); acc.w = fmaf(w4, v4.w, acc.w);
+        }
+        if (live)
+            *reinterpret_cast<float4 *>(out + pair * kFastD + c.sub * 4) = acc;
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Generic path: any channels / levels / points, float or double.
 // ---------------------------------------------------------------------------------------------
@@ -788,6 +906,61 @@ int rlipv2_msda_proj_ref4_backward_f32(const float *value, const int64_t *spatia
     return proj_backward_impl(value, spatial_shapes, level_start_index, reference_boxes, proj, grad_out,
                               batch, spatial_size, num_heads, channels, num_levels, num_query, num_point,
                               grad_value, grad_proj, (cudaStream_t)stream, 4);
+}
+
+int rlipv2_msda_forward_tma_f32(const float *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                                const float *sampling_loc, const float *attn_weight, int batch, int spatial_size,
+                                int num_heads, int channels, int num_levels, int num_query, int num_point,
+                                int coarse_start, float *out, void *stream)
+{
+    if (bad_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point)) return RLIPV2_MSDA_EINVAL;
+    if (!fast_ok(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point)) return RLIPV2_MSDA_ESHAPE;
+    if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !out) return RLIPV2_MSDA_EINVAL;
+    if (!aligned16(value, sampling_loc, attn_weight, out)) return RLIPV2_MSDA_EALIGN;
+    if (coarse_start <= 0 || coarse_start >= spatial_size) return RLIPV2_MSDA_EINVAL;
+    const int tile_cells = (spatial_size - coarse_start + kTmaBoxCells - 1) / kTmaBoxCells * kTmaBoxCells;
+    const size_t smem = (size_t)tile_cells * 128 + 32 * 4 * kFastLP * sizeof(uint4) + 16;
+    if (smem > 220 * 1024) return RLIPV2_MSDA_ESHAPE;          // coarse levels too large for one SM's shared memory
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiledFn enc = nullptr;
+    if (!enc) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return RLIPV2_MSDA_EINVAL;
+        enc = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    // value [N*S cells][M heads][32 channels]: box = 64 cells x 1 head x 32 channels, dense rows of 128 B in shared memory
+    CUtensorMap tm;
+    cuuint64_t dims[3] = {(cuuint64_t)kFastD, (cuuint64_t)num_heads, (cuuint64_t)batch * spatial_size};
+    cuuint64_t strides[2] = {(cuuint64_t)kFastD * 4, (cuuint64_t)num_heads * kFastD * 4};
+    cuuint32_t box[3] = {(cuuint32_t)kFastD, 1, (cuuint32_t)kTmaBoxCells};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(value), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return RLIPV2_MSDA_EINVAL;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(msda_fwd_tma_d32_l4p4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem;
+    }
+    // four waves of 148 CTAs over (query blocks, heads, images)
+    int blocks = (4 * 148) / (num_heads * batch);
+    if (blocks < 1) blocks = 1;
+    int qb = (num_query + blocks - 1) / blocks;
+    qb = (qb + 3) / 4 * 4;
+    blocks = (num_query + qb - 1) / qb;
+    dim3 grid((unsigned)blocks, (unsigned)num_heads, (unsigned)batch);
+    msda_fwd_tma_d32_l4p4<<<grid, kTmaThreads, smem, (cudaStream_t)stream>>>(tm, value, spatial_shapes, level_start_index,
+                                                                             sampling_loc, attn_weight, num_query, spatial_size,
+                                                                             num_heads, qb, coarse_start, tile_cells, out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
 }
 
 int rlipv2_msda_forward_f32(const float *value, const int64_t *spatial_shapes,

@@ -32,6 +32,8 @@ _lib.rlipv2_msda_proj_forward_f32.argtypes = [_p] * 5 + _DIMS + [_p, _p]
 _lib.rlipv2_msda_proj_backward_f32.argtypes = [_p] * 6 + _DIMS + [_p] * 3
 _lib.rlipv2_msda_proj_ref4_forward_f32.argtypes = [_p] * 5 + _DIMS + [_p, _p]
 _lib.rlipv2_msda_proj_ref4_backward_f32.argtypes = [_p] * 6 + _DIMS + [_p] * 3
+_lib.rlipv2_msda_forward_tma_f32.argtypes = [_p] * 5 + _DIMS + [_i, _p, _p]
+_lib.rlipv2_msda_forward_tma_f32.restype = _i
 for _f in ("forward_f32", "forward_f64", "backward_f32", "backward_f64", "proj_forward_f32", "proj_backward_f32",
            "proj_ref4_forward_f32", "proj_ref4_backward_f32"):
     getattr(_lib, "rlipv2_msda_" + _f).restype = _i
@@ -46,7 +48,7 @@ if _lib.rlipv2_msda_abi_version() != ABI_VERSION:
 EXPORTS = ("rlipv2_msda_forward_f32", "rlipv2_msda_forward_f64", "rlipv2_msda_backward_f32",
            "rlipv2_msda_backward_f64", "rlipv2_msda_proj_forward_f32", "rlipv2_msda_proj_backward_f32",
            "rlipv2_msda_proj_ref4_forward_f32", "rlipv2_msda_proj_ref4_backward_f32",
-           "rlipv2_msda_error_string", "rlipv2_msda_abi_version", "rlipv2_msda_launch_count")
+           "rlipv2_msda_forward_tma_f32", "rlipv2_msda_error_string", "rlipv2_msda_abi_version", "rlipv2_msda_launch_count")
 
 
 def library_path():
@@ -76,6 +78,20 @@ def forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
                   sampling_loc.data_ptr(), attn_weight.data_ptr(), N, S, M, D, L, Lq, P,
                   out.data_ptr(), _stream())
     _check(code, "ms_deform_attn_forward")
+
+
+def forward_tma(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, coarse_start):
+    """Experimental forward with the two coarsest levels staged in shared memory by TMA (include/rlipv2_msda.h);
+    coarse_start = level_start_index[-2] as a host int.  fp32, D = 32, L = 4, P = 4 only."""
+    N, S, M, D = value.shape
+    Lq, L, P = sampling_loc.shape[1], sampling_loc.shape[3], sampling_loc.shape[4]
+    out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        code = _lib.rlipv2_msda_forward_tma_f32(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                                                sampling_loc.data_ptr(), attn_weight.data_ptr(), N, S, M, D, L, Lq, P,
+                                                int(coarse_start), out.data_ptr(), _stream())
+    _check(code, "rlipv2_msda_forward_tma_f32")
+    return out
 
 
 def backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,

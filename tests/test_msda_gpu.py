@@ -225,3 +225,20 @@ def test_misaligned_views_take_the_generic_kernel():
         torch.testing.assert_close(gv2, gv, rtol=1e-4, atol=1e-6)
         torch.testing.assert_close(gl2, gl, rtol=1e-3, atol=1e-5)
         torch.testing.assert_close(ga2, ga, rtol=1e-4, atol=1e-6)
+
+
+def test_tma_staged_variant_equals_the_default_kernel():
+    """north_star's literal design (coarse levels staged in shared memory by TMA, rlipv2_msda_forward_tma_f32) against the
+    default forward: same gather, same arithmetic per corner -> equal up to the order of the 64 fused multiply-adds."""
+    from rlipv2_b200 import msda_abi, synth
+    for shapes, N in ((synth.LEVELS_800x1333, 2), ([(31, 40), (16, 20), (8, 10), (4, 5)], 3)):
+        value, sh, lsi, loc, attn, _ = synth.encoder_inputs(N, shapes, seed=11)
+        coarse = sum(h * w for h, w in shapes[:2])
+        ref = _msda().ms_deform_attn_forward(value, sh, lsi, loc, attn, 64)
+        out = msda_abi.forward_tma(value, sh, lsi, loc, attn, coarse)
+        torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
+    value, sh, lsi, loc, attn, _ = synth.random_inputs(2, 301, synth.LEVELS_MICRO, seed=3)      # out-of-range samples, ragged tail
+    loc = loc * 1.4 - 0.2
+    ref = _msda().ms_deform_attn_forward(value, sh, lsi, loc, attn, 64)
+    out = msda_abi.forward_tma(value, sh, lsi, loc, attn, 100 * 100 + 50 * 50)
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-6)

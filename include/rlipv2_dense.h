@@ -75,6 +75,13 @@ int rlipv2_dense_linear_splitk_tf32(const float *x, const float *w, const float 
 void rlipv2_dense_set_small_mode(int mode);
 int rlipv2_dense_get_small_mode(void);
 
+/* Large grids: linears with more than `tiles` 128 x 128 output tiles run the PERSISTENT kernel (one CTA per SM walks the
+ * tiles, TMA ring across tile boundaries, accumulator double-buffered in tensor memory so that a tile's epilogue overlaps the
+ * next tile's main loop); 0 = never.  The encoder's 44 446-row linears have thousands of tiles of only 8 k-blocks each.
+ * Results are identical to the one-tile-per-CTA kernel (same products, same accumulation order per output). */
+void rlipv2_dense_set_persistent_min_tiles(int tiles);
+int rlipv2_dense_get_persistent_min_tiles(void);
+
 const char *rlipv2_dense_error_string(int code);
 
 /* kernels launched by this library in this process (for bench.py's gpu_launches) */

@@ -35,6 +35,8 @@ std::atomic<unsigned long long> g_launches{0};
 // 1 = grids of at most one CTA per SM run a 6-stage ring (1 CTA/SM); 2 = additionally 128x64 tiles with an 8-stage ring
 // while that keeps the grid within one CTA per SM
 std::atomic<int> g_small_mode{2};
+// grids of more than this many 128 x 128 tiles run the persistent kernel (0 = never); rlipv2_dense_set_persistent_min_tiles
+std::atomic<int> g_persistent_min_tiles{0};
 constexpr int kNumSMs = 148;
 
 constexpr int kBlockM = 128;
@@ -465,6 +467,162 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent variant of linear_tf32_kernel for large grids (the encoder's 44k-row linears: thousands of 128 x 128
+// tiles with only 8 k-blocks each at K = 256).  One CTA per SM walks tiles b, b + G, b + 2G, ... (n fastest, so that
+// CTAs running at the same time share the rows of x in L2); the TMA ring runs on across tile boundaries and the
+// accumulator is double-buffered in tensor memory (2 x 128 columns): while the epilogue warps drain tile i, the
+// producer / MMA warps are already on tile i + 1.  The one-tile-per-CTA kernel pays barrier init, TMEM allocation,
+// pipeline fill and an un-overlapped epilogue per tile - more than the 8 k-blocks of math themselves.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive_plain(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+template <int STAGES, int ACT>
+__global__ void __launch_bounds__(kThreads, 1)
+linear_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                              const float *__restrict__ bias, const uint8_t *__restrict__ rowmask, float *__restrict__ C,
+                              int M, int N, int K)
+{
+    constexpr int BLOCK_N = 128;
+    using L = SmemLayout<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float *stage_all = reinterpret_cast<float *>(smem + STAGES * L::kStageBytes);          // 4 warps x 32 x 36 floats
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(stage_all + 4 * 32 * 36);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tmem_full = empty_bar + STAGES;          // [2]
+    uint64_t *tmem_empty = tmem_full + 2;              // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_k = K / kBlockK;
+    const int n_tiles = N / BLOCK_N;
+    const int num_tiles = n_tiles * ((M + kBlockM - 1) / kBlockM);
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tm_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tm_b) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(2 * BLOCK_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                   // ---- TMA producer: the ring does not stop at tile boundaries
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&full_bar[s], L::kStageBytes);
+                    uint8_t *sa = smem + s * L::kStageBytes;
+                    tma_load_2d(sa, &tm_a, &full_bar[s], kb * kBlockK, m_blk * kBlockM);
+                    tma_load_2d(sa + L::kABytes, &tm_b, &full_bar[s], kb * kBlockK, n_blk * BLOCK_N);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                   // ---- MMA issuer
+            constexpr uint32_t idesc = make_idesc<BLOCK_N>();
+            uint32_t it = 0, local = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+                const uint32_t acc = local & 1;
+                mbar_wait(&tmem_empty[acc], ((local >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tacc = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(smem + s * L::kStageBytes);
+                    const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                        umma_tf32(tacc, umma_desc_k_sw128(sa + k * kUmmaK * 4), umma_desc_k_sw128(sb + k * kUmmaK * 4), idesc,
+                                  (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tmem_full[acc]);
+            }
+        }
+    } else {                                               // ---- epilogue warps 2..5
+        const int q = warp & 3;
+        float *stage_out = stage_all + (warp - 2) * (32 * 36);
+        const int sub = lane & 7, rgrp = lane >> 3;
+        uint32_t local = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+            const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+            const uint32_t acc = local & 1;
+            mbar_wait(&tmem_full[acc], (local >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const size_t col0 = (size_t)n_blk * BLOCK_N;
+            const float *brow = bias ? bias + col0 : nullptr;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                           __uint_as_float(r[j + 3]));
+                    if (brow) {
+                        const float4 b = __ldg(reinterpret_cast<const float4 *>(brow + c * 32 + j));
+                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                    }
+                    if (ACT == RLIPV2_DENSE_ACT_RELU) {
+                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                    } else if (ACT == RLIPV2_DENSE_ACT_GELU) {
+                        o.x = gelu_exact(o.x); o.y = gelu_exact(o.y); o.z = gelu_exact(o.z); o.w = gelu_exact(o.w);
+                    }
+                    *reinterpret_cast<float4 *>(stage_out + lane * 36 + j) = o;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int it8 = 0; it8 < 8; ++it8) {
+                    const int rr = it8 * 4 + rgrp;
+                    const float4 v = *reinterpret_cast<const float4 *>(stage_out + rr * 36 + sub * 4);
+                    const int grow = m_blk * kBlockM + q * 32 + rr;
+                    if (grow < M) {
+                        const float4 o = (rowmask && rowmask[grow]) ? make_float4(0.f, 0.f, 0.f, 0.f) : v;
+                        *reinterpret_cast<float4 *>(C + (size_t)grow * N + col0 + c * 32 + sub * 4) = o;
+                    }
+                }
+                __syncwarp();
+            }
+            // this thread's TMEM reads of the accumulator are complete (wait::ld above): hand it back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive_plain(&tmem_empty[acc]);
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(2 * BLOCK_N) : "memory");
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -509,6 +667,26 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tb, const float *bias, cons
         configured = true;
     }
     dim3 grid(N / BLOCK_N, (M + kBlockM - 1) / kBlockM, 1);
+    kern<<<grid, kThreads, smem, stream>>>(ta, tb, bias, rowmask, y, M, N, K);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+template <int ACT>
+int launch_persistent(const CUtensorMap &ta, const CUtensorMap &tb, const float *bias, const uint8_t *rowmask, float *y, int M,
+                      int N, int K, cudaStream_t stream) {
+    constexpr int STAGES = 6;
+    using L = SmemLayout<128>;
+    constexpr int smem = STAGES * L::kStageBytes + 4 * 32 * 36 * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
+    auto kern = linear_tf32_persistent_kernel<STAGES, ACT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    const long long tiles = (long long)(N / 128) * ((M + kBlockM - 1) / kBlockM);
+    const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
     kern<<<grid, kThreads, smem, stream>>>(ta, tb, bias, rowmask, y, M, N, K);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
@@ -642,6 +820,14 @@ int rlipv2_dense_linear_tf32_rowmask(const float *x, const float *w, const float
     rc = make_map(&tb, w, (uint64_t)N, (uint64_t)K, cfg == 2 ? 64 : 128);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
+    const int pmin = g_persistent_min_tiles.load(std::memory_order_relaxed);
+    if (pmin > 0 && ctas128 > pmin) {
+        switch (act) {
+            case RLIPV2_DENSE_ACT_NONE: return launch_persistent<RLIPV2_DENSE_ACT_NONE>(ta, tb, bias, rowmask, y, M, N, K, s);
+            case RLIPV2_DENSE_ACT_RELU: return launch_persistent<RLIPV2_DENSE_ACT_RELU>(ta, tb, bias, rowmask, y, M, N, K, s);
+            default: return launch_persistent<RLIPV2_DENSE_ACT_GELU>(ta, tb, bias, rowmask, y, M, N, K, s);
+        }
+    }
 #define RLIPV2_DISPATCH_ACT(BN, ST)                                                                              \
     switch (act) {                                                                                               \
         case RLIPV2_DENSE_ACT_NONE: return launch<BN, ST, RLIPV2_DENSE_ACT_NONE>(ta, tb, bias, rowmask, y, M, N, K, s); \
@@ -657,6 +843,10 @@ int rlipv2_dense_linear_tf32_rowmask(const float *x, const float *w, const float
 void rlipv2_dense_set_small_mode(int mode) { g_small_mode.store(mode < 0 ? 0 : (mode > 2 ? 2 : mode), std::memory_order_relaxed); }
 
 int rlipv2_dense_get_small_mode(void) { return g_small_mode.load(std::memory_order_relaxed); }
+
+void rlipv2_dense_set_persistent_min_tiles(int tiles) { g_persistent_min_tiles.store(tiles < 0 ? 0 : tiles, std::memory_order_relaxed); }
+
+int rlipv2_dense_get_persistent_min_tiles(void) { return g_persistent_min_tiles.load(std::memory_order_relaxed); }
 
 int rlipv2_dense_linear_tf32(const float *x, const float *w, const float *bias, float *y, int M, int N, int K,
                              int act, void *stream)

@@ -29,13 +29,28 @@ _lib.rlipv2_dense_launch_count.restype = ctypes.c_ulonglong
 _lib.rlipv2_dense_set_small_mode.argtypes = [_i]
 _lib.rlipv2_dense_set_small_mode.restype = None
 _lib.rlipv2_dense_get_small_mode.restype = _i
+_lib.rlipv2_dense_set_persistent_min_tiles.argtypes = [_i]
+_lib.rlipv2_dense_set_persistent_min_tiles.restype = None
+_lib.rlipv2_dense_get_persistent_min_tiles.restype = _i
+# persistent kernel for grids above this many tiles (A/B switch: RLIPV2_DENSE_PERSISTENT=0 turns it off)
+_lib.rlipv2_dense_set_persistent_min_tiles(int(os.environ.get("RLIPV2_DENSE_PERSISTENT", "0")))
 if os.environ.get("RLIPV2_DENSE_SMALL_MODE"):                      # A/B switch for measurements
     _lib.rlipv2_dense_set_small_mode(int(os.environ["RLIPV2_DENSE_SMALL_MODE"]))
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 EXPORTS = ("rlipv2_dense_linear_tf32", "rlipv2_dense_linear_tf32_rowmask", "rlipv2_dense_linear_tf32_supported", "rlipv2_dense_wgrad_tf32",
            "rlipv2_dense_dgrad_tf32", "rlipv2_dense_error_string", "rlipv2_dense_launch_count",
-           "rlipv2_dense_set_small_mode", "rlipv2_dense_get_small_mode", "rlipv2_dense_linear_splitk_tf32")
+           "rlipv2_dense_set_small_mode", "rlipv2_dense_get_small_mode", "rlipv2_dense_linear_splitk_tf32",
+           "rlipv2_dense_set_persistent_min_tiles", "rlipv2_dense_get_persistent_min_tiles")
+
+
+def set_persistent_min_tiles(tiles):
+    """linears with more than `tiles` 128 x 128 output tiles run the persistent kernel; 0 = never (include/rlipv2_dense.h)"""
+    _lib.rlipv2_dense_set_persistent_min_tiles(int(tiles))
+
+
+def persistent_min_tiles():
+    return int(_lib.rlipv2_dense_get_persistent_min_tiles())
 
 
 def set_small_mode(mode):

@@ -420,6 +420,11 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         side.wait_stream(torch.cuda.current_stream())
         if first:
             self._setup_flat(side)
+            # the flat buffers, the learning-rate vector and the step counter were filled on the CURRENT stream; everything
+            # below runs on `side` (a non-blocking stream: no implicit ordering with the default stream).  Without this wait
+            # the first warm-up AdamW could read the learning rates before their copy had landed (seen once as NaN costs in a
+            # full-suite run, r02h).
+            side.wait_stream(torch.cuda.current_stream())
         self.graph_a = self.graph_b = None
         if not graphs:
             return self

@@ -278,3 +278,31 @@ def test_fused_gradient_accumulation_into_flat_views(T, mode):
         assert float((flat_r - 1).abs().max()) > 1                          # the gradients are not trivially zero
     finally:
         dense.set_matmul_precision("fp32")
+
+
+@pytest.mark.parametrize("M,N,K,act,mask", [(44446, 2048, 256, 1, False), (44446, 256, 2048, 0, False), (3001, 128, 256, 0, True),
+                                            (20000, 384, 256, 2, False), (777, 1024, 64, 0, False)])
+def test_persistent_kernel_is_bit_identical(M, N, K, act, mask):
+    """the persistent tcgen05 linear (one CTA per SM walking the tiles, double-buffered TMEM accumulator) issues the same MMAs
+    per tile as the one-tile-per-CTA kernel: identical bits, any tile count (more / fewer tiles than SMs, ragged last rows)"""
+    from rlipv2_b200 import dense_abi
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    x = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) * K ** -0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    rm = (torch.rand(M, device="cuda", generator=g) < 0.1) if mask else None
+    keep = dense_abi.persistent_min_tiles()
+    try:
+        dense_abi.set_persistent_min_tiles(0)
+        ref = dense_abi.linear_tf32(x, w, b, act, rm)
+        dense_abi.set_persistent_min_tiles(1)
+        assert dense_abi.persistent_min_tiles() == 1
+        out = dense_abi.linear_tf32(x, w, b, act, rm)
+        out2 = dense_abi.linear_tf32(x, w, b, act, rm)
+    finally:
+        dense_abi.set_persistent_min_tiles(keep)
+    assert torch.equal(out, ref) and torch.equal(out2, ref)
+    r64, bound = _ref(x, w, b, act)
+    if rm is not None:
+        r64 = r64.masked_fill(rm[:, None], 0.0)
+    assert bool(((out.double() - r64).abs() <= 1.5e-3 * bound + 1e-5).all())

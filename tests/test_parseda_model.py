@@ -150,7 +150,11 @@ def _assert_step(res, tol, loss_rtol, grad_tol, exact_indices=True):
         ref = g["grad_" + k].astype(np.float64)
         worst[k] = (abs(float(gk.norm()) - ref_norm) / (ref_norm + 1e-12),
                     float(np.linalg.norm(sample - ref) / (np.linalg.norm(ref) + 1e-12)))
-    bad = {k: v for k, v in worst.items() if v[0] > grad_tol[0] or v[1] > grad_tol[1]}
+    # ALIF's VXAc gate uses gamma[0] only (fuse_helper.py:720-721): that parameter's gradient is ONE sum of ~4e5 signed terms;
+    # under TF32 products it moves by up to 10 % from run to run (measured r02d-r02h: 2 % / 5.7 % / 10.3 %), under fp32 / 3xTF32
+    # it sits within the common tolerance
+    loose = lambda k: 3.0 if (not exact_indices and ".gamma_" in k) else 1.0
+    bad = {k: v for k, v in worst.items() if v[0] > grad_tol[0] * loose(k) or v[1] > grad_tol[1] * loose(k)}
     assert not bad, f"gradient mismatch (norm rel err, sample rel err): {bad}"
 
 

@@ -82,6 +82,13 @@ for name, M, N, K, act in SHAPES:
     if sp > 1:                                      # split-K forward (the default for these shapes since round 2)
         rec["splits"] = sp
         rec["ours_splitk_us"] = timeit([lambda x=x: dense_abi.linear_splitk_tf32(x, w, b, sp) for x in xs], iters) * 1e6
+    if (N // 128) * ((M + 127) // 128) > 296:      # large grids: the persistent kernel (double-buffered TMEM accumulator)
+        keep_p = dense_abi.persistent_min_tiles()
+        dense_abi.set_persistent_min_tiles(296)
+        rec["ours_persistent_us"] = timeit(ours, iters) * 1e6
+        dense_abi.set_persistent_min_tiles(0)
+        t_o = timeit(ours, iters)
+        dense_abi.set_persistent_min_tiles(keep_p)
     t_o, t_r = timeit(ours, iters), timeit(ref, iters)
     rec.update({"ours_us": t_o * 1e6, "cublas_us": t_r * 1e6, "ours_TFLOPs": fl / t_o / 1e12,
                 "cublas_TFLOPs": fl / t_r / 1e12, "ours_GBs": bytes_ / t_o / 1e9, "default_mode": keep})

@@ -625,6 +625,178 @@ linear_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent input-gradient GEMM with the ReLU gate:  dx[T, N] = (mask > 0) ? g[T, Kc] . w[Kc, N] : 0  and per-row-tile column
+// sums of the gated dx (EPI_MASK of gemm_tf32_kernel) - the encoder FFN's `gh = (g W2) * (h > 0)`, `db1 = colsum(gh)`:
+// T = 44 446, N = 2048, Kc = 256, 364 MB of gate in and 364 MB of gradient out per call.  Same schedule as
+// linear_tf32_persistent_kernel (one CTA per SM, 128 x 256 tiles, TMA ring across tiles, double-buffered TMEM accumulator);
+// A = g K-major, B = w as stored (MN-major 32 x 32 boxes).
+// ---------------------------------------------------------------------------------------------------------------
+template <int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+dgrad_mask_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                             float *__restrict__ C, const float *__restrict__ mask, float *__restrict__ colsum,
+                             int M, int N, int num_kb)
+{
+    constexpr int BLOCK_N = 256;
+    using L = SmemLayout<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float *stage_all = reinterpret_cast<float *>(smem + STAGES * L::kStageBytes);          // 4 warps x 32 x 36 floats
+    float *col_part = stage_all + 4 * 32 * 36;                                             // [4 warps][BLOCK_N]
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(col_part + 4 * BLOCK_N);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tmem_full = empty_bar + STAGES;
+    uint64_t *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+    const int num_tiles = n_tiles * ((M + kBlockM - 1) / kBlockM);
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tm_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tm_b) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(2 * BLOCK_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&full_bar[s], L::kStageBytes);
+                    uint8_t *sa = smem + s * L::kStageBytes;
+                    tma_load_2d(sa, &tm_a, &full_bar[s], kb * kBlockK, m_blk * kBlockM);
+#pragma unroll
+                    for (int j = 0; j < BLOCK_N / 32; ++j)
+                        tma_load_2d(sa + L::kABytes + j * 4096, &tm_b, &full_bar[s], n_blk * BLOCK_N + j * 32, kb * kBlockK);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_major<BLOCK_N, false, true>();
+            uint32_t it = 0, local = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+                const uint32_t acc = local & 1;
+                mbar_wait(&tmem_empty[acc], ((local >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tacc = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(smem + s * L::kStageBytes);
+                    const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                        umma_tf32(tacc, umma_desc_k_sw128(sa + k * kUmmaK * 4), umma_desc_mn_sw128(sb + k * 1024), idesc,
+                                  (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tmem_full[acc]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        float *stage_out = stage_all + (warp - 2) * (32 * 36);
+        const int sub = lane & 7, rgrp = lane >> 3;
+        uint32_t local = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+            const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+            const uint32_t acc = local & 1;
+            const size_t col0 = (size_t)n_blk * BLOCK_N;
+            float4 mk[8];
+            auto fetch_mask = [&](int c) {                 // the 8 gate vectors this lane needs for a 32-column chunk
+#pragma unroll
+                for (int it8 = 0; it8 < 8; ++it8) {
+                    const int grow = m_blk * kBlockM + q * 32 + it8 * 4 + rgrp;
+                    const size_t col = col0 + c * 32 + sub * 4;
+                    mk[it8] = (grow < M && col < (size_t)N) ? __ldg(reinterpret_cast<const float4 *>(mask + (size_t)grow * N + col))
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            fetch_mask(0);                                 // in flight while the accumulator completes
+            mbar_wait(&tmem_full[acc], (local >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4 *>(stage_out + lane * 36 + j) =
+                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                    __uint_as_float(r[j + 3]));
+                __syncwarp();
+                const size_t col = col0 + c * 32 + sub * 4;
+                float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int it8 = 0; it8 < 8; ++it8) {
+                    const int rr = it8 * 4 + rgrp;
+                    float4 v = *reinterpret_cast<const float4 *>(stage_out + rr * 36 + sub * 4);
+                    const int grow = m_blk * kBlockM + q * 32 + rr;
+                    if (grow < M && col < (size_t)N) {
+                        v.x = mk[it8].x > 0.f ? v.x : 0.f; v.y = mk[it8].y > 0.f ? v.y : 0.f;
+                        v.z = mk[it8].z > 0.f ? v.z : 0.f; v.w = mk[it8].w > 0.f ? v.w : 0.f;
+                        csum.x += v.x; csum.y += v.y; csum.z += v.z; csum.w += v.w;
+                        *reinterpret_cast<float4 *>(C + (size_t)grow * N + col) = v;
+                    }
+                }
+#pragma unroll
+                for (int o = 8; o < 32; o <<= 1) {
+                    csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o); csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
+                    csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o); csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
+                }
+                if (rgrp == 0)
+                    *reinterpret_cast<float4 *>(col_part + (warp - 2) * BLOCK_N + c * 32 + sub * 4) = csum;
+                if (c + 1 < BLOCK_N / 32) fetch_mask(c + 1);
+                __syncwarp();
+            }
+            // the accumulator has been read: hand it back before the column sums are finished
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive_plain(&tmem_empty[acc]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int t = threadIdx.x - 64;
+            for (int cc = t; cc < BLOCK_N; cc += 128) {
+                const float v = col_part[cc] + col_part[BLOCK_N + cc] + col_part[2 * BLOCK_N + cc] + col_part[3 * BLOCK_N + cc];
+                if (col0 + cc < (size_t)N) colsum[(size_t)m_blk * N + col0 + cc] = v;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");     // col_part is rewritten by the next tile
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(2 * BLOCK_N) : "memory");
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -773,6 +945,31 @@ int rlipv2_dense_dgrad_tf32(const float *g, const float *w, float *dx, const flo
     if (!aligned16(g) || !aligned16(w) || !aligned16(dx) || !aligned16(relu_out) || !aligned16(colsum)) return RLIPV2_DENSE_EALIGN;
     if ((relu_out == nullptr) != (colsum == nullptr)) return RLIPV2_DENSE_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
+    const int pmin = g_persistent_min_tiles.load(std::memory_order_relaxed);
+    if (relu_out && pmin > 0 && (K % 256) == 0 && (long long)(K / 128) * ((T + kBlockM - 1) / kBlockM) > pmin) {
+        // large gated input gradient (encoder FFN): persistent 128 x 256 tiles.  NB the colsum layout is the same
+        // [ceil(T/128), K] as the one-tile-per-CTA kernel's.
+        constexpr int STAGES = 4;
+        using L = SmemLayout<256>;
+        constexpr int smem = STAGES * L::kStageBytes + 4 * 32 * 36 * 4 + 4 * 256 * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
+        CUtensorMap ta, tb;
+        int rc = make_map_box(&ta, g, (uint64_t)T, (uint64_t)N, kBlockM, kBlockK, false);
+        if (rc) return rc;
+        rc = make_map_box(&tb, w, (uint64_t)N, (uint64_t)K, 32, 32, true);
+        if (rc) return rc;
+        auto kern = dgrad_mask_persistent_kernel<STAGES>;
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return (int)e;
+            configured = true;
+        }
+        const long long tiles = (long long)(K / 256) * ((T + kBlockM - 1) / kBlockM);
+        const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+        kern<<<grid, kThreads, smem, s>>>(ta, tb, dx, relu_out, colsum, T, K, (N + kBlockK - 1) / kBlockK);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return (int)cudaGetLastError();
+    }
     if (relu_out)
         return launch_gemm<128, false, true, EPI_MASK>(g, w, dx, relu_out, colsum, T, K, N, 1, s);
     return launch_gemm<128, false, true, EPI_STORE>(g, w, dx, nullptr, nullptr, T, K, N, 1, s);

@@ -306,3 +306,29 @@ def test_persistent_kernel_is_bit_identical(M, N, K, act, mask):
     if rm is not None:
         r64 = r64.masked_fill(rm[:, None], 0.0)
     assert bool(((out.double() - r64).abs() <= 1.5e-3 * bound + 1e-5).all())
+
+
+@pytest.mark.parametrize("T,N,K", [(44446, 256, 2048), (5000, 96, 512), (1000, 256, 256)])
+def test_persistent_gated_dgrad_is_bit_identical(T, N, K):
+    """dgrad_mask_persistent_kernel (128 x 256 tiles, one CTA per SM) against the one-tile-per-CTA EPI_MASK kernel: the gated
+    input gradient and the per-row-tile column sums, bit for bit; and both against fp64"""
+    from rlipv2_b200 import dense_abi
+    g = torch.Generator(device="cuda").manual_seed(T + K)
+    gy = torch.randn(T, N, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) * N ** -0.5
+    h = torch.relu(torch.randn(T, K, device="cuda", generator=g))
+    keep = dense_abi.persistent_min_tiles()
+    try:
+        dense_abi.set_persistent_min_tiles(0)
+        dx0, cs0 = dense_abi.dgrad_tf32(gy, w, h)
+        dense_abi.set_persistent_min_tiles(1)
+        dx1, cs1 = dense_abi.dgrad_tf32(gy, w, h)
+        dx2, cs2 = dense_abi.dgrad_tf32(gy, w, h)
+    finally:
+        dense_abi.set_persistent_min_tiles(keep)
+    assert torch.equal(dx1, dx0) and torch.equal(dx2, dx0)
+    assert torch.equal(cs1, cs0) and torch.equal(cs2, cs0)
+    ref = (gy.double() @ w.double()) * (h > 0)
+    bound = 1.5e-3 * _bound(gy, w) + 1e-6
+    assert float(((dx1.double() - ref).abs() / bound).max()) <= 1.0
+    assert float(((cs1.double() - ref.sum(0)).abs() / (bound.sum(0) + 1e-6)).max()) <= 1.0

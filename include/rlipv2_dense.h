@@ -82,6 +82,13 @@ int rlipv2_dense_get_small_mode(void);
 void rlipv2_dense_set_persistent_min_tiles(int tiles);
 int rlipv2_dense_get_persistent_min_tiles(void);
 
+/* The same schedule for rlipv2_dense_dgrad_tf32 with a ReLU gate (dgrad_mask_persistent_kernel, 128 x 256 tiles); applies to
+ * problems above the tile threshold when switched on.  Off by default: in the train step the gated input gradient runs
+ * beside the weight-gradient kernels of the parameter-gradient stream, and a one-CTA-per-SM kernel that takes all shared
+ * memory keeps them from co-running (measured r02l: 26.9 vs 26.5 ms/step). */
+void rlipv2_dense_set_persistent_dgrad(int on);
+int rlipv2_dense_get_persistent_dgrad(void);
+
 const char *rlipv2_dense_error_string(int code);
 
 /* kernels launched by this library in this process (for bench.py's gpu_launches) */

@@ -37,6 +37,8 @@ std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_small_mode{2};
 // grids of more than this many 128 x 128 tiles run the persistent kernel (0 = never); rlipv2_dense_set_persistent_min_tiles
 std::atomic<int> g_persistent_min_tiles{0};
+// the gated input gradient (encoder FFN backward) on its persistent kernel too (rlipv2_dense_set_persistent_dgrad)
+std::atomic<int> g_persistent_dgrad{0};
 constexpr int kNumSMs = 148;
 
 constexpr int kBlockM = 128;
@@ -946,7 +948,7 @@ int rlipv2_dense_dgrad_tf32(const float *g, const float *w, float *dx, const flo
     if ((relu_out == nullptr) != (colsum == nullptr)) return RLIPV2_DENSE_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
     const int pmin = g_persistent_min_tiles.load(std::memory_order_relaxed);
-    if (relu_out && pmin > 0 && (K % 256) == 0 && (long long)(K / 128) * ((T + kBlockM - 1) / kBlockM) > pmin) {
+    if (relu_out && pmin > 0 && g_persistent_dgrad.load(std::memory_order_relaxed) && (K % 256) == 0 && (long long)(K / 128) * ((T + kBlockM - 1) / kBlockM) > pmin) {
         // large gated input gradient (encoder FFN): persistent 128 x 256 tiles.  NB the colsum layout is the same
         // [ceil(T/128), K] as the one-tile-per-CTA kernel's.
         constexpr int STAGES = 4;
@@ -1052,6 +1054,10 @@ int rlipv2_dense_get_small_mode(void) { return g_small_mode.load(std::memory_ord
 void rlipv2_dense_set_persistent_min_tiles(int tiles) { g_persistent_min_tiles.store(tiles < 0 ? 0 : tiles, std::memory_order_relaxed); }
 
 int rlipv2_dense_get_persistent_min_tiles(void) { return g_persistent_min_tiles.load(std::memory_order_relaxed); }
+
+void rlipv2_dense_set_persistent_dgrad(int on) { g_persistent_dgrad.store(on ? 1 : 0, std::memory_order_relaxed); }
+
+int rlipv2_dense_get_persistent_dgrad(void) { return g_persistent_dgrad.load(std::memory_order_relaxed); }
 
 int rlipv2_dense_linear_tf32(const float *x, const float *w, const float *bias, float *y, int M, int N, int K,
                              int act, void *stream)

@@ -32,8 +32,13 @@ _lib.rlipv2_dense_get_small_mode.restype = _i
 _lib.rlipv2_dense_set_persistent_min_tiles.argtypes = [_i]
 _lib.rlipv2_dense_set_persistent_min_tiles.restype = None
 _lib.rlipv2_dense_get_persistent_min_tiles.restype = _i
-# persistent kernel for grids above this many tiles (A/B switch: RLIPV2_DENSE_PERSISTENT=0 turns it off)
-_lib.rlipv2_dense_set_persistent_min_tiles(int(os.environ.get("RLIPV2_DENSE_PERSISTENT", "0")))
+# persistent kernel for linears of more than 2 x 148 tiles (the encoder's 44k-row projections and FFN-up): measured r02n, two
+# repetitions on one box: 26.13 / 26.86 vs 26.59 / 27.28 ms/step without.  RLIPV2_DENSE_PERSISTENT=0 turns it off.
+_lib.rlipv2_dense_set_persistent_min_tiles(int(os.environ.get("RLIPV2_DENSE_PERSISTENT", "296")))
+_lib.rlipv2_dense_set_persistent_dgrad.argtypes = [_i]
+_lib.rlipv2_dense_set_persistent_dgrad.restype = None
+_lib.rlipv2_dense_get_persistent_dgrad.restype = _i
+_lib.rlipv2_dense_set_persistent_dgrad(int(os.environ.get("RLIPV2_DENSE_PERSISTENT_DGRAD", "0")))
 if os.environ.get("RLIPV2_DENSE_SMALL_MODE"):                      # A/B switch for measurements
     _lib.rlipv2_dense_set_small_mode(int(os.environ["RLIPV2_DENSE_SMALL_MODE"]))
 
@@ -41,7 +46,12 @@ ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 EXPORTS = ("rlipv2_dense_linear_tf32", "rlipv2_dense_linear_tf32_rowmask", "rlipv2_dense_linear_tf32_supported", "rlipv2_dense_wgrad_tf32",
            "rlipv2_dense_dgrad_tf32", "rlipv2_dense_error_string", "rlipv2_dense_launch_count",
            "rlipv2_dense_set_small_mode", "rlipv2_dense_get_small_mode", "rlipv2_dense_linear_splitk_tf32",
-           "rlipv2_dense_set_persistent_min_tiles", "rlipv2_dense_get_persistent_min_tiles")
+           "rlipv2_dense_set_persistent_min_tiles", "rlipv2_dense_get_persistent_min_tiles",
+           "rlipv2_dense_set_persistent_dgrad", "rlipv2_dense_get_persistent_dgrad")
+
+
+def set_persistent_dgrad(on):
+    _lib.rlipv2_dense_set_persistent_dgrad(1 if on else 0)
 
 
 def set_persistent_min_tiles(tiles):

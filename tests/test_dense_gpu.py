@@ -322,12 +322,16 @@ def test_persistent_gated_dgrad_is_bit_identical(T, N, K):
         dense_abi.set_persistent_min_tiles(0)
         dx0, cs0 = dense_abi.dgrad_tf32(gy, w, h)
         dense_abi.set_persistent_min_tiles(1)
+        dense_abi.set_persistent_dgrad(True)
         dx1, cs1 = dense_abi.dgrad_tf32(gy, w, h)
         dx2, cs2 = dense_abi.dgrad_tf32(gy, w, h)
     finally:
         dense_abi.set_persistent_min_tiles(keep)
+        dense_abi.set_persistent_dgrad(False)
     assert torch.equal(dx1, dx0) and torch.equal(dx2, dx0)
-    assert torch.equal(cs1, cs0) and torch.equal(cs2, cs0)
+    # the per-tile column sums are identical; their sum over the row tiles is formed with fp32 atomics (order varies)
+    torch.testing.assert_close(cs1, cs0, rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(cs2, cs0, rtol=1e-5, atol=1e-4)
     ref = (gy.double() @ w.double()) * (h > 0)
     bound = 1.5e-3 * _bound(gy, w) + 1e-6
     assert float(((dx1.double() - ref).abs() / bound).max()) <= 1.0

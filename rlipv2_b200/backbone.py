@@ -14,7 +14,7 @@ import torchvision
 from torch import nn
 from torchvision.models._utils import IntermediateLayerGetter
 
-from . import dense
+from . import dense, streams
 from .nested import NestedTensor
 
 
@@ -293,7 +293,7 @@ class Joiner(nn.Sequential):
             # on a side stream that forks before the backbone's convolutions and joins after them.
             cur = torch.cuda.current_stream(x_in.device)
             if getattr(self, "_pos_stream", None) is None:
-                self._pos_stream = torch.cuda.Stream(x_in.device)
+                self._pos_stream = streams.get(x_in.device, "pos")
             side = self._pos_stream
             side.wait_stream(cur)                               # fork point: before the convolutions are issued
             xs = self[0](tensor_list, defer_masks=True)

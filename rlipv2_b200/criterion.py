@@ -21,6 +21,7 @@ import torch.distributed as dist
 import torch.nn.functional as F
 from torch import nn
 
+from . import streams
 from .nested import box_cxcywh_to_xyxy, generalized_box_iou
 
 
@@ -472,7 +473,7 @@ class _Branches:
             self.cur = torch.cuda.current_stream(device)
             pool = _BRANCH_STREAMS.setdefault(str(device), [])
             while len(pool) < n:
-                pool.append(torch.cuda.Stream(device))
+                pool.append(streams.get(device, f"branch{len(pool)}"))
             self.streams = pool[:n]
 
     def run(self, fn):

@@ -29,6 +29,8 @@ import os
 import torch
 import torch.nn.functional as F
 
+from . import streams
+
 _PRECISION = "fp32"
 _USE_TCGEN05 = True
 _USE_FUSED = True        # fused LayerNorm / bias-gradient kernels (exact fp32 arithmetic; CUDA tensors only)
@@ -62,7 +64,7 @@ _param_grad_pending = set()
 def _param_grad_stream(device):
     st = _param_grad_streams.get(device)
     if st is None:
-        st = _param_grad_streams[device] = torch.cuda.Stream(device)
+        st = _param_grad_streams[device] = streams.get(device, "param_grad")
     return st
 
 

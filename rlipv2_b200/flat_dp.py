@@ -12,6 +12,8 @@ train_step.py.
 import torch
 import torch.distributed as dist
 
+from . import streams
+
 
 def world_size():
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
@@ -161,7 +163,7 @@ class EarlyReducer:
         self.wait_streams = wait_streams or (lambda: [])
         self.active = force or world_size() > 1
         self.cuda = flat.flat_grad.is_cuda
-        self.comm = torch.cuda.Stream(flat.flat_grad.device) if self.cuda else None
+        self.comm = streams.get(flat.flat_grad.device, "comm") if self.cuda else None
         self.fired, self.launched, self.events = set(), [], {}
 
     def begin(self):

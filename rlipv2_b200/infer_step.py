@@ -9,6 +9,7 @@ image shape into one CUDA graph (the eager forward is ~2 700 launches of mostly 
 """
 import torch
 
+from . import streams
 from .nested import NestedTensor, nested_tensor_from_tensor_list
 
 
@@ -67,7 +68,7 @@ class ParSeDAInference:
         bs = self.batch_size if batch is None else int(batch)
         self.s_samples = NestedTensor(torch.zeros(bs, 3, height, width, device=self.device),
                                       torch.zeros(bs, height, width, dtype=torch.bool, device=self.device))
-        side = torch.cuda.Stream(self.device)
+        side = streams.get(self.device, "capture")
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(warmup):

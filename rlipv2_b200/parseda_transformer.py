@@ -29,7 +29,7 @@ from torch import nn
 from torch.nn.init import normal_
 from torch.nn.utils.rnn import pad_sequence
 
-from . import dense, grad_ready
+from . import dense, grad_ready, streams
 from .alif import FeatureResizer, RLIPv2_VLFuse
 from .ms_deform_attn import MSDeformAttn
 from .nested import inverse_sigmoid
@@ -253,7 +253,7 @@ class RLIPv2_DeformableTransformerEncoder(nn.Module):
         side, pending = None, False
         if _LANG_STREAM and src.is_cuda:
             if getattr(self, "_lang_stream", None) is None:
-                self._lang_stream = torch.cuda.Stream(src.device)
+                self._lang_stream = streams.get(src.device, "lang")
             side = self._lang_stream
         for idx, layer in enumerate(self.layers):
             if idx % self.fusion_interval == 0:
@@ -426,7 +426,7 @@ class DABDeformableTransformerDecoderHOI(nn.Module):
         if _VALUE_STREAM and src.is_cuda:
             cur = torch.cuda.current_stream(src.device)
             if getattr(self, "_value_stream", None) is None:
-                self._value_stream = torch.cuda.Stream(src.device)
+                self._value_stream = streams.get(src.device, "value_pair" if self.ParSe else "value_verb")
             side = self._value_stream
             side.wait_stream(cur)
             values, value_ready = [], []
@@ -609,7 +609,7 @@ class RLIP_ParSeDABDeformableTransformer_v2(nn.Module):
         and inside a CUDA-graph capture (the fork/join become graph edges)."""
         cur = torch.cuda.current_stream(device)
         if getattr(self, "_text_stream", None) is None:
-            self._text_stream = torch.cuda.Stream(device)
+            self._text_stream = streams.get(device, "text")
         side = self._text_stream
         side.wait_stream(cur)
         with torch.cuda.stream(side):

@@ -17,7 +17,7 @@ import os
 import torch
 import torch.distributed as dist
 
-from . import dense, models
+from . import dense, models, streams
 from .nested import NestedTensor
 
 
@@ -183,7 +183,7 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
             # 850 MB memset beside the (launch-bound) start of the text tower / backbone stem, joined below
             cur = torch.cuda.current_stream(self.device)
             if getattr(self, "_zero_stream", None) is None:
-                self._zero_stream = torch.cuda.Stream(self.device)
+                self._zero_stream = streams.get(self.device, "zero")
             zero_side = self._zero_stream
             zero_side.wait_stream(cur)
             with torch.cuda.stream(zero_side):
@@ -415,7 +415,7 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         # (AccumulateGrad included) on the stream its forward op first ran on, so all of them must be
         # the capture stream - never the legacy default stream.
         if first:
-            self.cap_stream = torch.cuda.Stream()
+            self.cap_stream = streams.get(self.device, "capture")
         side = self.cap_stream
         side.wait_stream(torch.cuda.current_stream())
         if first:
@@ -660,7 +660,7 @@ class GraphedParSeDATrainStep(ParSeDATrainStep):
         `step()` without a batch consumes it: device-to-device copies into the graphs' static buffers, then the replay."""
         dev = self.device
         if getattr(self, "_copy_stream", None) is None:
-            self._copy_stream = torch.cuda.Stream(dev)
+            self._copy_stream = streams.get(dev, "copy")
             self.p_images = torch.empty_like(self.s_samples.tensors)
             self.p_targets = [{k: torch.empty_like(v) for k, v in t.items()} for t in self.s_targets]
             self.p_tok = None

@@ -134,3 +134,30 @@ def test_bucketed_step_follows_the_eager_trajectory_over_changing_shapes():
             assert float(d) < 3e-3, (k, float(d))
     finally:
         dense.set_matmul_precision("fp32")
+
+
+def test_role_streams_never_alias():
+    """torch recycles its 32 pool streams round-robin; round 2 found the graphed step producing NaN parameters when a process
+    had created enough streams for the capture stream to coincide with a criterion branch stream (tools/debug_nan_sequence.py).
+    Every side stream now comes from rlipv2_b200.streams (one per role): distinct handles, a bounded count, however many models
+    the process has built - and throw-away pool streams created in between change nothing."""
+    from rlipv2_b200 import dense, models, streams, train_step
+    try:
+        junk = [torch.cuda.Stream() for _ in range(40)]          # push torch's round-robin counter past a full cycle
+        for cls in (train_step.ParSeDATrainStep, train_step.GraphedParSeDATrainStep):
+            ts, imgs, tg, text = _make(cls)
+            if cls is train_step.GraphedParSeDATrainStep:
+                ts.capture(imgs, tg, text, warmup=2)
+                loss = float(ts.replay())
+                assert torch.isfinite(ts.flat_param).all()
+            else:
+                samples, targets = ts.to_device(imgs, tg)
+                loss = float(ts.step_device(samples, targets, text))
+            assert loss == loss and loss > 0
+            junk += [torch.cuda.Stream() for _ in range(7)]
+        h = streams.handles("cuda:0")
+        assert len(set(h.values())) == len(h) <= 20, h
+        for role in ("capture", "text", "lang", "pos", "value_pair", "value_verb", "zero", "branch0"):
+            assert role in h, (role, sorted(h))
+    finally:
+        dense.set_matmul_precision("fp32")

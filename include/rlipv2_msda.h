@@ -138,6 +138,16 @@ const char *rlipv2_msda_error_string(int code);
 /* RLIPV2_MSDA_ABI_VERSION the library was built with. */
 int rlipv2_msda_abi_version(void);
 
+/* Backward schedule of the fast path (fp32, D = 32, L = 4, P = 4), process-wide:
+ *   0  one red.global.add.v4.f32 per valid corner - the reference's one atomicAdd per corner and channel
+ *      (ms_deform_im2col_cuda.cuh:125,134,143,152), vectorised;
+ *   1  corners of one (image, query, head) that fall on the same cell of a level are merged before they are issued
+ *      (every contribution is a scalar times the pair's grad_out row, so the scalars add), and corners whose merged scalar
+ *      is exactly zero are not issued.  Same sums as mode 0 up to fp32 rounding order (rlipv2_b200/csrc/msda_merge.h).
+ * Returns 0, or RLIPV2_MSDA_EINVAL for another mode. */
+int rlipv2_msda_set_backward_mode(int mode);
+int rlipv2_msda_get_backward_mode(void);
+
 /* Number of kernels launched by this library in this process since load (for bench.py's
  * `gpu_launches`; relaxed atomic counter, never reset). */
 unsigned long long rlipv2_msda_launch_count(void);

@@ -38,10 +38,14 @@
 #include <atomic>
 
 #include "rlipv2_msda.h"
+#include "msda_merge.h"
 
 namespace {
 
 std::atomic<unsigned long long> g_launches{0};
+// backward of the fast path: 0 = one reduction per valid corner, 1 = corners of one pair that fall on the same cell merged
+// before they are issued (msda_merge.h); set through rlipv2_msda_set_backward_mode
+std::atomic<int> g_bwd_mode{0};
 
 constexpr int kFastD = 32;
 constexpr int kFastL = 4;
@@ -267,15 +271,18 @@ __device__ __forceinline__ float group_reduce_scatter8(const float (&x)[8], int 
 // backward for the 4 pairs owned by this warp.  The 16 points are walked in two halves of 8 so
 // that the per-point partials (3 x 8 registers) stay small; scaleW/scaleH = (W, H) of the level
 // of point `sub` in each half (cuh:156-158).
-template <int PROJ>
+// MERGE: phase 1 also forms, per point, the four reduction scalars after merging the corners of the pair that share a cell
+// (msda_merge.h: each lane merges its own two points against the level's other two, held by its neighbour lane) and stages
+// them as a second 4-word record; phase 2 issues a reduction only for a non-zero scalar.
+template <int PROJ, int MERGE>
 __device__ __forceinline__ void bwd_warp_pairs(const float *__restrict__ value, const PairSrc &src,
                                                const float *__restrict__ grad_out,
                                                float *__restrict__ grad_value,
                                                float *__restrict__ grad_loc,
                                                float *__restrict__ grad_attn, const WarpCtx &c,
                                                const LevelRow &my, const float (&scaleW)[2],
-                                               const float (&scaleH)[2], uint4 *mine, int Q,
-                                               bool live, int n, int S, int M, int m)
+                                               const float (&scaleH)[2], uint4 *mine, float4 *mine_s,
+                                               int Q, bool live, int n, int S, int M, int m)
 {
     const size_t pair = (size_t)(live ? Q : 0) * M + m;
     float4 l4;
@@ -284,11 +291,37 @@ __device__ __forceinline__ void bwd_warp_pairs(const float *__restrict__ value, 
     lane_points<PROJ>(src, c, my, Q, M, m, live, l4, a2);
     if (live) g4 = ldg_f4(grad_out + pair * kFastD + c.sub * 4);
     const uint32_t cell0 = ((uint32_t)n * (uint32_t)S + my.start) * c.MD + (uint32_t)m * kFastD;
-    uint4 p0 = pack_point(l4.x, l4.y, a2.x, my.H, my.W, cell0, c.MD);
-    uint4 p1 = pack_point(l4.z, l4.w, a2.y, my.H, my.W, cell0, c.MD);
-    if (!live) { p0.x &= ~15u; p1.x &= ~15u; }       // dead group: no loads, no reductions
-    mine[c.grp * kFastLP + c.sub * 2 + 0] = p0;
-    mine[c.grp * kFastLP + c.sub * 2 + 1] = p1;
+    if (MERGE) {
+        MsdaPoint m0 = msda_point(l4.x, l4.y, a2.x, my.H, my.W);
+        MsdaPoint m1 = msda_point(l4.z, l4.w, a2.y, my.H, my.W);
+        if (!live) { m0.bits = 0u; m1.bits = 0u; }   // dead group: no loads, no reductions
+        // the level's other two points live in the neighbour lane (sub ^ 1); w + 1 >= 0 rides with the validity bits
+        MsdaPoint q0, q1;
+        const unsigned wb0 = ((unsigned)(m0.w + 1) << 4) | m0.bits, wb1 = ((unsigned)(m1.w + 1) << 4) | m1.bits;
+        const unsigned xb0 = __shfl_xor_sync(0xffffffffu, wb0, 1), xb1 = __shfl_xor_sync(0xffffffffu, wb1, 1);
+        q0.h = __shfl_xor_sync(0xffffffffu, m0.h, 1);   q1.h = __shfl_xor_sync(0xffffffffu, m1.h, 1);
+        q0.w = (int)(xb0 >> 4) - 1;                     q1.w = (int)(xb1 >> 4) - 1;
+        q0.bits = xb0 & 15u;                            q1.bits = xb1 & 15u;
+        q0.lh = __shfl_xor_sync(0xffffffffu, m0.lh, 1); q1.lh = __shfl_xor_sync(0xffffffffu, m1.lh, 1);
+        q0.lw = __shfl_xor_sync(0xffffffffu, m0.lw, 1); q1.lw = __shfl_xor_sync(0xffffffffu, m1.lw, 1);
+        q0.a = __shfl_xor_sync(0xffffffffu, m0.a, 1);   q1.a = __shfl_xor_sync(0xffffffffu, m1.a, 1);
+        float s0[4], s1[4];
+        msda_merge_lane(m0, m1, q0, q1, (c.sub & 1) != 0, s0, s1);
+        const uint32_t b0 = cell0 + (uint32_t)(max(m0.h, 0) * my.W + max(m0.w, 0)) * c.MD;
+        const uint32_t b1 = cell0 + (uint32_t)(max(m1.h, 0) * my.W + max(m1.w, 0)) * c.MD;
+        mine[c.grp * kFastLP + c.sub * 2 + 0] =
+            make_uint4(b0 | m0.bits, __float_as_uint(m0.lh), __float_as_uint(m0.lw), __float_as_uint(m0.a));
+        mine[c.grp * kFastLP + c.sub * 2 + 1] =
+            make_uint4(b1 | m1.bits, __float_as_uint(m1.lh), __float_as_uint(m1.lw), __float_as_uint(m1.a));
+        mine_s[c.grp * kFastLP + c.sub * 2 + 0] = make_float4(s0[0], s0[1], s0[2], s0[3]);
+        mine_s[c.grp * kFastLP + c.sub * 2 + 1] = make_float4(s1[0], s1[1], s1[2], s1[3]);
+    } else {
+        uint4 p0 = pack_point(l4.x, l4.y, a2.x, my.H, my.W, cell0, c.MD);
+        uint4 p1 = pack_point(l4.z, l4.w, a2.y, my.H, my.W, cell0, c.MD);
+        if (!live) { p0.x &= ~15u; p1.x &= ~15u; }       // dead group: no loads, no reductions
+        mine[c.grp * kFastLP + c.sub * 2 + 0] = p0;
+        mine[c.grp * kFastLP + c.sub * 2 + 1] = p1;
+    }
     __syncwarp();
 
     const float *vbase = value + c.sub * 4;
@@ -327,11 +360,20 @@ __device__ __forceinline__ void bwd_warp_pairs(const float *__restrict__ value, 
             pw[j] = a * fmaf(hh, d2 - d1, lh * (d4 - d3));
             ph[j] = a * fmaf(hw, d3 - d1, lw * (d4 - d2));
             // cuh:125,134,143,152  grad_value[corner] += w_k * top_grad * attn
-            const float s1 = w1 * a, s2 = w2 * a, s3 = w3 * a, s4 = w4 * a;
-            if (c1) red_add_v4(gbase + base, s1 * g4.x, s1 * g4.y, s1 * g4.z, s1 * g4.w);
-            if (c2) red_add_v4(gbase + base + dx, s2 * g4.x, s2 * g4.y, s2 * g4.z, s2 * g4.w);
-            if (c3) red_add_v4(gbase + base + dy, s3 * g4.x, s3 * g4.y, s3 * g4.z, s3 * g4.w);
-            if (c4) red_add_v4(gbase + base + dy + dx, s4 * g4.x, s4 * g4.y, s4 * g4.z, s4 * g4.w);
+            if (MERGE) {
+                // merged scalars: 0 for a corner that is outside, owned by an earlier corner of the pair, or weightless
+                const float4 sw = mine_s[c.grp * kFastLP + half * 8 + j];
+                if (sw.x != 0.f) red_add_v4(gbase + base, sw.x * g4.x, sw.x * g4.y, sw.x * g4.z, sw.x * g4.w);
+                if (sw.y != 0.f) red_add_v4(gbase + base + dx, sw.y * g4.x, sw.y * g4.y, sw.y * g4.z, sw.y * g4.w);
+                if (sw.z != 0.f) red_add_v4(gbase + base + dy, sw.z * g4.x, sw.z * g4.y, sw.z * g4.z, sw.z * g4.w);
+                if (sw.w != 0.f) red_add_v4(gbase + base + dy + dx, sw.w * g4.x, sw.w * g4.y, sw.w * g4.z, sw.w * g4.w);
+            } else {
+                const float s1 = w1 * a, s2 = w2 * a, s3 = w3 * a, s4 = w4 * a;
+                if (c1) red_add_v4(gbase + base, s1 * g4.x, s1 * g4.y, s1 * g4.z, s1 * g4.w);
+                if (c2) red_add_v4(gbase + base + dx, s2 * g4.x, s2 * g4.y, s2 * g4.z, s2 * g4.w);
+                if (c3) red_add_v4(gbase + base + dy, s3 * g4.x, s3 * g4.y, s3 * g4.z, s3 * g4.w);
+                if (c4) red_add_v4(gbase + base + dy + dx, s4 * g4.x, s4 * g4.y, s4 * g4.z, s4 * g4.w);
+            }
         }
         const float ga = group_reduce_scatter8(pa, c.sub);
         const float gw = group_reduce_scatter8(pw, c.sub);
@@ -416,7 +458,7 @@ msda_fwd_d32_l4p4(const float *__restrict__ value, const int64_t *__restrict__ s
         fwd_warp_pairs<UNROLL, PROJ>(value, src, out, c, my, prep[warp], Q, live, n, S, M, m);
 }
 
-template <int MINB, int PROJ = 0>
+template <int MINB, int PROJ = 0, int MERGE = 0>
 __global__ void __launch_bounds__(kThreads, MINB)
 msda_bwd_d32_l4p4(const float *__restrict__ value, const int64_t *__restrict__ shapes,
                   const int64_t *__restrict__ lsi, const float *__restrict__ loc,
@@ -427,6 +469,7 @@ msda_bwd_d32_l4p4(const float *__restrict__ value, const int64_t *__restrict__ s
     // PROJ: `loc` = proj, `attn` = ref, `grad_loc` = grad_proj [NQ, M*48] (fully written), grad_attn unused
     const PairSrc src = PROJ ? PairSrc{nullptr, nullptr, loc, attn} : PairSrc{loc, attn, nullptr, nullptr};
     __shared__ __align__(16) uint4 prep[kWarpsPerCta][4 * kFastLP];
+    __shared__ __align__(16) float4 prep_s[MERGE ? kWarpsPerCta : 1][MERGE ? 4 * kFastLP : 1];
     __shared__ LevelRow lvl_tab[kFastL];
     load_level_table(lvl_tab, shapes, lsi, (uint32_t)M * kFastD);
     const WarpCtx c = make_ctx(lvl_tab, M);
@@ -441,8 +484,8 @@ msda_bwd_d32_l4p4(const float *__restrict__ value, const int64_t *__restrict__ s
     const int m_begin = blockIdx.y * heads_per;
     const int m_end = min(M, m_begin + heads_per);
     for (int m = m_begin; m < m_end; ++m)
-        bwd_warp_pairs<PROJ>(value, src, grad_out, grad_value, grad_loc, grad_attn, c, my, scaleW,
-                             scaleH, prep[warp], Q, live, n, S, M, m);
+        bwd_warp_pairs<PROJ, MERGE>(value, src, grad_out, grad_value, grad_loc, grad_attn, c, my, scaleW,
+                                    scaleH, prep[warp], prep_s[MERGE ? warp : 0], Q, live, n, S, M, m);
 }
 
 
@@ -786,10 +829,16 @@ int backward_impl(const T *value, const int64_t *shapes, const int64_t *lsi, con
     if (allow_fast) {
         const int NQ = batch * num_query;
         const dim3 grid = fast_grid(NQ, num_heads);
-        msda_bwd_d32_l4p4<2><<<grid, kThreads, 0, stream>>>(
-            (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn,
-            (const float *)grad_out, NQ, num_query, spatial_size, num_heads, (float *)grad_value,
-            (float *)grad_loc, (float *)grad_attn);
+        if (g_bwd_mode.load(std::memory_order_relaxed) == 1)
+            msda_bwd_d32_l4p4<2, 0, 1><<<grid, kThreads, 0, stream>>>(
+                (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn,
+                (const float *)grad_out, NQ, num_query, spatial_size, num_heads, (float *)grad_value,
+                (float *)grad_loc, (float *)grad_attn);
+        else
+            msda_bwd_d32_l4p4<2><<<grid, kThreads, 0, stream>>>(
+                (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn,
+                (const float *)grad_out, NQ, num_query, spatial_size, num_heads, (float *)grad_value,
+                (float *)grad_loc, (float *)grad_attn);
     } else {
         msda_bwd_generic<T><<<grid_for(pairs * 32, 256), 256, 0, stream>>>(
             value, shapes, lsi, loc, attn, grad_out, pairs, num_query, spatial_size, num_heads,
@@ -852,9 +901,17 @@ int proj_backward_impl(const float *value, const int64_t *shapes, const int64_t 
     if (!value || !shapes || !lsi || !ref || !proj || !grad_out || !grad_proj) return RLIPV2_MSDA_EINVAL;
     if (!aligned16(value, ref, proj, grad_out, grad_value, grad_proj)) return RLIPV2_MSDA_EALIGN;
     const dim3 grid = fast_grid(NQ, num_heads);
-    if (ref_dim == 4)
-        msda_bwd_d32_l4p4<2, 2><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, grad_out, NQ, num_query,
-                                                                spatial_size, num_heads, grad_value, grad_proj, nullptr);
+    const bool merge = g_bwd_mode.load(std::memory_order_relaxed) == 1;
+    if (ref_dim == 4) {
+        if (merge)
+            msda_bwd_d32_l4p4<2, 2, 1><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, grad_out, NQ, num_query,
+                                                                       spatial_size, num_heads, grad_value, grad_proj, nullptr);
+        else
+            msda_bwd_d32_l4p4<2, 2><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, grad_out, NQ, num_query,
+                                                                    spatial_size, num_heads, grad_value, grad_proj, nullptr);
+    } else if (merge)
+        msda_bwd_d32_l4p4<2, 1, 1><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, grad_out, NQ, num_query,
+                                                                   spatial_size, num_heads, grad_value, grad_proj, nullptr);
     else
         msda_bwd_d32_l4p4<2, 1><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, grad_out, NQ, num_query,
                                                                 spatial_size, num_heads, grad_value, grad_proj, nullptr);
@@ -1030,6 +1087,15 @@ const char *rlipv2_msda_error_string(int code)
 }
 
 int rlipv2_msda_abi_version(void) { return RLIPV2_MSDA_ABI_VERSION; }
+
+int rlipv2_msda_set_backward_mode(int mode)
+{
+    if (mode != 0 && mode != 1) return RLIPV2_MSDA_EINVAL;
+    g_bwd_mode.store(mode, std::memory_order_relaxed);
+    return 0;
+}
+
+int rlipv2_msda_get_backward_mode(void) { return g_bwd_mode.load(std::memory_order_relaxed); }
 
 
 unsigned long long rlipv2_msda_launch_count(void)

@@ -41,6 +41,9 @@ _lib.rlipv2_msda_error_string.argtypes = [_i]
 _lib.rlipv2_msda_error_string.restype = ctypes.c_char_p
 _lib.rlipv2_msda_abi_version.restype = _i
 _lib.rlipv2_msda_launch_count.restype = ctypes.c_ulonglong
+_lib.rlipv2_msda_set_backward_mode.argtypes = [_i]
+_lib.rlipv2_msda_set_backward_mode.restype = _i
+_lib.rlipv2_msda_get_backward_mode.restype = _i
 
 if _lib.rlipv2_msda_abi_version() != ABI_VERSION:
     raise ImportError(f"{_path}: ABI version {_lib.rlipv2_msda_abi_version()} != {ABI_VERSION}; rebuild")
@@ -48,11 +51,25 @@ if _lib.rlipv2_msda_abi_version() != ABI_VERSION:
 EXPORTS = ("rlipv2_msda_forward_f32", "rlipv2_msda_forward_f64", "rlipv2_msda_backward_f32",
            "rlipv2_msda_backward_f64", "rlipv2_msda_proj_forward_f32", "rlipv2_msda_proj_backward_f32",
            "rlipv2_msda_proj_ref4_forward_f32", "rlipv2_msda_proj_ref4_backward_f32",
-           "rlipv2_msda_forward_tma_f32", "rlipv2_msda_error_string", "rlipv2_msda_abi_version", "rlipv2_msda_launch_count")
+           "rlipv2_msda_forward_tma_f32", "rlipv2_msda_error_string", "rlipv2_msda_abi_version", "rlipv2_msda_launch_count",
+           "rlipv2_msda_set_backward_mode", "rlipv2_msda_get_backward_mode")
 
 
 def library_path():
     return _path
+
+
+def set_backward_mode(mode):
+    """0 = one reduction per valid corner, 1 = same-cell corners of a pair merged before issue (include/rlipv2_msda.h)"""
+    _check(_lib.rlipv2_msda_set_backward_mode(int(mode)), "rlipv2_msda_set_backward_mode")
+
+
+def get_backward_mode():
+    return int(_lib.rlipv2_msda_get_backward_mode())
+
+
+if os.environ.get("RLIPV2_MSDA_BWD_MERGE"):                            # A/B switch for measurements
+    set_backward_mode(int(os.environ["RLIPV2_MSDA_BWD_MERGE"]))
 
 
 def launch_count():

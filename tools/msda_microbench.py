@@ -1,11 +1,13 @@
 """MSDeformAttn micro-benchmark (BASELINE config 5 + encoder-shaped calls), one GPU.
 
-    python tools/msda_microbench.py [--ref] [--iters 50]
+    python tools/msda_microbench.py [--ref] [--iters 50] [--bwd-modes 0,1]
 
 Timing: CUDA events on the current stream around `iters` back-to-back launches that rotate over
 enough independent input sets to exceed the L2 (>= 2x126 MB working set), after 5 warm-up
 launches.  GB/s = algorithmic bytes (rlipv2_b200.synth.msda_bytes) / mean launch time.
-`--ref` also times the reference's own CUDA kernel (oracle/_ref, built by oracle/build_ref.py)."""
+`--ref` also times the reference's own CUDA kernel (oracle/_ref, built by oracle/build_ref.py);
+`--bwd-modes 0,1` times the backward under each schedule of rlipv2_msda_set_backward_mode (0 = one reduction per corner,
+1 = same-cell corners of a pair merged) and restores the mode it found."""
 import argparse
 import json
 import os
@@ -33,7 +35,7 @@ def time_rot(fn_list, iters):
     return e0.elapsed_time(e1) / iters * 1e-3
 
 
-def run_case(name, make, N, S, Lq, iters, impls, peak):
+def run_case(name, make, N, S, Lq, iters, impls, peak, bwd_modes=()):
     fwd_b, bwd_b = synth.msda_bytes(N, S, Lq)
     ncopies = max(2, min(24, int(2.2 * L2_BYTES / fwd_b) + 1))
     sets = [make(seed) for seed in range(ncopies)]
@@ -46,6 +48,15 @@ def run_case(name, make, N, S, Lq, iters, impls, peak):
         tb = time_rot(b, iters)
         res[iname] = {"fwd_us": tf * 1e6, "fwd_GBs": fwd_b / tf / 1e9, "fwd_frac": fwd_b / tf / 1e9 / peak,
                       "bwd_us": tb * 1e6, "bwd_GBs": bwd_b / tb / 1e9, "bwd_frac": bwd_b / tb / 1e9 / peak}
+    if bwd_modes:
+        from rlipv2_b200 import msda_abi
+        before = msda_abi.get_backward_mode()
+        b = [lambda s=s: MSDA.ms_deform_attn_backward(s[0], s[1], s[2], s[3], s[4], s[5], 64) for s in sets]
+        for mode in bwd_modes:
+            msda_abi.set_backward_mode(mode)
+            tb = time_rot(b, iters)
+            res[f"ours_bwd_mode{mode}"] = {"bwd_us": tb * 1e6, "bwd_GBs": bwd_b / tb / 1e9, "bwd_frac": bwd_b / tb / 1e9 / peak}
+        msda_abi.set_backward_mode(before)
     print(json.dumps(res))
     return res
 
@@ -55,6 +66,7 @@ def main():
     ap.add_argument("--ref", action="store_true")
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--cases", default="dec16,dec2,encrand2,enc2,enc2init,enc2n025")
+    ap.add_argument("--bwd-modes", default="", help="comma-separated backward schedules to time (rlipv2_msda_set_backward_mode)")
     args = ap.parse_args()
     peak = 6581.2
     try:
@@ -87,7 +99,7 @@ def main():
     }
     for key in args.cases.split(","):
         name, make, N, S, Lq = cases[key]
-        run_case(name, make, N, S, Lq, args.iters, impls, peak)
+        run_case(name, make, N, S, Lq, args.iters, impls, peak, [int(m) for m in args.bwd_modes.split(",") if m])
 
 
 if __name__ == "__main__":

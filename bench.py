@@ -241,11 +241,29 @@ def alif_tensor_roofline(device):
         y = dense_abi.linear_splitk_tf32(x2, w, b, sp) if sp > 1 else dense_abi.linear_tf32(x2, w, b, 0)
         return y.view(*x.shape[:-1], w.shape[0])
 
+    from rlipv2_b200 import alif as alif_mod, streams
+    two = alif_mod._ALIF_STREAMS                       # issue the layer the way the model does (alif.py::_two_stream_call)
+
     def layer():
-        q, k, vv, vl = lin(v, "q"), lin(l, "k"), lin(v, "vv"), lin(l, "vl")
+        if not two:
+            q, k, vv, vl = lin(v, "q"), lin(l, "k"), lin(v, "vv"), lin(l, "vl")
+            ov, _, _ = attn_abi.forward(q, k, vl, H, None, 256 ** -0.5, 0.0, None, 0)
+            ol, _, _ = attn_abi.forward(k, q, vv, H, None, 256 ** -0.5, 0.0, None, 1)
+            return lin(ov, "ov"), lin(ol, "ol")
+        cur, side = torch.cuda.current_stream(device), streams.get(device, "alif")
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            k, vl = lin(l, "k"), lin(l, "vl")
+        q, vv = lin(v, "q"), lin(v, "vv")
+        cur.wait_stream(side)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            ol, _, _ = attn_abi.forward(k, q, vv, H, None, 256 ** -0.5, 0.0, None, 1)
+            o_l = lin(ol, "ol")
         ov, _, _ = attn_abi.forward(q, k, vl, H, None, 256 ** -0.5, 0.0, None, 0)
-        ol, _, _ = attn_abi.forward(k, q, vv, H, None, 256 ** -0.5, 0.0, None, 1)
-        return lin(ov, "ov"), lin(ol, "ol")
+        o_v = lin(ov, "ov")
+        cur.wait_stream(side)
+        return o_v, o_l
 
     for _ in range(3):
         layer()
@@ -286,7 +304,9 @@ def alif_tensor_roofline(device):
             "us_per_layer": t * 1e6, "flops_per_layer": flops, "flops_per_image_layer": flops / B,
             "ncu": "profiles/attn_r02_ncu.txt, profiles/dense_r01_final_alif_ncu.txt (sm__pipe_tensor_cycles_active per kernel); "
                    "512-546 row problems fill 16-112 of 148 SMs: latency-bound, not pipe-bound",
-            "timing": "CUDA-graph replay of the 8 launches x 10, CUDA events"}
+            "streams": 2 if two else 1,
+            "timing": "CUDA-graph replay of the 8 launches x 10, CUDA events"
+                      + (" (label chain beside the image chain, as alif.py issues it)" if two else "")}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -25,10 +25,18 @@ Reference quirks reproduced on purpose:
   * dropout p=0.1 on both attention maps whenever the module is in training mode, independent of
     `--dropout` (fuse_helper.py:438-439, 1011).
 """
+import os
+
 import torch
 from torch import nn
 
-from . import dense
+from . import dense, streams
+
+# The block is two chains that meet only in the attention core: LayerNorm + two projections of the image tokens, the same
+# for the labels, then one attention direction + out-projection + gate each.  Every kernel in them is a few hundred rows -
+# latency-bound, 16-112 of 148 SMs busy (DESIGN.md 6e) - so the label chain runs on its own stream beside the image chain,
+# forward and (through autograd's stream bookkeeping) backward.  RLIPV2_ALIF_STREAMS=0/1 is the A/B switch.
+_ALIF_STREAMS = os.environ.get("RLIPV2_ALIF_STREAMS", "0") != "0"
 
 
 class FeatureResizer(nn.Module):
@@ -129,7 +137,49 @@ class RLIPv2_BiAttentionBlockForCheckpoint(nn.Module):
         new_v, new_l = self.single_attention_call(q, l, q_pos, attention_mask_l, attention_mask_v)
         return new_v, new_l, None, None, None
 
+    def _gate(self, x, gamma, delta):
+        if self.gating_mechanism == "VXAc":
+            return x + gamma[0] * delta
+        if self.gating_mechanism == "GLIP":
+            return x + gamma * delta
+        return x + delta                                     # XGating
+
+    def _two_stream_call(self, v, l, v_pos):
+        """same arithmetic as single_attention_call, the label chain on the 'alif' side stream"""
+        a = self.attn
+        cur = torch.cuda.current_stream(v.device)
+        side = streams.get(v.device, "alif")
+        salt = getattr(a, "_rlipv2_salt", 0)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            l_n = dense.layer_norm(l, self.layer_norm_l.weight, self.layer_norm_l.bias, self.layer_norm_l.eps)
+            k = dense.linear(l_n, a.l_proj.weight, a.l_proj.bias)
+            vl = dense.linear(l_n, a.values_l_proj.weight, a.values_l_proj.bias)
+        v_n = dense.layer_norm(v, self.layer_norm_v.weight, self.layer_norm_v.bias, self.layer_norm_v.eps)
+        q = dense.linear(v_n if v_pos is None else v_n + v_pos, a.v_proj.weight, a.v_proj.bias)
+        vv = dense.linear(v_n, a.values_v_proj.weight, a.values_v_proj.bias)
+        # each direction needs the other chain's projections
+        cur.wait_stream(side)
+        side.wait_stream(cur)
+        for t in (k, vl):
+            t.record_stream(cur)
+        for t in (q, vv):
+            t.record_stream(side)
+        with torch.cuda.stream(side):
+            out_l = dense.attention(k, q, vv, a.num_heads, a.scale, None, a.dropout, a.training, 2 * salt + 1)
+            l_out = self._gate(l_n, self.gamma_l, dense.linear(out_l, a.out_l_proj.weight, a.out_l_proj.bias))
+        out_v = dense.attention(q, k, vl, a.num_heads, a.scale, None, a.dropout, a.training, 2 * salt)
+        v_out = self._gate(v_n, self.gamma_v, dense.linear(out_v, a.out_v_proj.weight, a.out_v_proj.bias))
+        cur.wait_stream(side)
+        l_out.record_stream(cur)
+        return v_out, l_out
+
     def single_attention_call(self, v, l, v_pos, attention_mask_l=None, attention_mask_v=None, dummy_tensor=None):
+        if _ALIF_STREAMS and v.is_cuda:
+            for m in (attention_mask_l, attention_mask_v):
+                if m is not None and m.dtype != torch.bool:
+                    raise NotImplementedError("non-bool ALIF masks are not on the reference's call path")
+            return self._two_stream_call(v, l, v_pos)
         v = dense.layer_norm(v, self.layer_norm_v.weight, self.layer_norm_v.bias, self.layer_norm_v.eps)
         l = dense.layer_norm(l, self.layer_norm_l.weight, self.layer_norm_l.bias, self.layer_norm_l.eps)
         delta_v, delta_l = self.attn(v, l, v_pos, attention_mask_l=attention_mask_l,

@@ -1,0 +1,109 @@
+"""ALIF with the label chain on its own stream (rlipv2_b200/alif.py::_two_stream_call, RLIPV2_ALIF_STREAMS=1) is the same
+arithmetic as the one-stream block (/root/reference/models/fuse_helper.py:684-721 over :365-466).
+
+CPU: the wiring (which weights, which salts, which gate) with the stream calls stubbed out; GPU: outputs and gradients of the
+two schedules in training mode (hashed dropout: same seed + call site -> same masks) and the reference's ALIF fixture."""
+import contextlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.detfill import det_fill_
+from tests.test_parseda_model import _args, _load
+
+
+def _block(device, seed=1):
+    from rlipv2_b200.alif import RLIPv2_VLFuse
+    fuse = det_fill_(RLIPv2_VLFuse(_args(device)), seed=seed).to(device)
+    fuse.b_attn.attn._rlipv2_salt = 0x101
+    return fuse
+
+
+def _inputs(device, B=2, Tv=37, Tl=19, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    v = torch.randn(B, Tv, 256, generator=g).to(device)
+    l = torch.randn(B, Tl, 768, generator=g).to(device)
+    pos = torch.randn(B, Tv, 256, generator=g).to(device)
+    return v, l, pos
+
+
+def _run(block, v, l, pos, two_streams):
+    v = v.clone().requires_grad_(True)
+    l = l.clone().requires_grad_(True)
+    for p in block.parameters():
+        p.grad = None
+    b = block.b_attn
+    ov, ol = b._two_stream_call(v, l, pos) if two_streams else b.single_attention_call(v, l, pos)
+    ((ov * ov).sum() + (ol * ol).sum() * 0.5).backward()
+    grads = {n: p.grad.clone() for n, p in block.named_parameters() if p.grad is not None}
+    return ov.detach(), ol.detach(), v.grad.clone(), l.grad.clone(), grads
+
+
+def test_two_stream_wiring_equals_single_stream_cpu(monkeypatch):
+    import rlipv2_b200.alif as alif
+
+    class _Stream:
+        def wait_stream(self, other):
+            pass
+    monkeypatch.setattr(alif.streams, "get", lambda device, role: _Stream())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: _Stream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None)
+    from rlipv2_b200 import dense
+    dense.set_matmul_precision("fp32")
+    block = _block("cpu").eval()                    # eval: torch dropout would draw different masks per call order
+    v, l, pos = _inputs("cpu")
+    a = _run(block, v, l, pos, False)
+    b = _run(block, v, l, pos, True)
+    for x, y in zip(a[:4], b[:4]):
+        torch.testing.assert_close(y, x, rtol=1e-6, atol=1e-6)
+    assert a[4].keys() == b[4].keys() and len(a[4]) == 18
+    for n in a[4]:
+        torch.testing.assert_close(b[4][n], a[4][n], rtol=1e-5, atol=1e-6, msg=n)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_two_stream_equals_single_stream_training_gpu(mode):
+    from rlipv2_b200 import dense
+    try:
+        dense.set_matmul_precision(mode)
+        block = _block("cuda").train()
+        v, l, pos = _inputs("cuda", Tv=273, Tl=256)
+        if mode == "fp32":
+            block.eval()                            # torch dropout (fp32 path) is not call-order independent
+        a = _run(block, v, l, pos, False)
+        torch.cuda.synchronize()
+        for rep in range(3):                        # repeated: a missing dependency shows up as run-to-run differences
+            b = _run(block, v, l, pos, True)
+            torch.cuda.synchronize()
+            for x, y in zip(a[:4], b[:4]):
+                assert float((x - y).abs().max()) <= 2e-5 * float(x.abs().max()), rep
+            assert a[4].keys() == b[4].keys()
+            for n in a[4]:
+                assert float((a[4][n] - b[4][n]).abs().max()) <= 1e-4 * float(a[4][n].abs().max()) + 1e-12, (n, rep)
+    finally:
+        dense.set_matmul_precision("fp32")
+
+
+@pytest.mark.gpu
+def test_two_stream_block_matches_the_reference_fixture_gpu(monkeypatch):
+    import rlipv2_b200.alif as alif
+    from rlipv2_b200 import dense
+    monkeypatch.setattr(alif, "_ALIF_STREAMS", True)
+    g = _load("parseda_alif.npz")
+    t = lambda k: torch.from_numpy(g[k]).to("cuda")
+    try:
+        for mode, tol in (("fp32", 1e-4), ("tf32", 5e-3)):
+            dense.set_matmul_precision(mode)
+            fuse = det_fill_(alif.RLIPv2_VLFuse(_args("cuda")), seed=1).eval().to("cuda")
+            with torch.no_grad():
+                for rep in range(2):
+                    out = fuse({"visual": {"src": t("v"), "padding_mask": t("mask_v"), "pos": t("pos")},
+                                "lang": {"hidden": t("l"), "masks": t("mask_l")}})
+                    for a, key in ((out["visual"]["src"], "out_v"), (out["lang"]["hidden"], "out_l")):
+                        ref = g[key]
+                        assert float(np.abs(a.cpu().numpy() - ref).max()) <= tol * float(np.abs(ref).max()) + 1e-6, (mode, key)
+    finally:
+        dense.set_matmul_precision("fp32")

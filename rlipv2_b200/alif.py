@@ -36,7 +36,7 @@ from . import dense, streams
 # for the labels, then one attention direction + out-projection + gate each.  Every kernel in them is a few hundred rows -
 # latency-bound, 16-112 of 148 SMs busy - so the label chain runs on its own stream beside the image chain,
 # forward and (through autograd's stream bookkeeping) backward.  RLIPV2_ALIF_STREAMS=0/1 is the A/B switch.
-_ALIF_STREAMS = os.environ.get("RLIPV2_ALIF_STREAMS", "0") != "0"
+_ALIF_STREAMS = os.environ.get("RLIPV2_ALIF_STREAMS", "1") != "0"
 
 
 class FeatureResizer(nn.Module):

@@ -44,8 +44,18 @@ namespace {
 
 std::atomic<unsigned long long> g_launches{0};
 // backward of the fast path: 0 = one reduction per valid corner, 1 = corners of one pair that fall on the same cell merged
-// before they are issued (msda_merge.h); set through rlipv2_msda_set_backward_mode
-std::atomic<int> g_bwd_mode{0};
+// before they are issued (msda_merge.h), 2 = merged for encoder-shaped calls only; set through rlipv2_msda_set_backward_mode
+std::atomic<int> g_bwd_mode{2};
+constexpr int kMergeMinQueries = 8192;
+
+// Measured on B200 (profiles/msda_r02.md, r02u): merging pays where a pair's points cluster - the encoder's self-attention,
+// one query per cell sampling around itself (481.8 -> 387.9 us with the initialisation's offsets, 472 -> 460 us with a cell of
+// noise on top) - and costs 4 % on decoder-shaped calls (a few hundred queries, learned far-apart points: nothing merges and
+// the kernel is DRAM-latency-bound).  The same query-count test selects the forward's variant.
+inline bool use_merged_backward(int NQ) {
+    const int mode = g_bwd_mode.load(std::memory_order_relaxed);
+    return mode == 1 || (mode == 2 && NQ >= kMergeMinQueries);
+}
 
 constexpr int kFastD = 32;
 constexpr int kFastL = 4;
@@ -829,7 +839,7 @@ int backward_impl(const T *value, const int64_t *shapes, const int64_t *lsi, con
     if (allow_fast) {
         const int NQ = batch * num_query;
         const dim3 grid = fast_grid(NQ, num_heads);
-        if (g_bwd_mode.load(std::memory_order_relaxed) == 1)
+        if (use_merged_backward(NQ))
             msda_bwd_d32_l4p4<2, 0, 1><<<grid, kThreads, 0, stream>>>(
                 (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn,
                 (const float *)grad_out, NQ, num_query, spatial_size, num_heads, (float *)grad_value,
@@ -901,7 +911,7 @@ int proj_backward_impl(const float *value, const int64_t *shapes, const int64_t 
     if (!value || !shapes || !lsi || !ref || !proj || !grad_out || !grad_proj) return RLIPV2_MSDA_EINVAL;
     if (!aligned16(value, ref, proj, grad_out, grad_value, grad_proj)) return RLIPV2_MSDA_EALIGN;
     const dim3 grid = fast_grid(NQ, num_heads);
-    const bool merge = g_bwd_mode.load(std::memory_order_relaxed) == 1;
+    const bool merge = use_merged_backward(NQ);
     if (ref_dim == 4) {
         if (merge)
             msda_bwd_d32_l4p4<2, 2, 1><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, proj, ref, grad_out, NQ, num_query,
@@ -1090,7 +1100,7 @@ int rlipv2_msda_abi_version(void) { return RLIPV2_MSDA_ABI_VERSION; }
 
 int rlipv2_msda_set_backward_mode(int mode)
 {
-    if (mode != 0 && mode != 1) return RLIPV2_MSDA_EINVAL;
+    if (mode < 0 || mode > 2) return RLIPV2_MSDA_EINVAL;
     g_bwd_mode.store(mode, std::memory_order_relaxed);
     return 0;
 }

@@ -60,16 +60,14 @@ def library_path():
 
 
 def set_backward_mode(mode):
-    """0 = one reduction per valid corner, 1 = same-cell corners of a pair merged before issue (include/rlipv2_msda.h)"""
+    """0 = one reduction per valid corner, 1 = same-cell corners of a pair merged before issue, 2 (the library's default) =
+    merged for encoder-shaped calls only (include/rlipv2_msda.h)"""
     _check(_lib.rlipv2_msda_set_backward_mode(int(mode)), "rlipv2_msda_set_backward_mode")
 
 
 def get_backward_mode():
     return int(_lib.rlipv2_msda_get_backward_mode())
 
-
-if os.environ.get("RLIPV2_MSDA_BWD_MERGE"):                            # A/B switch for measurements
-    set_backward_mode(int(os.environ["RLIPV2_MSDA_BWD_MERGE"]))
 
 
 def launch_count():
@@ -152,3 +150,7 @@ def proj_backward(value, spatial_shapes, level_start_index, reference_points, pr
             proj.data_ptr(), grad_output.data_ptr(), N, S, M, D, 4, Lq, 4, grad_value.data_ptr(),
             grad_proj.data_ptr(), _stream())
     _check(code, "msda_proj_backward")
+
+
+if os.environ.get("RLIPV2_MSDA_BWD_MERGE"):                            # A/B switch for measurements (0 / 1 / 2)
+    set_backward_mode(int(os.environ["RLIPV2_MSDA_BWD_MERGE"]))

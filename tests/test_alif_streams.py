@@ -78,11 +78,17 @@ def test_two_stream_equals_single_stream_training_gpu(mode):
         for rep in range(3):                        # repeated: a missing dependency shows up as run-to-run differences
             b = _run(block, v, l, pos, True)
             torch.cuda.synchronize()
+            # fp32: the same deterministic kernels in another issue order.  tf32: the split-K projections add their partial
+            # sums with atomics, and that reordering (1e-6) passes through two softmaxes - measured 2e-5 of the scale
+            # (r02u); a missing dependency would show as O(1) garbage
+            tol = 2e-5 if mode == "fp32" else 3e-4
             for x, y in zip(a[:4], b[:4]):
-                assert float((x - y).abs().max()) <= 2e-5 * float(x.abs().max()), rep
+                assert float((x - y).abs().max()) <= tol * float(x.abs().max()), rep
             assert a[4].keys() == b[4].keys()
             for n in a[4]:
-                assert float((a[4][n] - b[4][n]).abs().max()) <= 1e-4 * float(a[4][n].abs().max()) + 1e-12, (n, rep)
+                # the VXAc gate's gamma[0] receives ONE sum of ~1e5 signed terms (cancellation): looser
+                gtol = 5e-2 if "gamma" in n else 10 * tol
+                assert float((a[4][n] - b[4][n]).abs().max()) <= gtol * float(a[4][n].abs().max()) + 1e-12, (n, rep)
     finally:
         dense.set_matmul_precision("fp32")
 

@@ -193,3 +193,16 @@ def test_merged_grad_value_on_the_reference_fixture(shim):
                                N, S, M, Lq, got.ctypes.data)
     ref = g["grad_value"].astype(np.float64)
     assert np.abs(got - ref).max() <= 3e-6 * np.abs(ref).max()
+
+
+def test_mode_switch_and_env_variable_without_a_gpu():
+    """the schedule switch is host state of the library: default 2 (merged for encoder-shaped calls), RLIPV2_MSDA_BWD_MERGE
+    sets it at import (r02u: the switch was read before the module had defined its error check)"""
+    import sys
+    code = "from rlipv2_b200 import msda_abi; print(msda_abi.get_backward_mode())"
+    for env, want in (({}, "2"), ({"RLIPV2_MSDA_BWD_MERGE": "0"}, "0"), ({"RLIPV2_MSDA_BWD_MERGE": "1"}, "1")):
+        e = {k: v for k, v in os.environ.items() if k != "RLIPV2_MSDA_BWD_MERGE"}
+        e.update(env)
+        out = subprocess.run([sys.executable, "-c", code], env=e, cwd=ROOT, capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr[-500:]
+        assert out.stdout.strip().splitlines()[-1] == want

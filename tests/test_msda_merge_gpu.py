@@ -47,6 +47,8 @@ def test_mode_switch_round_trip(modes):
     assert msda_abi.get_backward_mode() == 1
     modes(0)
     assert msda_abi.get_backward_mode() == 0
+    modes(2)
+    assert msda_abi.get_backward_mode() == 2
     with pytest.raises(RuntimeError):
         msda_abi.set_backward_mode(7)
 
@@ -108,7 +110,8 @@ def test_merged_against_oracle_and_unmerged(cfg, modes):
     assert float(np.abs(gv1.cpu().numpy() - rgv).max()) <= 1e-4 * scale
     assert float((gv1 - gv0).abs().max()) <= 2e-5 * scale
     assert _same(gl1, gl0) and _same(ga1, ga0)
-    np.testing.assert_allclose(ga1.cpu().numpy(), rga, rtol=1e-4, atol=1e-5)
+    # (grad_attn / grad_loc do not depend on the mode - checked above - and are sums with cancellation: tolerance of their scale)
+    np.testing.assert_allclose(ga1.cpu().numpy(), rga, rtol=1e-4, atol=1e-5 * float(np.abs(rga).max()))
     np.testing.assert_allclose(gl1.cpu().numpy(), rgl, rtol=1e-3, atol=1e-3 * float(np.abs(rgl).max()))
 
 

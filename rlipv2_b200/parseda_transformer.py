@@ -34,7 +34,7 @@ from .alif import FeatureResizer, RLIPv2_VLFuse
 from .ms_deform_attn import MSDeformAttn
 from .nested import inverse_sigmoid
 from .roberta_layer import RobertaLayer
-from .text_encoder import build_text_encoder, pooled_text
+from .text_encoder import build_text_encoder, pooled_text, pooled_text_sharded
 
 
 _LEVEL_CACHE = {}
@@ -546,6 +546,15 @@ class RLIP_ParSeDABDeformableTransformer_v2(nn.Module):
         self.verb_query_tgt_type = args.verb_query_tgt_type
         if "MBF" in self.verb_query_tgt_type:
             self.verb_tgt_generator = MultiBranchFusion(256, 256, 256, 16)
+        self.shard_labels, self.label_shard_group = False, None
+
+    def shard_label_text(self, enabled=True, group=None):
+        """SURVEY 8f rank 3 (label set de-duplicated across ranks): when EVERY rank passes the same label strings to every
+        step - fine-tuning on a dataset's fixed object / relation vocabulary - each rank runs the text tower on 1 / world of
+        them and the pooled vectors are all-gathered (text_encoder.pooled_text_sharded).  The caller owns that promise; label
+        sets that differ per rank (relational pre-training with per-batch negatives, engine.py:92-98) must leave this off."""
+        self.shard_labels, self.label_shard_group = bool(enabled), group
+        return self
 
     def _reset_parameters(self):
         # xavier on every matrix built so far - including the RobertaLayers / ALIF blocks, but not the
@@ -585,7 +594,11 @@ class RLIP_ParSeDABDeformableTransformer_v2(nn.Module):
         tok = text if isinstance(text, dict) else self.tokenize(text, device)
         sums = tok["sums"]
         obj_pred_names_sums = torch.tensor(sums)
-        pooled = pooled_text(self.text_encoder, tok["input_ids"], tok["attention_mask"])
+        if getattr(self, "shard_labels", False):
+            # every rank was promised the same label set: encode 1 / world of it here (text_encoder.pooled_text_sharded)
+            pooled = pooled_text_sharded(self.text_encoder, tok["input_ids"], tok["attention_mask"], self.label_shard_group)
+        else:
+            pooled = pooled_text(self.text_encoder, tok["input_ids"], tok["attention_mask"])
         pooled = grad_ready.mark(pooled, "text")         # no-op unless the data-parallel step installed a callback
         i, objs, preds = 0, [], []
         for n_obj, n_pred in sums:

@@ -89,6 +89,64 @@ def pooled_text(text_encoder, input_ids, attention_mask):
     return te(input_ids=input_ids, attention_mask=attention_mask).pooler_output
 
 
+# ---- one label set, many ranks: each rank encodes 1 / world of the strings -----------------------------------------
+class _GatherRows(torch.autograd.Function):
+    """x [rows, C] on every rank -> the ranks' blocks stacked [world * rows, C]; the backward hands every rank the SUM over
+    ranks of the gradient of its own block (the label embeddings feed every rank's loss)."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        import torch.distributed as dist
+        ctx.group = group
+        world = dist.get_world_size(group)
+        x = x.contiguous()
+        out = x.new_empty((world * x.shape[0],) + tuple(x.shape[1:]))
+        if dist.get_backend(group) == "gloo":                      # CPU tests: no all_gather_into_tensor / reduce-scatter
+            parts = list(out.chunk(world, 0))
+            dist.all_gather(parts, x, group=group)
+        else:
+            dist.all_gather_into_tensor(out, x, group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(ctx.group), dist.get_rank(ctx.group)
+        g = g.contiguous()
+        rows = g.shape[0] // world
+        if dist.get_backend(ctx.group) == "gloo":
+            g = g.clone()
+            dist.all_reduce(g, group=ctx.group)
+            return g[rank * rows:(rank + 1) * rows].clone(), None
+        mine = g.new_empty((rows,) + tuple(g.shape[1:]))
+        dist.reduce_scatter_tensor(mine, g, group=ctx.group)
+        return mine, None
+
+
+def pooled_text_sharded(text_encoder, input_ids, attention_mask, group=None):
+    """`pooled_text` for a label set that is THE SAME on every rank of `group` (fine-tuning on a fixed vocabulary: every
+    rank tokenises the same object + relation names each step, dab_deformable/deformable_transformer.py:489-502, and runs
+    the 12-layer tower on all of them).  Rank r encodes rows [r * n, (r + 1) * n) of the (padded) token matrix, the pooled
+    vectors are all-gathered; in the backward every rank receives the rank-sum of the gradient of its rows, so that after
+    the step's gradient averaging the tower's parameter gradients equal the data-parallel ones (both are
+    1 / world * sum over ranks and labels).  Dropout inside the tower is then drawn once per label instead of once per
+    label and rank.  Falls back to `pooled_text` without an initialised process group or with one rank."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return pooled_text(text_encoder, input_ids, attention_mask)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = input_ids.shape[0]
+    per = (n + world - 1) // world
+    lo = min(rank * per, n)
+    ids, mask = input_ids[lo:lo + per], attention_mask[lo:lo + per]
+    if ids.shape[0] < per:                                         # ragged tail: pad with copies of the first string
+        fill = per - ids.shape[0]
+        ids = torch.cat((ids, input_ids[:1].expand(fill, -1)), 0)
+        mask = torch.cat((mask, attention_mask[:1].expand(fill, -1)), 0)
+    mine = pooled_text(text_encoder, ids, mask)
+    return _GatherRows.apply(mine, group)[:n]
+
+
 # ---- short-sequence attention for the label strings (csrc/fused_ops.cu short_attn_*) --------------------------------
 _SHORT_ATTN = os.environ.get("RLIPV2_SHORT_ATTN", "1") != "0"
 _ATTN_KEY = "rlipv2_short"

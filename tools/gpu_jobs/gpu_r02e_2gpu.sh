@@ -1,7 +1,7 @@
 #!/bin/bash
 # N-GPU A/B of the data-parallel step variants: one all-reduce behind the backward (round 1), sharded optimizer step
 # (reduce-scatter + 1/N AdamW + all-gather; the round-2 default), marker-driven overlapped all-reduce.  Each run under its own
-# timeout so that a collective-order bug cannot hang the box.     gpurun --gpus 2 --timeout 1200 -- 'bash tools/gpu_r02e_2gpu.sh r02e 2'
+# timeout so that a collective-order bug cannot hang the box.     gpurun --gpus 2 --timeout 1200 -- 'bash tools/gpu_jobs/gpu_r02e_2gpu.sh r02e 2'
 TAG=${1:-r02e}
 N=${2:-2}
 mkdir -p gpurun_out

@@ -144,8 +144,10 @@ int rlipv2_msda_abi_version(void);
  *   1  corners of one (image, query, head) that fall on the same cell of a level are merged before they are issued
  *      (every contribution is a scalar times the pair's grad_out row, so the scalars add), and corners whose merged scalar
  *      is exactly zero are not issued.  Same sums as mode 0 up to fp32 rounding order (rlipv2_b200/csrc/msda_merge.h);
- *   2  (default) mode 1 for calls with at least 8192 (image, query) rows - the encoder's self-attention, whose points
- *      cluster around the query's own cell - and mode 0 for the rest (decoder-shaped calls: nothing merges, 4 % slower).
+ *   2  (default) by call shape: mode 1 for calls with at least 8192 (image, query) rows - the encoder's self-attention, whose
+ *      points cluster around the query's own cell; for the rest (decoder-shaped calls: nothing merges, DRAM-latency-bound) the
+ *      unmerged schedule, which rlipv2_msda_backward_f32 then runs at 3 CTAs per SM instead of 2 (same source, 80 registers);
+ *   3 / 4  measurement only: the merged / unmerged schedule of rlipv2_msda_backward_f32 forced to 3 CTAs per SM.
  * Returns 0, or RLIPV2_MSDA_EINVAL for another mode. */
 int rlipv2_msda_set_backward_mode(int mode);
 int rlipv2_msda_get_backward_mode(void);

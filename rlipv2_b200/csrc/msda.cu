@@ -43,8 +43,10 @@
 namespace {
 
 std::atomic<unsigned long long> g_launches{0};
-// backward of the fast path: 0 = one reduction per valid corner, 1 = corners of one pair that fall on the same cell merged
-// before they are issued (msda_merge.h), 2 = merged for encoder-shaped calls only; set through rlipv2_msda_set_backward_mode
+// backward of the fast path: 0 = one reduction per valid corner, 2 CTAs per SM (round 1's kernel), 1 = corners of one pair that
+// fall on the same cell merged before they are issued (msda_merge.h), 2 = by call shape: merged for encoder-shaped calls,
+// unmerged at 3 CTAs per SM for the plain op's decoder-shaped calls; 3 / 4 = the two 3-CTA variants forced (measurements);
+// set through rlipv2_msda_set_backward_mode
 std::atomic<int> g_bwd_mode{2};
 constexpr int kMergeMinQueries = 8192;
 
@@ -839,16 +841,24 @@ int backward_impl(const T *value, const int64_t *shapes, const int64_t *lsi, con
     if (allow_fast) {
         const int NQ = batch * num_query;
         const dim3 grid = fast_grid(NQ, num_heads);
-        if (use_merged_backward(NQ))
-            msda_bwd_d32_l4p4<2, 0, 1><<<grid, kThreads, 0, stream>>>(
-                (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn,
-                (const float *)grad_out, NQ, num_query, spatial_size, num_heads, (float *)grad_value,
-                (float *)grad_loc, (float *)grad_attn);
+        const int mode = g_bwd_mode.load(std::memory_order_relaxed);
+        const float *v = (const float *)value, *l = (const float *)loc, *a = (const float *)attn, *g = (const float *)grad_out;
+        float *gv = (float *)grad_value, *gl = (float *)grad_loc, *ga = (float *)grad_attn;
+        if (mode == 3)                                    // experiment: merged at 80 registers, 3 CTAs per SM
+            msda_bwd_d32_l4p4<3, 0, 1><<<grid, kThreads, 0, stream>>>(v, shapes, lsi, l, a, g, NQ, num_query, spatial_size,
+                                                                       num_heads, gv, gl, ga);
+        else if (use_merged_backward(NQ))
+            msda_bwd_d32_l4p4<2, 0, 1><<<grid, kThreads, 0, stream>>>(v, shapes, lsi, l, a, g, NQ, num_query, spatial_size,
+                                                                       num_heads, gv, gl, ga);
+        else if (mode == 4 || (mode == 2 && NQ < kMergeMinQueries))
+            // decoder-shaped calls scatter over the whole value map and wait on DRAM: 3 CTAs per SM (80 registers, the same
+            // source) hide more of that latency - config 5 backward 142.5 -> 129.7 us (r02w); on the encoder call the
+            // lower register budget costs 10 % (474 -> 518 us), so mode 2 uses it below kMergeMinQueries only
+            msda_bwd_d32_l4p4<3, 0, 0><<<grid, kThreads, 0, stream>>>(v, shapes, lsi, l, a, g, NQ, num_query, spatial_size,
+                                                                       num_heads, gv, gl, ga);
         else
-            msda_bwd_d32_l4p4<2><<<grid, kThreads, 0, stream>>>(
-                (const float *)value, shapes, lsi, (const float *)loc, (const float *)attn,
-                (const float *)grad_out, NQ, num_query, spatial_size, num_heads, (float *)grad_value,
-                (float *)grad_loc, (float *)grad_attn);
+            msda_bwd_d32_l4p4<2><<<grid, kThreads, 0, stream>>>(v, shapes, lsi, l, a, g, NQ, num_query, spatial_size,
+                                                                 num_heads, gv, gl, ga);
     } else {
         msda_bwd_generic<T><<<grid_for(pairs * 32, 256), 256, 0, stream>>>(
             value, shapes, lsi, loc, attn, grad_out, pairs, num_query, spatial_size, num_heads,
@@ -1100,7 +1110,7 @@ int rlipv2_msda_abi_version(void) { return RLIPV2_MSDA_ABI_VERSION; }
 
 int rlipv2_msda_set_backward_mode(int mode)
 {
-    if (mode < 0 || mode > 2) return RLIPV2_MSDA_EINVAL;
+    if (mode < 0 || mode > 4) return RLIPV2_MSDA_EINVAL;
     g_bwd_mode.store(mode, std::memory_order_relaxed);
     return 0;
 }

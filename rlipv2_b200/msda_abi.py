@@ -61,7 +61,7 @@ def library_path():
 
 def set_backward_mode(mode):
     """0 = one reduction per valid corner, 1 = same-cell corners of a pair merged before issue, 2 (the library's default) =
-    merged for encoder-shaped calls only (include/rlipv2_msda.h)"""
+    chosen by call shape, 3 / 4 = measurement variants (include/rlipv2_msda.h)"""
     _check(_lib.rlipv2_msda_set_backward_mode(int(mode)), "rlipv2_msda_set_backward_mode")
 
 

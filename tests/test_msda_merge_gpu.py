@@ -47,8 +47,9 @@ def test_mode_switch_round_trip(modes):
     assert msda_abi.get_backward_mode() == 1
     modes(0)
     assert msda_abi.get_backward_mode() == 0
-    modes(2)
-    assert msda_abi.get_backward_mode() == 2
+    for m in (2, 3, 4):
+        modes(m)
+        assert msda_abi.get_backward_mode() == m
     with pytest.raises(RuntimeError):
         msda_abi.set_backward_mode(7)
 
@@ -112,7 +113,31 @@ def test_merged_against_oracle_and_unmerged(cfg, modes):
     assert _same(gl1, gl0) and _same(ga1, ga0)
     # (grad_attn / grad_loc do not depend on the mode - checked above - and are sums with cancellation: tolerance of their scale)
     np.testing.assert_allclose(ga1.cpu().numpy(), rga, rtol=1e-4, atol=1e-5 * float(np.abs(rga).max()))
-    np.testing.assert_allclose(gl1.cpu().numpy(), rgl, rtol=1e-3, atol=1e-3 * float(np.abs(rgl).max()))
+    if noise > 0.0:
+        # (on exact cell centres floor() of the sample position is decided by the last bit of `loc * W - 0.5` - fused on the
+        # device, two roundings in the host oracle - and grad_loc, unlike the output and grad_value, is discontinuous there)
+        np.testing.assert_allclose(gl1.cpu().numpy(), rgl, rtol=1e-3, atol=1e-3 * float(np.abs(rgl).max()))
+
+
+@pytest.mark.parametrize("mode", [2, 3, 4])
+def test_call_shape_mode_and_three_cta_variants_equal_mode0(mode, modes):
+    """mode 2 runs decoder-shaped calls of the plain op on the 3-CTA-per-SM instantiation of the unmerged kernel and
+    encoder-shaped calls on the merged one; 3 / 4 force the 3-CTA variants: same sums as mode 0 in every case"""
+    from rlipv2_b200 import synth
+    for args in (synth.random_inputs(2, 300, synth.LEVELS_MICRO, seed=3),
+                 _dev_tuple(_clustered(3, 77, 8, [(25, 42), (13, 21), (7, 11), (4, 6)], seed=5, noise=0.3, lo=-0.2, hi=1.2)),
+                 synth.encoder_inputs(1, [(70, 100), (35, 50), (18, 25), (9, 13)], seed=2, noise_px=0.5)):     # NQ = 9392
+        run = lambda: _msda().ms_deform_attn_backward(*args[:5], args[5], 64)
+        modes(0)
+        gv0, gl0, ga0 = run()
+        modes(mode)
+        gv1, gl1, ga1 = run()
+        assert float((gv1 - gv0).abs().max()) <= 2e-5 * float(gv0.abs().max())
+        assert _same(gl1, gl0) and _same(ga1, ga0)
+
+
+def _dev_tuple(t):
+    return tuple(x.cuda().contiguous() for x in t)
 
 
 def test_merged_random_locations_equal_unmerged(modes):

@@ -63,6 +63,12 @@ class ParSeDATrainStep:
         self.model = model.to(self.device).train()
         self.criterion = criterion.to(self.device).train()
         self.module = self.model
+        if (os.environ.get("RLIPV2_SHARD_LABELS", "0") == "1" and dist.is_available() and dist.is_initialized()
+                and dist.get_world_size() > 1 and hasattr(self.module.transformer, "shard_label_text")):
+            # opt-in, for runs whose label text is THE SAME on every rank (fine-tuning on a fixed vocabulary): each rank
+            # runs the text tower on 1 / world of the strings (text_encoder.pooled_text_sharded; checked on two gloo ranks,
+            # not yet run under NCCL inside the captured graphs)
+            self.module.transformer.shard_label_text(True)
         # NB: channels_last (NHWC) for the backbone was measured and dropped: it removes cuDNN's
         # nchwToNhwc/nhwcToNchw pairs (1.7 ms) but the frozen-BN / GroupNorm elementwise kernels get
         # slower by more than that (52.1 vs 50.3 ms per step).
